@@ -1,0 +1,285 @@
+"""Phase-1 (powers of tau) chunk contribution and verification, restated.
+
+Test infrastructure (see oracle/__init__.py).  Follows the call sites of the
+reference — `phase1_cli::contribute` at src/bin/contribute.rs:809-824,
+`phase1_cli::transform_pok_and_correctness` at src/bin/contribute.rs:966-987 and
+src/bin/verify_transcript.rs:465-484, `setup_utils::calculate_hash` at
+src/utils.rs:618-623 — and the upstream algorithm as recorded in SURVEY.md §3 (A),
+§8a rows a2-a6 and Appendix A.3/A.4 ([UP]: `phase1`, `setup-utils` crates of
+nimiq/snark-setup rev bd530da, not on disk).
+
+Algorithm restated (per element, no batching tricks):
+    generate_powers_of_tau : tau^i by an independent `pow` per index          (K1)
+    batch_exp              : out[i] = (coeff * tau^i) * in[i], double-and-add (K2)
+    read_batch/write_batch : arkworks byte formats, oracle/serialize.py       (K3/K4)
+"""
+from __future__ import annotations
+
+import hashlib
+from dataclasses import dataclass
+
+from . import serialize as ser
+from .chacha import ChaChaRng, field_rand, fp_rand, group_rand
+from .curves import Curve, Group
+from .params import HASH_SIZE, Phase1Params
+
+
+def calculate_hash(data: bytes) -> bytes:
+    """setup_utils::calculate_hash = Blake2b-512, unkeyed (src/utils.rs:618-623)."""
+    return hashlib.blake2b(data, digest_size=64).digest()
+
+
+def blank_hash() -> bytes:
+    return calculate_hash(b"")
+
+
+# ---------------------------------------------------------------------------------------------
+# keys
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class PrivateKey:
+    tau: int
+    alpha: int
+    beta: int
+
+
+@dataclass
+class PublicKey:
+    tau_g1: tuple      # (g1_s, g1_s_x)
+    alpha_g1: tuple
+    beta_g1: tuple
+    tau_g2: object
+    alpha_g2: object
+    beta_g2: object
+
+    def to_bytes(self, curve: Curve) -> bytes:
+        g1, g2 = curve.g1, curve.g2
+        out = b""
+        for pair in (self.tau_g1, self.alpha_g1, self.beta_g1):
+            out += ser.point_to_bytes(g1, pair[0], False) + ser.point_to_bytes(g1, pair[1], False)
+        for p in (self.tau_g2, self.alpha_g2, self.beta_g2):
+            out += ser.point_to_bytes(g2, p, False)
+        return out
+
+    @staticmethod
+    def from_bytes(curve: Curve, buf: bytes) -> "PublicKey":
+        g1, g2 = curve.g1, curve.g2
+        s1, s2 = ser.point_size(g1, False), ser.point_size(g2, False)
+        assert len(buf) == 6 * s1 + 3 * s2
+        p1 = [ser.point_from_bytes(g1, buf[i * s1:(i + 1) * s1], False) for i in range(6)]
+        o = 6 * s1
+        p2 = [ser.point_from_bytes(g2, buf[o + i * s2:o + (i + 1) * s2], False) for i in range(3)]
+        return PublicKey((p1[0], p1[1]), (p1[2], p1[3]), (p1[4], p1[5]), p2[0], p2[1], p2[2])
+
+
+def hash_to_g2(curve: Curve, digest: bytes):
+    """[UP] setup_utils::hash_to_g2: ChaCha20 seeded with digest[..32], then `G2::rand`.
+    Highest-risk item for byte parity of the pubkey block; it does not
+    touch the accumulator bytes."""
+    return group_rand(curve.g2, ChaChaRng(digest[:32]))
+
+
+def compute_g2_s(curve: Curve, digest: bytes, g1_s, g1_s_x, personalization: int):
+    """[UP] setup_utils::compute_g2_s: Blake2b-512(personalization || digest || g1_s || g1_s_x)
+    with both points in uncompressed form, then hash_to_g2."""
+    h = hashlib.blake2b(digest_size=64)
+    h.update(bytes([personalization]))
+    h.update(digest)
+    h.update(ser.point_to_bytes(curve.g1, g1_s, False))
+    h.update(ser.point_to_bytes(curve.g1, g1_s_x, False))
+    return hash_to_g2(curve, h.digest())
+
+
+def key_generation(curve: Curve, rng: ChaChaRng, digest: bytes):
+    """[UP] Phase1::key_generation: tau, alpha, beta <- Fr::rand (in that order), then for
+    each of them (personalization 0, 1, 2) a proof of knowledge."""
+    Fr = curve.Fr
+    tau, alpha, beta = fp_rand(Fr, rng), fp_rand(Fr, rng), fp_rand(Fr, rng)
+
+    def op(x: int, pers: int):
+        g1_s = group_rand(curve.g1, rng)
+        g1_s_x = curve.g1.mul(g1_s, x)
+        g2_s = compute_g2_s(curve, digest, g1_s, g1_s_x, pers)
+        g2_s_x = curve.g2.mul(g2_s, x)
+        return (g1_s, g1_s_x), g2_s_x
+
+    pk_tau = op(tau, 0)
+    pk_alpha = op(alpha, 1)
+    pk_beta = op(beta, 2)
+    pub = PublicKey(pk_tau[0], pk_alpha[0], pk_beta[0], pk_tau[1], pk_alpha[1], pk_beta[1])
+    return pub, PrivateKey(tau, alpha, beta)
+
+
+# ---------------------------------------------------------------------------------------------
+# chunk files
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class ChunkVectors:
+    tau_g1: list
+    tau_g2: list
+    alpha_g1: list
+    beta_g1: list
+    beta_g2: object
+
+
+def split_chunk(params: Phase1Params, buf: bytes, compressed: bool):
+    """-> (hash64, raw byte slices of the five vectors)"""
+    o1, o2, oa, ob, o5, end = params.offsets(compressed)
+    return buf[:HASH_SIZE], (buf[o1:o2], buf[o2:oa], buf[oa:ob], buf[ob:o5], buf[o5:end])
+
+
+def read_chunk(params: Phase1Params, buf: bytes, compressed: bool) -> ChunkVectors:
+    c = params.curve
+    _, (b1, b2, ba, bb, b5) = split_chunk(params, buf, compressed)
+    return ChunkVectors(ser.points_from_bytes(c.g1, b1, compressed),
+                        ser.points_from_bytes(c.g2, b2, compressed),
+                        ser.points_from_bytes(c.g1, ba, compressed),
+                        ser.points_from_bytes(c.g1, bb, compressed),
+                        ser.point_from_bytes(c.g2, b5, compressed))
+
+
+def write_chunk(params: Phase1Params, head: bytes, v: ChunkVectors, compressed: bool) -> bytes:
+    c = params.curve
+    assert len(head) == HASH_SIZE
+    return (head + ser.points_to_bytes(c.g1, v.tau_g1, compressed)
+            + ser.points_to_bytes(c.g2, v.tau_g2, compressed)
+            + ser.points_to_bytes(c.g1, v.alpha_g1, compressed)
+            + ser.points_to_bytes(c.g1, v.beta_g1, compressed)
+            + ser.point_to_bytes(c.g2, v.beta_g2, compressed))
+
+
+def new_challenge(params: Phase1Params) -> bytes:
+    """phase1_cli::new_challenge (src/bin/new_setup.rs:105-109): every element = generator,
+    hash slot = Blake2b-512 of the empty string."""
+    c = params.curve
+    v = ChunkVectors([c.g1.gen] * params.g1_count, [c.g2.gen] * params.other_count,
+                     [c.g1.gen] * params.other_count, [c.g1.gen] * params.other_count, c.g2.gen)
+    return write_chunk(params, blank_hash(), v, False)
+
+
+# ---------------------------------------------------------------------------------------------
+# contribution
+# ---------------------------------------------------------------------------------------------
+def generate_powers_of_tau(Fr, tau: int, start: int, end: int):
+    return [pow(tau, i, Fr.p) for i in range(start, end)]
+
+
+def batch_exp(G: Group, Fr, bases, exps, coeff=None):
+    out = []
+    for P, e in zip(bases, exps):
+        k = e if coeff is None else e * coeff % Fr.p
+        out.append(G.mul(P, k))
+    return out
+
+
+def computation(params: Phase1Params, vin: ChunkVectors, key: PrivateKey) -> ChunkVectors:
+    """Phase1::computation on the parsed vectors of one chunk."""
+    c = params.curve
+    Fr = c.Fr
+    s = params.start
+    tau_pows_g1 = generate_powers_of_tau(Fr, key.tau, s, s + params.g1_count)
+    tau_pows = tau_pows_g1[:params.other_count]
+    return ChunkVectors(
+        batch_exp(c.g1, Fr, vin.tau_g1, tau_pows_g1),
+        batch_exp(c.g2, Fr, vin.tau_g2, tau_pows),
+        batch_exp(c.g1, Fr, vin.alpha_g1, tau_pows, key.alpha),
+        batch_exp(c.g1, Fr, vin.beta_g1, tau_pows, key.beta),
+        c.g2.mul(vin.beta_g2, key.beta))
+
+
+def contribute_with_key(params: Phase1Params, challenge: bytes, key: PrivateKey, pubkey_bytes: bytes) -> bytes:
+    """The RNG-free core of phase1_cli::contribute: challenge (uncompressed) -> response
+    (compressed || pubkey), response[0..64] = Blake2b(challenge)."""
+    assert len(challenge) == params.accumulator_size, "challenge has the wrong size"
+    vin = read_chunk(params, challenge, False)
+    vout = computation(params, vin, key)
+    out = write_chunk(params, calculate_hash(challenge), vout, True) + pubkey_bytes
+    assert len(out) == params.contribution_size
+    return out
+
+
+def contribute(params: Phase1Params, challenge: bytes, rng: ChaChaRng):
+    """phase1_cli::contribute (src/bin/contribute.rs:811-823).
+    -> (response bytes, challenge_hash, response_hash)"""
+    ch_hash = calculate_hash(challenge)
+    pub, key = key_generation(params.curve, rng, ch_hash)
+    resp = contribute_with_key(params, challenge, key, pub.to_bytes(params.curve))
+    return resp, ch_hash, calculate_hash(resp)
+
+
+# ---------------------------------------------------------------------------------------------
+# verification building blocks
+# ---------------------------------------------------------------------------------------------
+CHECK_NO, CHECK_NONZERO, CHECK_FULL = 0, 1, 2            # CheckForCorrectness::{No, OnlyNonZero, Full}
+SUBGROUP_AUTO, SUBGROUP_DIRECT, SUBGROUP_BATCHED, SUBGROUP_NO = 0, 1, 2, 3
+
+
+class VerificationError(Exception):
+    pass
+
+
+def check_point(G: Group, P, check: int, subgroup: bool):
+    """What `read_batch` enforces per element after parsing."""
+    if check == CHECK_NO:
+        return
+    if P is None:
+        raise VerificationError("point at infinity")
+    if check == CHECK_FULL:
+        if not G.on_curve(P):
+            raise VerificationError("point not on curve")
+        if subgroup and G.mul(P, G.r) is not None:
+            raise VerificationError("point not in the prime-order subgroup")
+
+
+def power_pairs_with(G: Group, v, rs):
+    """power_pairs with caller-supplied randomness: (sum r_i v_i, sum r_i v_{i+1})."""
+    return G.msm(v[:-1], rs), G.msm(v[1:], rs)
+
+
+def merge_pairs_with(G: Group, v1, v2, rs):
+    return G.msm(v1, rs), G.msm(v2, rs)
+
+
+def same_ratio_dl(G1: Group, pair1, x: int) -> bool:
+    """Test-only stand-in for the pairing check when the harness knows the ratio x:
+    (a, b) has ratio x  <=>  b = x * a."""
+    a, b = pair1
+    return G1.eq(G1.mul(a, x), b)
+
+
+def decompress_response(params: Phase1Params, response: bytes) -> bytes:
+    """The re-encoding half of transform_pok_and_correctness: response vectors
+    (compressed) -> new challenge (uncompressed) whose hash slot is Blake2b(response)."""
+    body = response[:len(response) - params.public_key_size]
+    v = read_chunk(params, body, True)
+    return write_chunk(params, calculate_hash(response), v, False)
+
+
+def verify_chunk_with_key(params: Phase1Params, challenge: bytes, response: bytes, key: PrivateKey,
+                          check_out: int = CHECK_FULL, subgroup: bool = True) -> bytes:
+    """Chunk verification with the pairing checks replaced by knowledge of the contributor's
+    scalars (the harness made them): every output element must equal scalar * input element.
+    Returns the new challenge.  Verdict-equivalent to the ratio checks of
+    transform_pok_and_correctness on honest-or-corrupted outputs of a known key."""
+    c = params.curve
+    if len(response) != params.contribution_size:
+        raise VerificationError("response has the wrong size")
+    if response[:HASH_SIZE] != calculate_hash(challenge):
+        raise VerificationError("hash chain broken: response does not continue the challenge")
+    vin = read_chunk(params, challenge, False)
+    try:
+        vout = read_chunk(params, response[:len(response) - params.public_key_size], True)
+    except ser.FormatError as e:
+        raise VerificationError(str(e))
+    for G, pts in ((c.g1, vout.tau_g1), (c.g2, vout.tau_g2), (c.g1, vout.alpha_g1), (c.g1, vout.beta_g1),
+                   (c.g2, [vout.beta_g2])):
+        for P in pts:
+            check_point(G, P, check_out, subgroup)
+    want = computation(params, vin, key)
+    for G, a, b in ((c.g1, want.tau_g1, vout.tau_g1), (c.g2, want.tau_g2, vout.tau_g2),
+                    (c.g1, want.alpha_g1, vout.alpha_g1), (c.g1, want.beta_g1, vout.beta_g1),
+                    (c.g2, [want.beta_g2], [vout.beta_g2])):
+        for P, Q in zip(a, b):
+            if not G.eq(P, Q):
+                raise VerificationError("ratio check failed")
+    return write_chunk(params, calculate_hash(response), vout, False)
