@@ -1,0 +1,141 @@
+/* sso_b200 — C ABI of the B200-native compute core for the phase-1 / phase-2 hot path of
+ * nimiq/snark-setup-operator.
+ *
+ * Drop-in boundary: the operator's binaries call the Rust crates
+ *   phase1_cli::contribute                      reference src/bin/contribute.rs:811-823,
+ *                                               src/bin/verify_transcript.rs:678-696, src/bin/control.rs:793-808
+ *   phase1_cli::transform_pok_and_correctness   src/bin/contribute.rs:968-986, src/bin/verify_transcript.rs:466-484
+ *   phase1_cli::transform_ratios                src/bin/verify_transcript.rs:646-653, src/bin/control.rs:587-591
+ *   phase1_cli::combine / new_challenge         src/bin/verify_transcript.rs:603-607, src/bin/new_setup.rs:105-109
+ *   phase2_cli::contribute::<P>                 src/bin/contribute.rs:827-838
+ * with file names (or mmapped byte buffers underneath) as arguments and panic on failure.
+ * Every export below is what a Rust `-sys` crate (bindgen) binds in their place; INTEGRATION.md
+ * shows the shim.  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Conventions
+ *   - return value: 0 = ok, negative = error class (SSO_E_*); a human-readable message is
+ *     written to `err` (NUL-terminated, at most errcap bytes) — the Rust shim turns non-zero into
+ *     `panic!("{err}")`, which is the reference's error convention (src/bin/contribute.rs:842-856).
+ *   - a failed verification is an error return (SSO_E_VERIFY), not a separate boolean.
+ *   - scalars are canonical little-endian byte strings of the curve's Fr size (32/48/95/95).
+ *   - `_dev` entry points take DEVICE pointers (inputs already resident in HBM) and enqueue on
+ *     internal streams, returning after the work completed; `_buf` take HOST pointers and do
+ *     the copies themselves; `_file` take paths, mirroring the reference signatures.
+ *   - every call is re-entrant (own streams, stream-ordered scratch), so raising the
+ *     operator's --max-in-process-lane to the GPU count shards chunks with no other change.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry returns SSO_E_CUDA.
+ */
+#ifndef SSO_B200_H
+#define SSO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* curveKind (reference src/data_structs.rs:123-131; "bw6" default at src/bin/new_setup.rs:53-54) */
+enum { SSO_CURVE_BLS12_377 = 0, SSO_CURVE_BW6_761 = 1, SSO_CURVE_MNT4_753 = 2, SSO_CURVE_MNT6_753 = 3 };
+enum { SSO_G1 = 0, SSO_G2 = 1 };
+/* setup_utils::CheckForCorrectness (used at src/bin/contribute.rs:816-819, 971-980) */
+enum { SSO_CHECK_NO = 0, SSO_CHECK_NONZERO = 1, SSO_CHECK_FULL = 2 };
+/* setup_utils::SubgroupCheckMode (src/bin/contribute.rs:38-43; verify_transcript.rs:461-464) */
+enum { SSO_SUBGROUP_AUTO = 0, SSO_SUBGROUP_DIRECT = 1, SSO_SUBGROUP_BATCHED = 2, SSO_SUBGROUP_NO = 3 };
+/* setup_utils::BatchExpMode — accepted and ignored: outputs are mode-independent */
+enum { SSO_BATCHEXP_AUTO = 0, SSO_BATCHEXP_DIRECT = 1, SSO_BATCHEXP_BATCH_INVERSION = 2 };
+/* phase1::ContributionMode / ProvingSystem (src/utils.rs:326-352) */
+enum { SSO_MODE_CHUNKED = 0, SSO_MODE_FULL = 1 };
+enum { SSO_PROVING_GROTH16 = 0, SSO_PROVING_MARLIN = 1 };
+
+enum {
+  SSO_OK = 0,
+  SSO_E_ARG = -1,      /* invalid argument / size mismatch (the reference asserts file lengths) */
+  SSO_E_CUDA = -2,     /* CUDA runtime error or no device */
+  SSO_E_INPUT = -3,    /* input failed its correctness check (non-canonical, not on curve, zero, ...) */
+  SSO_E_VERIFY = -4,   /* verification verdict: reject */
+  SSO_E_IO = -5        /* file could not be read / created (outputs are created with O_EXCL) */
+};
+
+/* phase1::Phase1Parameters as built by create_parameters_for_chunk / create_full_parameters
+ * (reference src/utils.rs:326-352). */
+typedef struct {
+  uint32_t curve;
+  uint32_t proving_system;
+  uint32_t contribution_mode;
+  uint32_t power;
+  uint64_t chunk_index;
+  uint64_t chunk_size;
+  uint64_t batch_size;
+} sso_p1_params_t;
+
+/* indices into the array filled by sso_p1_sizes */
+enum {
+  SSO_SZ_POWERS_LENGTH = 0, SSO_SZ_POWERS_G1_LENGTH = 1, SSO_SZ_G1_COUNT = 2, SSO_SZ_OTHER_COUNT = 3,
+  SSO_SZ_ACCUMULATOR = 4,   /* challenge file size (uncompressed)          */
+  SSO_SZ_CONTRIBUTION = 5,  /* response file size (compressed + public key) */
+  SSO_SZ_PUBLIC_KEY = 6, SSO_SZ_NUM_CHUNKS = 7
+};
+
+const char* sso_version(void);
+/* number of usable CUDA devices (0 if none) */
+int32_t sso_device_count(void);
+/* name of device `device` (e.g. "NVIDIA B200") for ContributedData.processor_data (src/bin/contribute.rs:858-864) */
+int32_t sso_device_name(int device, char* out, size_t cap);
+
+/* Phase1Parameters size arithmetic (host only). Replaces the accumulator_size / contribution_size /
+ * powers_length fields read at reference src/utils.rs:526-532, src/bin/new_setup.rs:95-102, 265-277. */
+int32_t sso_p1_sizes(const sso_p1_params_t* p, uint64_t out[8], char* err, size_t errcap);
+/* serialized element sizes: out = {g1 compressed, g1 uncompressed, g2 compressed, g2 uncompressed, Fr bytes} */
+int32_t sso_curve_sizes(uint32_t curve, uint64_t out[5]);
+
+/* setup_utils::batch_exp on one vector (K1-K4): out[j] = (coeff * tau^(first_index + j)) * in[j].
+ * d_in / d_out are device pointers to n serialized points; coeff may be NULL (= 1). */
+int32_t sso_batch_exp_dev(uint32_t curve, uint32_t group, const void* d_in, uint32_t in_compressed, uint64_t n,
+                          uint64_t first_index, const uint8_t* tau, const uint8_t* coeff, void* d_out,
+                          uint32_t out_compressed, uint32_t check_input, int device, char* err, size_t errcap);
+
+/* phase-2 batch_mul (K7): out[j] = scalar * in[j] for one shared scalar (delta^-1 for the H / L queries,
+ * reference src/bin/contribute.rs:827-838). */
+int32_t sso_batch_mul_dev(uint32_t curve, uint32_t group, const void* d_in, uint32_t in_compressed, uint64_t n,
+                          const uint8_t* scalar, void* d_out, uint32_t out_compressed, uint32_t check_input,
+                          int device, char* err, size_t errcap);
+
+/* read_batch + write_batch alone: re-encode n points between the compressed and uncompressed formats
+ * with the correctness / subgroup checks of transform_pok_and_correctness and combine. */
+int32_t sso_reencode_dev(uint32_t curve, uint32_t group, const void* d_in, uint32_t in_compressed, uint64_t n,
+                         void* d_out, uint32_t out_compressed, uint32_t check, uint32_t subgroup_check,
+                         int device, char* err, size_t errcap);
+
+/* Phase1::computation for one chunk, device-resident: d_challenge holds the challenge file image
+ * (accumulator_size bytes, uncompressed), d_response receives the compressed vectors at their
+ * response-file offsets (contribution_size bytes; the 64-byte hash slot and the public key tail
+ * are left untouched for the host). */
+int32_t sso_p1_contribute_dev(const sso_p1_params_t* p, const void* d_challenge, void* d_response,
+                              const uint8_t* tau, const uint8_t* alpha, const uint8_t* beta,
+                              uint32_t check_input, int device, char* err, size_t errcap);
+
+/* The RNG-free core of phase1_cli::contribute on host buffers: copies the challenge to the device,
+ * computes, copies the response back, writes Blake2b-512(challenge) into response[0..64) and the
+ * caller-supplied serialized public key into the tail. */
+int32_t sso_p1_contribute_buf(const sso_p1_params_t* p, const uint8_t* challenge, size_t challenge_len,
+                              uint8_t* response, size_t response_len, const uint8_t* tau, const uint8_t* alpha,
+                              const uint8_t* beta, const uint8_t* pubkey, size_t pubkey_len, uint32_t check_input,
+                              int device, char* err, size_t errcap);
+
+/* setup_utils::calculate_hash (reference src/utils.rs:618-623): Blake2b-512, unkeyed. Host only. */
+int32_t sso_blake2b_512(const uint8_t* data, size_t len, uint8_t out[64]);
+
+/* Microbenchmark behind roofline.peak: dependent-free 32x32+64 multiply-accumulate chains on all SMs.
+ * Returns multiply-accumulates per second (SURVEY.md §8d "IMAD_peak is measured on the box"). */
+int32_t sso_imad_peak(int device, int variant, double* macs_per_s, char* err, size_t errcap);
+
+/* Test hook: elementwise field multiplication out[i] = a[i] * b[i] on the device, canonical
+ * little-endian elements of the field's serialized size. field: 0 r253, 1 q377, 2 q761, 3 q4(753), 4 q6(753). */
+int32_t sso_test_field_mul(uint32_t field, const uint8_t* a, const uint8_t* b, uint8_t* out, uint64_t n, int device,
+                           char* err, size_t errcap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSO_B200_H */

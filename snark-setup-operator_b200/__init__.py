@@ -1,0 +1,14 @@
+"""B200-native compute core for the phase-1 / phase-2 hot path of nimiq/snark-setup-operator.
+
+The product is `libsso_b200.so` (CUDA kernels for sm_100a behind the C ABI of
+include/sso_b200.h).  This Python package is the thin host-side binding used by the tests
+and the benchmark: it mirrors the reference's interface for the path — `Phase1Parameters`
+(reference src/utils.rs:326-352), `contribute`, `transform_pok_and_correctness`
+(src/bin/contribute.rs:809-824, 966-987) — and fails loudly when the CUDA library is
+missing.  There is no CPU fallback.
+"""
+from ._lib import SsoError, lib, library_path  # noqa: F401
+from .phase1 import (  # noqa: F401
+    CHECK_FULL, CHECK_NO, CHECK_NONZERO, CURVES, Phase1Parameters, batch_exp, batch_mul, contribute_buf,
+    contribute_dev, reencode,
+)

@@ -1,0 +1,348 @@
+// libsso_b200.so — the C ABI declared in include/sso_b200.h.
+//
+// Everything the operator's `contribute` / `verify_transcript` binaries reach through
+// phase1_cli / phase2_cli on this path is computed on the GPU; the host side
+// only moves bytes, hashes (Blake2b, sequential by construction) and checks sizes.
+// There is no CPU fallback: without a device every compute entry returns SSO_E_CUDA.
+#include "blake2b.h"
+#include "curve_ops.cuh"
+
+using namespace sso;
+
+// ---------------------------------------------------------------------------------------------
+// small kernels that are not per-curve
+// ---------------------------------------------------------------------------------------------
+template <class F>
+__global__ void k_test_field_mul(const uint8_t* a, const uint8_t* b, uint8_t* out, uint32_t n, uint32_t* status) {
+  uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= n) return;
+  typename F::T x, y;
+  uint32_t fl;
+  bool ok = F::from_bytes(a + (size_t)tid * F::NBYTES, false, fl, x);
+  ok = F::from_bytes(b + (size_t)tid * F::NBYTES, false, fl, y) && ok;
+  if (!ok) report(status, ST_NONCANONICAL, tid);
+  F::to_bytes(out + (size_t)tid * F::NBYTES, F::mul(x, y), 0);
+}
+
+// Multiply-accumulate peak probes (roofline denominator).
+//   variant 0: mad.wide.u32 (32x32+64 -> 64) on 8 independent accumulators per thread
+//   variant 1: the mad.lo.cc / madc.hi.cc carry-chain pairs the field multiplication is written in
+//   variant 2: mad.lo.u32 (32x32+32 -> 32), for reference
+// Every variant issues 32 multiply-accumulates per thread per iteration.
+__global__ void k_imad_probe(uint32_t iters, uint32_t variant, uint32_t seed, uint64_t* sink) {
+  uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t a = seed * 2654435761u + tid, b = (seed ^ 0x9e3779b9u) + tid * 7u;
+  if (variant == 0) {
+    uint64_t acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = tid + i;
+    for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"(a + i), "r"(b + u));
+      }
+    }
+    uint64_t s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s ^= acc[i];
+    if (s == 0x1234567ull) sink[0] = s;
+  } else if (variant == 1) {
+    uint32_t acc[4][8];
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+      for (int i = 0; i < 8; i++) acc[c][i] = tid + i + c;
+    for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          // one carry chain of 4 products (8 half-instructions) per accumulator row
+          acc[c][0] = mad_lo_cc(a + u, b + c, acc[c][0]);
+          acc[c][1] = madc_hi_cc(a + u, b + c, acc[c][1]);
+          acc[c][2] = madc_lo_cc(a + 1, b + c, acc[c][2]);
+          acc[c][3] = madc_hi_cc(a + 1, b + c, acc[c][3]);
+          acc[c][4] = madc_lo_cc(a + 2, b + c, acc[c][4]);
+          acc[c][5] = madc_hi_cc(a + 2, b + c, acc[c][5]);
+          acc[c][6] = madc_lo_cc(a + 3, b + c, acc[c][6]);
+          acc[c][7] = madc_hi(a + 3, b + c, acc[c][7]);
+        }
+      }
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+      for (int i = 0; i < 8; i++) s ^= acc[c][i];
+    if (s == 0x1234567u) sink[0] = s;
+  } else {
+    uint32_t acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = tid + i;
+    for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc[i]) : "r"(a + i), "r"(b + u));
+      }
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s ^= acc[i];
+    if (s == 0x1234567u) sink[0] = s;
+  }
+}
+
+namespace {
+
+const CurveOps* ops_for(uint32_t curve) {
+  switch (curve) {
+    case SSO_CURVE_BLS12_377: return curve_ops_bls12_377();
+    case SSO_CURVE_BW6_761: return curve_ops_bw6_761();
+    case SSO_CURVE_MNT4_753: return curve_ops_mnt4_753();
+    case SSO_CURVE_MNT6_753: return curve_ops_mnt6_753();
+  }
+  return nullptr;
+}
+
+// Phase1::computation on the five vectors of one chunk; G1 vectors on stream 0, G2 on stream 1.
+int p1_contribute_streams(Ctx& c, const CurveOps* ops, const P1Layout& L, const uint8_t* d_ch, uint8_t* d_resp,
+                          const uint8_t* tau, const uint8_t* alpha, const uint8_t* beta, uint32_t check, uint32_t* d_status,
+                          char* err, size_t errcap) {
+  int rc;
+  if ((rc = ops->batch_exp(c, 0, GROUP_G1, d_ch + L.off_u[0], 0, L.g1n, L.start, tau, nullptr, 0, d_resp + L.off_c[0], 1, check, d_status, err, errcap))) return rc;
+  if ((rc = ops->batch_exp(c, 1, GROUP_G2, d_ch + L.off_u[1], 0, L.on, L.start, tau, nullptr, 0, d_resp + L.off_c[1], 1, check, d_status, err, errcap))) return rc;
+  if ((rc = ops->batch_exp(c, 0, GROUP_G1, d_ch + L.off_u[2], 0, L.on, L.start, tau, alpha, 0, d_resp + L.off_c[2], 1, check, d_status, err, errcap))) return rc;
+  if ((rc = ops->batch_exp(c, 0, GROUP_G1, d_ch + L.off_u[3], 0, L.on, L.start, tau, beta, 0, d_resp + L.off_c[3], 1, check, d_status, err, errcap))) return rc;
+  // beta_g2 *= beta : one element, shared-scalar mode
+  std::vector<uint8_t> one(ops->fr_bytes, 0);
+  one[0] = 1;
+  return ops->batch_exp(c, 1, GROUP_G2, d_ch + L.off_u[4], 0, 1, 0, one.data(), beta, 1, d_resp + L.off_c[4], 1, check, d_status, err, errcap);
+}
+
+int status_buffer(Ctx& c, uint32_t** d_status, char* err, size_t errcap) {
+  int rc = c.alloc((void**)d_status, 8);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemsetAsync(*d_status, 0, 8, c.s[0]));
+  CUDA_TRY(cudaStreamSynchronize(c.s[0]));
+  return SSO_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* sso_version(void) { return "sso_b200 0.1 (sm_100a)"; }
+
+int32_t sso_device_count(void) {
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess) return 0;
+  return cnt;
+}
+
+int32_t sso_device_name(int device, char* out, size_t cap) {
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SSO_E_CUDA;
+  snprintf(out, cap, "%s", prop.name);
+  return SSO_OK;
+}
+
+int32_t sso_curve_sizes(uint32_t curve, uint64_t out[5]) {
+  CurveSizes s;
+  if (!curve_sizes(curve, s)) return SSO_E_ARG;
+  out[0] = s.g1c; out[1] = s.g1u; out[2] = s.g2c; out[3] = s.g2u; out[4] = s.fr;
+  return SSO_OK;
+}
+
+int32_t sso_p1_sizes(const sso_p1_params_t* p, uint64_t out[8], char* err, size_t errcap) {
+  P1Layout L;
+  int rc = p1_layout(p, L, err, errcap);
+  if (rc) return rc;
+  out[SSO_SZ_POWERS_LENGTH] = L.powers_length;
+  out[SSO_SZ_POWERS_G1_LENGTH] = L.powers_g1_length;
+  out[SSO_SZ_G1_COUNT] = L.g1n;
+  out[SSO_SZ_OTHER_COUNT] = L.on;
+  out[SSO_SZ_ACCUMULATOR] = L.acc_size;
+  out[SSO_SZ_CONTRIBUTION] = L.contrib_size;
+  out[SSO_SZ_PUBLIC_KEY] = L.pk_size;
+  out[SSO_SZ_NUM_CHUNKS] = L.num_chunks;
+  return SSO_OK;
+}
+
+int32_t sso_blake2b_512(const uint8_t* data, size_t len, uint8_t out[64]) {
+  blake2b_512(data, len, out);
+  return SSO_OK;
+}
+
+int32_t sso_batch_exp_dev(uint32_t curve, uint32_t group, const void* d_in, uint32_t in_compressed, uint64_t n,
+                          uint64_t first_index, const uint8_t* tau, const uint8_t* coeff, void* d_out,
+                          uint32_t out_compressed, uint32_t check_input, int device, char* err, size_t errcap) {
+  const CurveOps* ops = ops_for(curve);
+  if (!ops || !tau) { set_err(err, errcap, "unknown curve %u or null scalar", curve); return SSO_E_ARG; }
+  Ctx c(err, errcap);
+  int rc = c.init(device);
+  if (rc) return rc;
+  uint32_t* d_status;
+  if ((rc = status_buffer(c, &d_status, err, errcap))) return rc;
+  if ((rc = ops->batch_exp(c, 0, group, (const uint8_t*)d_in, in_compressed, n, first_index, tau, coeff, 0, (uint8_t*)d_out,
+                           out_compressed, check_input, d_status, err, errcap))) return rc;
+  if ((rc = sync_all(c, err, errcap))) return rc;
+  return check_status(c, d_status, "batch_exp input", err, errcap);
+}
+
+int32_t sso_batch_mul_dev(uint32_t curve, uint32_t group, const void* d_in, uint32_t in_compressed, uint64_t n,
+                          const uint8_t* scalar, void* d_out, uint32_t out_compressed, uint32_t check_input,
+                          int device, char* err, size_t errcap) {
+  const CurveOps* ops = ops_for(curve);
+  if (!ops || !scalar) { set_err(err, errcap, "unknown curve %u or null scalar", curve); return SSO_E_ARG; }
+  Ctx c(err, errcap);
+  int rc = c.init(device);
+  if (rc) return rc;
+  uint32_t* d_status;
+  if ((rc = status_buffer(c, &d_status, err, errcap))) return rc;
+  std::vector<uint8_t> one(ops->fr_bytes, 0);
+  one[0] = 1;
+  // vectors longer than the table span are processed in segments (the scalar is index-independent)
+  CurveSizes cs;
+  curve_sizes(curve, cs);
+  uint64_t in_sz = group == GROUP_G1 ? (in_compressed ? cs.g1c : cs.g1u) : (in_compressed ? cs.g2c : cs.g2u);
+  uint64_t out_sz = group == GROUP_G1 ? (out_compressed ? cs.g1c : cs.g1u) : (out_compressed ? cs.g2c : cs.g2u);
+  const uint64_t SEG = 1ull << 22;
+  for (uint64_t off = 0; off < n; off += SEG) {
+    uint64_t m = n - off < SEG ? n - off : SEG;
+    if ((rc = ops->batch_exp(c, 0, group, (const uint8_t*)d_in + off * in_sz, in_compressed, m, 0, one.data(), scalar, 1,
+                             (uint8_t*)d_out + off * out_sz, out_compressed, check_input, d_status, err, errcap))) return rc;
+  }
+  if ((rc = sync_all(c, err, errcap))) return rc;
+  return check_status(c, d_status, "batch_mul input", err, errcap);
+}
+
+int32_t sso_reencode_dev(uint32_t curve, uint32_t group, const void* d_in, uint32_t in_compressed, uint64_t n,
+                         void* d_out, uint32_t out_compressed, uint32_t check, uint32_t subgroup_check,
+                         int device, char* err, size_t errcap) {
+  const CurveOps* ops = ops_for(curve);
+  if (!ops) { set_err(err, errcap, "unknown curve %u", curve); return SSO_E_ARG; }
+  Ctx c(err, errcap);
+  int rc = c.init(device);
+  if (rc) return rc;
+  uint32_t* d_status;
+  if ((rc = status_buffer(c, &d_status, err, errcap))) return rc;
+  if ((rc = ops->reencode(c, 0, group, (const uint8_t*)d_in, in_compressed, n, (uint8_t*)d_out, out_compressed, check,
+                          subgroup_check, nullptr, d_status, err, errcap))) return rc;
+  if ((rc = sync_all(c, err, errcap))) return rc;
+  return check_status(c, d_status, "point", err, errcap);
+}
+
+int32_t sso_p1_contribute_dev(const sso_p1_params_t* p, const void* d_challenge, void* d_response,
+                              const uint8_t* tau, const uint8_t* alpha, const uint8_t* beta,
+                              uint32_t check_input, int device, char* err, size_t errcap) {
+  P1Layout L;
+  int rc = p1_layout(p, L, err, errcap);
+  if (rc) return rc;
+  const CurveOps* ops = ops_for(p->curve);
+  if (!tau || !alpha || !beta) { set_err(err, errcap, "null scalar"); return SSO_E_ARG; }
+  Ctx c(err, errcap);
+  if ((rc = c.init(device, 2))) return rc;
+  uint32_t* d_status;
+  if ((rc = status_buffer(c, &d_status, err, errcap))) return rc;
+  if ((rc = p1_contribute_streams(c, ops, L, (const uint8_t*)d_challenge, (uint8_t*)d_response, tau, alpha, beta, check_input, d_status, err, errcap))) return rc;
+  if ((rc = sync_all(c, err, errcap))) return rc;
+  return check_status(c, d_status, "challenge", err, errcap);
+}
+
+int32_t sso_p1_contribute_buf(const sso_p1_params_t* p, const uint8_t* challenge, size_t challenge_len,
+                              uint8_t* response, size_t response_len, const uint8_t* tau, const uint8_t* alpha,
+                              const uint8_t* beta, const uint8_t* pubkey, size_t pubkey_len, uint32_t check_input,
+                              int device, char* err, size_t errcap) {
+  P1Layout L;
+  int rc = p1_layout(p, L, err, errcap);
+  if (rc) return rc;
+  const CurveOps* ops = ops_for(p->curve);
+  if (!tau || !alpha || !beta || !challenge || !response) { set_err(err, errcap, "null argument"); return SSO_E_ARG; }
+  if (challenge_len != L.acc_size) { set_err(err, errcap, "challenge has %zu bytes, expected accumulator_size %llu", challenge_len, (unsigned long long)L.acc_size); return SSO_E_ARG; }
+  if (response_len != L.contrib_size) { set_err(err, errcap, "response has %zu bytes, expected contribution_size %llu", response_len, (unsigned long long)L.contrib_size); return SSO_E_ARG; }
+  if (pubkey && pubkey_len != L.pk_size) { set_err(err, errcap, "public key has %zu bytes, expected %llu", pubkey_len, (unsigned long long)L.pk_size); return SSO_E_ARG; }
+  Ctx c(err, errcap);
+  if ((rc = c.init(device, 2))) return rc;
+  uint8_t *d_ch, *d_resp;
+  uint32_t* d_status;
+  if ((rc = c.alloc((void**)&d_ch, L.acc_size))) return rc;
+  if ((rc = c.alloc((void**)&d_resp, L.contrib_size))) return rc;
+  if ((rc = status_buffer(c, &d_status, err, errcap))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(d_ch, challenge, L.acc_size, cudaMemcpyHostToDevice, c.s[0]));
+  CUDA_TRY(cudaStreamSynchronize(c.s[0]));
+  if ((rc = p1_contribute_streams(c, ops, L, d_ch, d_resp, tau, alpha, beta, check_input, d_status, err, errcap))) return rc;
+  // the hash-chain link is computed on the host while the GPU works
+  blake2b_512(challenge, challenge_len, response);
+  if ((rc = sync_all(c, err, errcap))) return rc;
+  if ((rc = check_status(c, d_status, "challenge", err, errcap))) return rc;
+  CUDA_TRY(cudaMemcpy(response + 64, d_resp + 64, L.off_c[5] - 64, cudaMemcpyDeviceToHost));
+  if (pubkey) memcpy(response + L.off_c[5], pubkey, L.pk_size);
+  return SSO_OK;
+}
+
+int32_t sso_imad_peak(int device, int variant, double* macs_per_s, char* err, size_t errcap) {
+  Ctx c(err, errcap);
+  int rc = c.init(device);
+  if (rc) return rc;
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  uint64_t* d_sink;
+  if ((rc = c.alloc((void**)&d_sink, 8))) return rc;
+  const uint32_t iters = 4096, threads = 256, blocks = prop.multiProcessorCount * 8;
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  double best = 0;
+  for (int rep = 0; rep < 6; rep++) {
+    CUDA_TRY(cudaEventRecord(e0, c.s[0]));
+    k_imad_probe<<<blocks, threads, 0, c.s[0]>>>(iters, (uint32_t)variant, 12345u + rep, d_sink);
+    CUDA_TRY(cudaEventRecord(e1, c.s[0]));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    double macs = (double)iters * 32.0 * threads * blocks;
+    double rate = macs / (ms * 1e-3);
+    if (rep > 0 && rate > best) best = rate;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *macs_per_s = best;
+  return SSO_OK;
+}
+
+int32_t sso_test_field_mul(uint32_t field, const uint8_t* a, const uint8_t* b, uint8_t* out, uint64_t n, int device,
+                           char* err, size_t errcap) {
+  Ctx c(err, errcap);
+  int rc = c.init(device);
+  if (rc) return rc;
+  static const size_t nbytes[5] = {32, 48, 96, 95, 95};
+  if (field > 4) { set_err(err, errcap, "unknown field %u", field); return SSO_E_ARG; }
+  size_t bytes = n * nbytes[field];
+  uint8_t *d_a, *d_b, *d_o;
+  uint32_t* d_status;
+  if ((rc = c.alloc((void**)&d_a, bytes))) return rc;
+  if ((rc = c.alloc((void**)&d_b, bytes))) return rc;
+  if ((rc = c.alloc((void**)&d_o, bytes))) return rc;
+  if ((rc = status_buffer(c, &d_status, err, errcap))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(d_a, a, bytes, cudaMemcpyHostToDevice, c.s[0]));
+  CUDA_TRY(cudaMemcpyAsync(d_b, b, bytes, cudaMemcpyHostToDevice, c.s[0]));
+  uint32_t g = div_up(n, 128);
+  switch (field) {
+    case 0: k_test_field_mul<Fr253><<<g, 128, 0, c.s[0]>>>(d_a, d_b, d_o, (uint32_t)n, d_status); break;
+    case 1: k_test_field_mul<Fq377><<<g, 128, 0, c.s[0]>>>(d_a, d_b, d_o, (uint32_t)n, d_status); break;
+    case 2: k_test_field_mul<Fq761><<<g, 128, 0, c.s[0]>>>(d_a, d_b, d_o, (uint32_t)n, d_status); break;
+    case 3: k_test_field_mul<Fq4><<<g, 128, 0, c.s[0]>>>(d_a, d_b, d_o, (uint32_t)n, d_status); break;
+    case 4: k_test_field_mul<Fq6><<<g, 128, 0, c.s[0]>>>(d_a, d_b, d_o, (uint32_t)n, d_status); break;
+  }
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(out, d_o, bytes, cudaMemcpyDeviceToHost, c.s[0]));
+  if ((rc = sync_all(c, err, errcap))) return rc;
+  return check_status(c, d_status, "field element", err, errcap);
+}
+
+}  // extern "C"

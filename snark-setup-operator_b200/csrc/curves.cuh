@@ -1,0 +1,104 @@
+// The eight groups of the ceremony: G1 / G2 of BLS12-377, BW6-761, MNT4-753, MNT6-753.
+//
+// Mirrors the `curveKind` values the operator accepts (reference src/data_structs.rs:123-131,
+// src/bin/new_setup.rs:53-54) and the curve crates ark-bls12-377 / ark-bw6-761 / ark-mnt4-753 /
+// ark-mnt6-753 0.4.0 (Cargo.lock:150-151,173-174,282-283,293-294); constants from SURVEY.md A.1
+// via tools/gen_constants.py.
+#pragma once
+#include "ec.cuh"
+
+namespace sso {
+
+using Fr253 = Fp<P_r253>;
+using Fq377 = Fp<P_q377>;
+using Fq761 = Fp<P_q761>;
+using Fq4 = Fp<P_q4>;      // MNT4-753 base field = MNT6-753 scalar field
+using Fq6 = Fp<P_q6>;      // MNT6-753 base field = MNT4-753 scalar field
+
+using Fq377x2 = Fp2<Fq377, SmallNR<Fq377, 5, true>>;     // u^2 = -5
+using Fq4x2 = Fp2<Fq4, SmallNR<Fq4, 13, false>>;          // u^2 = 13
+using Fq6x3 = Fp3<Fq6, SmallNR<Fq6, 11, false>>;          // u^3 = 11
+
+#define SSO_GROUP_COMMON(NAME, FIELD, SCALAR)                                                      \
+  using F = FIELD;                                                                                  \
+  using Fr = SCALAR;                                                                                \
+  __device__ __forceinline__ static typename F::T coeff_b() { return F::from_const(c_##NAME##_b); } \
+  __device__ __forceinline__ static const uint32_t* order() { return c_##NAME##_order; }           \
+  __device__ __forceinline__ static typename F::T gen_x() { return F::from_const(c_##NAME##_gx); }  \
+  __device__ __forceinline__ static typename F::T gen_y() { return F::from_const(c_##NAME##_gy); }
+
+struct Bls12_377_G1 {
+  SSO_GROUP_COMMON(bls12_377_g1, Fq377, Fr253)
+  static constexpr bool A_IS_ZERO = true;
+  __device__ __forceinline__ static F::T mul_a(const F::T&) { return F::zero(); }
+  __device__ __forceinline__ static bool field_sqrt(const F::T& a, F::T& o) { return F::sqrt(a, o); }
+};
+struct Bls12_377_G2 {
+  SSO_GROUP_COMMON(bls12_377_g2, Fq377x2, Fr253)
+  static constexpr bool A_IS_ZERO = true;
+  __device__ __forceinline__ static F::T mul_a(const F::T&) { return F::zero(); }
+  __device__ __forceinline__ static bool field_sqrt(const F::T& a, F::T& o) { return F::sqrt(a, o); }
+};
+struct Bw6_761_G1 {
+  SSO_GROUP_COMMON(bw6_761_g1, Fq761, Fq377)
+  static constexpr bool A_IS_ZERO = true;
+  __device__ __forceinline__ static F::T mul_a(const F::T&) { return F::zero(); }
+  __device__ __forceinline__ static bool field_sqrt(const F::T& a, F::T& o) { return F::sqrt(a, o); }
+};
+struct Bw6_761_G2 {
+  SSO_GROUP_COMMON(bw6_761_g2, Fq761, Fq377)
+  static constexpr bool A_IS_ZERO = true;
+  __device__ __forceinline__ static F::T mul_a(const F::T&) { return F::zero(); }
+  __device__ __forceinline__ static bool field_sqrt(const F::T& a, F::T& o) { return F::sqrt(a, o); }
+};
+struct Mnt4_753_G1 {                                         // a = 2
+  SSO_GROUP_COMMON(mnt4_753_g1, Fq4, Fq6)
+  static constexpr bool A_IS_ZERO = false;
+  __device__ __forceinline__ static F::T mul_a(const F::T& x) { return F::dbl(x); }
+  __device__ __forceinline__ static bool field_sqrt(const F::T& a, F::T& o) { return F::sqrt(a, o); }
+};
+struct Mnt4_753_G2 {                                         // a' = (26, 0)
+  SSO_GROUP_COMMON(mnt4_753_g2, Fq4x2, Fq6)
+  static constexpr bool A_IS_ZERO = false;
+  __device__ __forceinline__ static F::T mul_a(const F::T& x) { return F::mul_small<26>(x); }
+  __device__ __forceinline__ static bool field_sqrt(const F::T& a, F::T& o) { return F::sqrt(a, o); }
+};
+struct Mnt6_753_G1 {                                         // a = 11
+  SSO_GROUP_COMMON(mnt6_753_g1, Fq6, Fq4)
+  static constexpr bool A_IS_ZERO = false;
+  __device__ __forceinline__ static F::T mul_a(const F::T& x) { return F::mul_small<11>(x); }
+  __device__ __forceinline__ static bool field_sqrt(const F::T& a, F::T& o) { return F::sqrt(a, o); }
+};
+struct Mnt6_753_G2 {                                         // a' = (0, 0, 11) = 11 u^2, u^3 = 11
+  SSO_GROUP_COMMON(mnt6_753_g2, Fq6x3, Fq4)
+  static constexpr bool A_IS_ZERO = false;
+  __device__ __forceinline__ static F::T mul_a(const F::T& x) {
+    // x * u^2 = (11 c1, 11 c2, c0), then times 11
+    F::T t{Fq6::mul_small<11>(x.c1), Fq6::mul_small<11>(x.c2), x.c0};
+    return F::mul_small<11>(t);
+  }
+  __device__ __forceinline__ static bool field_sqrt(const F::T& a, F::T& o) {
+    return F::sqrt_ts<TS_q6x3>(a, o, c_q6x3_tm1h, c_q6x3_tsz);
+  }
+};
+
+// ids on the C ABI (include/sso_b200.h)
+enum : uint32_t { CURVE_BLS12_377 = 0, CURVE_BW6_761 = 1, CURVE_MNT4_753 = 2, CURVE_MNT6_753 = 3 };
+enum : uint32_t { GROUP_G1 = 0, GROUP_G2 = 1 };
+
+// Dispatch a generic lambda on (curve, group): f(GroupCfg{})
+template <class Fn> inline int dispatch_group(uint32_t curve, uint32_t group, Fn&& f) {
+  switch (curve * 2 + group) {
+    case 0: f(Bls12_377_G1{}); return 0;
+    case 1: f(Bls12_377_G2{}); return 0;
+    case 2: f(Bw6_761_G1{}); return 0;
+    case 3: f(Bw6_761_G2{}); return 0;
+    case 4: f(Mnt4_753_G1{}); return 0;
+    case 5: f(Mnt4_753_G2{}); return 0;
+    case 6: f(Mnt6_753_G1{}); return 0;
+    case 7: f(Mnt6_753_G2{}); return 0;
+  }
+  return -1;
+}
+
+}  // namespace sso

@@ -1,0 +1,238 @@
+// Short-Weierstrass group law in Jacobian coordinates, generic over the base field.
+//
+// B200-native counterpart of ark-ec 0.4.2 `short_weierstrass::{Affine, Projective}` as driven by
+// setup_utils::batch_exp / batch_mul (§8a rows a4, a10).  Where the
+// reference does MSB-first double-and-add per point, this core uses a signed fixed-window
+// ladder (w = 4, digits in [-8, 7], table 1P..8P) — the scalar multiple is mathematically the
+// same point, and results are compared after normalisation to affine.
+//
+// Field-multiplication counts (S = M), used by the roofline in DESIGN.md:
+//   dbl  (a = 0)  7 M      dbl (a != 0)  9 M + mul_a
+//   madd          11 M     add           16 M
+#pragma once
+#include "ext.cuh"
+
+namespace sso {
+
+template <class Cfg> struct SW {
+  using F = typename Cfg::F;
+  using FT = typename F::T;
+  struct Affine { FT x, y; bool inf; };
+  struct Jac { FT X, Y, Z; };
+
+  __device__ __forceinline__ static Jac identity() { return Jac{F::one(), F::one(), F::zero()}; }
+  __device__ __forceinline__ static bool is_identity(const Jac& p) { return F::is_zero(p.Z); }
+  __device__ __forceinline__ static Jac from_affine(const Affine& a) {
+    if (a.inf) return identity();
+    return Jac{a.x, a.y, F::one()};
+  }
+  __device__ __forceinline__ static Jac neg(const Jac& p) { return Jac{p.X, F::neg(p.Y), p.Z}; }
+
+  // y^2 == x^3 + a x + b
+  __device__ __noinline__ static bool on_curve(const Affine& p) {
+    if (p.inf) return true;
+    FT rhs = F::add(F::mul(F::sqr(p.x), p.x), Cfg::coeff_b());
+    if (!Cfg::A_IS_ZERO) rhs = F::add(rhs, Cfg::mul_a(p.x));
+    return F::eq(F::sqr(p.y), rhs);
+  }
+  __device__ __forceinline__ static FT rhs(const FT& x) {
+    FT r = F::add(F::mul(F::sqr(x), x), Cfg::coeff_b());
+    if (!Cfg::A_IS_ZERO) r = F::add(r, Cfg::mul_a(x));
+    return r;
+  }
+
+  __device__ __noinline__ static Jac dbl(const Jac& p) {
+    Jac r;
+    if (Cfg::A_IS_ZERO) {
+      FT A = F::sqr(p.X);
+      FT B = F::sqr(p.Y);
+      FT C = F::sqr(B);
+      FT D = F::sub(F::sub(F::sqr(F::add(p.X, B)), A), C);
+      D = F::dbl(D);
+      FT E = F::add(F::dbl(A), A);
+      FT Fq = F::sqr(E);
+      r.Z = F::dbl(F::mul(p.Y, p.Z));
+      r.X = F::sub(Fq, F::dbl(D));
+      FT C8 = F::dbl(F::dbl(F::dbl(C)));
+      r.Y = F::sub(F::mul(E, F::sub(D, r.X)), C8);
+    } else {
+      FT XX = F::sqr(p.X);
+      FT YY = F::sqr(p.Y);
+      FT YYYY = F::sqr(YY);
+      FT ZZ = F::sqr(p.Z);
+      FT S = F::sub(F::sub(F::sqr(F::add(p.X, YY)), XX), YYYY);
+      S = F::dbl(S);
+      FT M = F::add(F::add(F::dbl(XX), XX), Cfg::mul_a(F::sqr(ZZ)));
+      r.Z = F::sub(F::sub(F::sqr(F::add(p.Y, p.Z)), YY), ZZ);
+      r.X = F::sub(F::sqr(M), F::dbl(S));
+      FT Y8 = F::dbl(F::dbl(F::dbl(YYYY)));
+      r.Y = F::sub(F::mul(M, F::sub(S, r.X)), Y8);
+    }
+    return r;
+  }
+
+  // p + q with q affine (q.inf handled)
+  __device__ __noinline__ static Jac madd(const Jac& p, const Affine& q) {
+    if (q.inf) return p;
+    if (is_identity(p)) return Jac{q.x, q.y, F::one()};
+    FT Z1Z1 = F::sqr(p.Z);
+    FT U2 = F::mul(q.x, Z1Z1);
+    FT S2 = F::mul(F::mul(q.y, p.Z), Z1Z1);
+    FT H = F::sub(U2, p.X);
+    FT rr = F::sub(S2, p.Y);
+    if (F::is_zero(H)) {
+      if (F::is_zero(rr)) return dbl(p);
+      return identity();
+    }
+    rr = F::dbl(rr);
+    FT HH = F::sqr(H);
+    FT I = F::dbl(F::dbl(HH));
+    FT J = F::mul(H, I);
+    FT V = F::mul(p.X, I);
+    Jac r;
+    r.X = F::sub(F::sub(F::sqr(rr), J), F::dbl(V));
+    r.Y = F::sub(F::mul(rr, F::sub(V, r.X)), F::dbl(F::mul(p.Y, J)));
+    r.Z = F::sub(F::sub(F::sqr(F::add(p.Z, H)), Z1Z1), HH);
+    return r;
+  }
+
+  __device__ __noinline__ static Jac add(const Jac& p, const Jac& q) {
+    if (is_identity(p)) return q;
+    if (is_identity(q)) return p;
+    FT Z1Z1 = F::sqr(p.Z);
+    FT Z2Z2 = F::sqr(q.Z);
+    FT U1 = F::mul(p.X, Z2Z2);
+    FT U2 = F::mul(q.X, Z1Z1);
+    FT S1 = F::mul(F::mul(p.Y, q.Z), Z2Z2);
+    FT S2 = F::mul(F::mul(q.Y, p.Z), Z1Z1);
+    FT H = F::sub(U2, U1);
+    FT rr = F::sub(S2, S1);
+    if (F::is_zero(H)) {
+      if (F::is_zero(rr)) return dbl(p);
+      return identity();
+    }
+    rr = F::dbl(rr);
+    FT I = F::sqr(F::dbl(H));
+    FT J = F::mul(H, I);
+    FT V = F::mul(U1, I);
+    Jac r;
+    r.X = F::sub(F::sub(F::sqr(rr), J), F::dbl(V));
+    r.Y = F::sub(F::mul(rr, F::sub(V, r.X)), F::dbl(F::mul(S1, J)));
+    r.Z = F::mul(F::sub(F::sub(F::sqr(F::add(p.Z, q.Z)), Z1Z1), Z2Z2), H);
+    return r;
+  }
+
+  // Signed fixed-window scalar multiplication.  `k` = canonical scalar, KL little-endian words,
+  // value < 2^KBITS; the bias trick k' = k + 0x88..8 makes every window digit = nibble(k') - 8
+  // with no carry propagation, so digits can be read MSB-first.
+  template <int KL, int KBITS>
+  __device__ __forceinline__ static Jac scalar_mul(const Affine& base, const uint32_t* k) {
+    constexpr int NW = (KBITS + 2 + 3) / 4;                 // 4*NW >= KBITS + 2
+    constexpr int BL = (4 * NW + 31) / 32;                  // words of the biased scalar
+    static_assert(BL >= KL, "window count must cover the scalar");
+    if (base.inf) return identity();
+    // biased scalar
+    uint32_t kb[BL];
+    {
+      uint32_t carry = 0;
+#pragma unroll
+      for (int i = 0; i < BL; i++) {
+        uint32_t ki = i < KL ? k[i] : 0u;
+        int lo = 32 * i, hi = 32 * i + 32;
+        uint32_t c = 0x88888888u;
+        if (4 * NW < hi) c = (4 * NW <= lo) ? 0u : (0x88888888u & ((1u << (4 * NW - lo)) - 1u));
+        uint64_t s = (uint64_t)ki + c + carry;
+        kb[i] = (uint32_t)s;
+        carry = (uint32_t)(s >> 32);
+      }
+    }
+    // table 1P .. 8P
+    Jac tab[8];
+    tab[0] = Jac{base.x, base.y, F::one()};
+    tab[1] = dbl(tab[0]);
+    tab[2] = madd(tab[1], base);
+    tab[3] = dbl(tab[1]);
+    tab[4] = madd(tab[3], base);
+    tab[5] = dbl(tab[2]);
+    tab[6] = madd(tab[5], base);
+    tab[7] = dbl(tab[3]);
+    Jac acc = identity();
+#pragma unroll 1
+    for (int w = NW - 1; w >= 0; w--) {
+      if (w != NW - 1) {
+#pragma unroll 1
+        for (int d = 0; d < 4; d++) acc = dbl(acc);
+      }
+      int nib = (int)((kb[w >> 3] >> ((w & 7) * 4)) & 15u);
+      int dgt = nib - 8;
+      if (dgt != 0) {
+        int idx = (dgt < 0 ? -dgt : dgt) - 1;
+        Jac q = tab[idx];
+        if (dgt < 0) q.Y = F::neg(q.Y);
+        acc = add(acc, q);
+      }
+    }
+    return acc;
+  }
+
+  // plain MSB-first double-and-add for a constant-memory exponent (subgroup checks, cofactors)
+  __device__ __noinline__ static Jac mul_const(const Affine& base, const uint32_t* e, int nwords) {
+    Jac acc = identity();
+    for (int i = nwords * 32 - 1; i >= 0; i--) {
+      acc = dbl(acc);
+      if ((e[i >> 5] >> (i & 31)) & 1) acc = madd(acc, base);
+    }
+    return acc;
+  }
+
+  // Jacobian -> affine given zinv = 1/Z
+  __device__ __forceinline__ static Affine to_affine_with(const Jac& p, const FT& zinv) {
+    FT zi2 = F::sqr(zinv);
+    Affine a;
+    a.x = F::mul(p.X, zi2);
+    a.y = F::mul(p.Y, F::mul(zi2, zinv));
+    a.inf = false;
+    return a;
+  }
+
+  // ---- byte formats (ark-ec 0.4.2 SWFlags: bit7 = y > -y, bit6 = infinity) ----
+  static constexpr int SIZE_C = F::NBYTES;
+  static constexpr int SIZE_U = 2 * F::NBYTES;
+  enum : uint32_t { DESER_OK = 0, DESER_NONCANONICAL = 1, DESER_BAD_FLAGS = 2, DESER_NOT_ON_CURVE = 3 };
+
+  __device__ __forceinline__ static uint32_t read_uncompressed(const uint8_t* src, Affine& out) {
+    uint32_t fx, fy;
+    bool okx = F::from_bytes(src, false, fx, out.x);
+    bool oky = F::from_bytes(src + F::NBYTES, true, fy, out.y);
+    out.inf = false;
+    if (fy == 0xC0u) return DESER_BAD_FLAGS;
+    if (!okx || !oky) return DESER_NONCANONICAL;
+    if (fy & 0x40u) { out.inf = true; out.x = F::zero(); out.y = F::zero(); }
+    return DESER_OK;
+  }
+  __device__ __forceinline__ static uint32_t read_compressed(const uint8_t* src, Affine& out) {
+    uint32_t fx;
+    bool okx = F::from_bytes(src, true, fx, out.x);
+    out.inf = false;
+    if (fx == 0xC0u) return DESER_BAD_FLAGS;
+    if (!okx) return DESER_NONCANONICAL;
+    if (fx & 0x40u) { out.inf = true; out.x = F::zero(); out.y = F::zero(); return DESER_OK; }
+    FT y;
+    if (!Cfg::field_sqrt(rhs(out.x), y)) return DESER_NOT_ON_CURVE;
+    bool want_neg = (fx & 0x80u) != 0;
+    if (F::lex_is_neg(y) != want_neg) y = F::neg(y);
+    out.y = y;
+    return DESER_OK;
+  }
+  __device__ __forceinline__ static void write_compressed(uint8_t* dst, const Affine& a) {
+    if (a.inf) { F::to_bytes(dst, F::zero(), 0x40u); return; }
+    F::to_bytes(dst, a.x, F::lex_is_neg(a.y) ? 0x80u : 0u);
+  }
+  __device__ __forceinline__ static void write_uncompressed(uint8_t* dst, const Affine& a) {
+    if (a.inf) { F::to_bytes(dst, F::zero(), 0); F::to_bytes(dst + F::NBYTES, F::zero(), 0x40u); return; }
+    F::to_bytes(dst, a.x, 0);
+    F::to_bytes(dst + F::NBYTES, a.y, F::lex_is_neg(a.y) ? 0x80u : 0u);
+  }
+};
+
+}  // namespace sso

@@ -1,0 +1,343 @@
+// Prime-field arithmetic for sm_100a: Montgomery form, 32-bit limbs, one thread per element.
+//
+// B200-native replacement for the role ark-ff 0.4.2 `Fp<MontBackend<_, N>>` plays under
+// setup_utils::batch_exp.  The Montgomery radix is 2^(32 L), which
+// equals ark-ff's 2^(64 ceil(bits/64)) for all five primes, so Montgomery residues coincide
+// with the reference's in-memory representation (relevant for Fr::rand).
+//
+// Multiplication is CIOS with the partial products split by limb parity into two carry chains
+// ("even" and "odd" accumulators) so that every 32x32->64 product lands in an adjacent register
+// pair and ptxas can emit one IMAD.WIDE-class instruction per product with the carry riding the
+// chain.  Work per multiplication: 2 L^2 + L multiply-accumulates.
+#pragma once
+#include <cstdint>
+#include "constants.cuh"
+
+namespace sso {
+
+// ---------------------------------------------------------------------------------------------
+// PTX carry-chain primitives (CC.CF lives across consecutive asm volatile statements)
+// ---------------------------------------------------------------------------------------------
+#ifndef SSO_HOST_EMUL
+__device__ __forceinline__ uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t addc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t addc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t sub_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t mul_lo(uint32_t a, uint32_t b) { uint32_t r; asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t mul_hi(uint32_t a, uint32_t b) { uint32_t r; asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+#else
+// TEST-ONLY instruction-level emulation of the PTX carry flag so that the device algorithms can be
+// exercised by g++ in this GPU-less container (tests/emul/).  Never part of the product library.
+static thread_local uint32_t g_cf = 0;
+static inline uint32_t emu_add(uint32_t a, uint32_t b, uint32_t cin, bool setc) { uint64_t s = (uint64_t)a + b + cin; if (setc) g_cf = (uint32_t)(s >> 32); return (uint32_t)s; }
+static inline uint32_t emu_sub(uint32_t a, uint32_t b, uint32_t bin, bool setc) { uint64_t s = (uint64_t)a - b - bin; if (setc) g_cf = (uint32_t)((s >> 32) & 1); return (uint32_t)s; }
+static inline uint32_t add_cc(uint32_t a, uint32_t b) { return emu_add(a, b, 0, true); }
+static inline uint32_t addc_cc(uint32_t a, uint32_t b) { return emu_add(a, b, g_cf, true); }
+static inline uint32_t addc(uint32_t a, uint32_t b) { return emu_add(a, b, g_cf, false); }
+static inline uint32_t sub_cc(uint32_t a, uint32_t b) { return emu_sub(a, b, 0, true); }
+static inline uint32_t subc_cc(uint32_t a, uint32_t b) { return emu_sub(a, b, g_cf, true); }
+static inline uint32_t subc(uint32_t a, uint32_t b) { return emu_sub(a, b, g_cf, false); }
+static inline uint32_t mul_lo(uint32_t a, uint32_t b) { return (uint32_t)((uint64_t)a * b); }
+static inline uint32_t mul_hi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+static inline uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return emu_add(mul_lo(a, b), c, 0, true); }
+static inline uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return emu_add(mul_lo(a, b), c, g_cf, true); }
+static inline uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return emu_add(mul_hi(a, b), c, g_cf, true); }
+static inline uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return emu_add(mul_hi(a, b), c, g_cf, false); }
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// fixed-width helpers on raw limb arrays
+// ---------------------------------------------------------------------------------------------
+template <int N> struct big { uint32_t v[N]; };
+
+template <int N> __device__ __forceinline__ bool limbs_is_zero(const uint32_t* a) {
+  uint32_t o = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) o |= a[i];
+  return o == 0;
+}
+template <int N> __device__ __forceinline__ bool limbs_eq(const uint32_t* a, const uint32_t* b) {
+  uint32_t o = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) o |= a[i] ^ b[i];
+  return o == 0;
+}
+// a > b (unsigned, little-endian limbs)
+template <int N> __device__ __forceinline__ bool limbs_gt(const uint32_t* a, const uint32_t* b) {
+  // b - a borrows  <=>  a > b
+  sub_cc(b[0], a[0]);
+#pragma unroll
+  for (int i = 1; i < N; i++) subc_cc(b[i], a[i]);
+  return subc(0, 0) != 0;
+}
+// r = a + b, returns carry
+template <int N> __device__ __forceinline__ uint32_t limbs_add(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  r[0] = add_cc(a[0], b[0]);
+#pragma unroll
+  for (int i = 1; i < N; i++) r[i] = addc_cc(a[i], b[i]);
+  return addc(0, 0);
+}
+// r = a - b, returns borrow (0 or 0xffffffff)
+template <int N> __device__ __forceinline__ uint32_t limbs_sub(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  r[0] = sub_cc(a[0], b[0]);
+#pragma unroll
+  for (int i = 1; i < N; i++) r[i] = subc_cc(a[i], b[i]);
+  return subc(0, 0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Montgomery multiplication building blocks (n = L limbs, n even)
+// ---------------------------------------------------------------------------------------------
+// acc[0..n) = sum_{j even} a[j] * bi * 2^(32 j)   (disjoint register pairs, no carries)
+template <int n> __device__ __forceinline__ void mul_n(uint32_t* acc, const uint32_t* a, uint32_t bi) {
+#pragma unroll
+  for (int j = 0; j < n; j += 2) {
+    acc[j] = mul_lo(a[j], bi);
+    acc[j + 1] = mul_hi(a[j], bi);
+  }
+}
+// acc += sum_{j even} a[j] * bi * 2^(32 j); carry-out left in CC.CF
+template <int n> __device__ __forceinline__ void cmad_n(uint32_t* acc, const uint32_t* a, uint32_t bi) {
+  acc[0] = mad_lo_cc(a[0], bi, acc[0]);
+  acc[1] = madc_hi_cc(a[0], bi, acc[1]);
+#pragma unroll
+  for (int j = 2; j < n; j += 2) {
+    acc[j] = madc_lo_cc(a[j], bi, acc[j]);
+    acc[j + 1] = madc_hi_cc(a[j], bi, acc[j + 1]);
+  }
+}
+// acc = (acc >> 64) + sum_{j even} a[j] * bi * 2^(32 j), carry-in from CC.CF
+template <int n> __device__ __forceinline__ void madc_n_rshift(uint32_t* acc, const uint32_t* a, uint32_t bi) {
+#pragma unroll
+  for (int j = 0; j < n - 2; j += 2) {
+    acc[j] = madc_lo_cc(a[j], bi, acc[j + 2]);
+    acc[j + 1] = madc_hi_cc(a[j], bi, acc[j + 3]);
+  }
+  acc[n - 2] = madc_lo_cc(a[n - 2], bi, 0);
+  acc[n - 1] = madc_hi(a[n - 2], bi, 0);
+}
+
+// One CIOS step: T <- (T + a * bi + m * p) / 2^32 with T held as E (aligned at limb 0) plus
+// O (aligned at limb 1).  After the step the roles of E and O are exchanged (caller swaps).
+template <class P> __device__ __forceinline__ void mad_n_redc(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi, bool first) {
+  constexpr int n = P::L;
+  const uint32_t* MOD = P::p();
+  if (first) {
+    mul_n<n>(O, a + 1, bi);
+    mul_n<n>(E, a, bi);
+  } else {
+    E[0] = add_cc(E[0], O[1]);
+    madc_n_rshift<n>(O, a + 1, bi);
+    cmad_n<n>(E, a, bi);
+    O[n - 1] = addc(O[n - 1], 0);
+  }
+  uint32_t mi = E[0] * P::INV;
+  cmad_n<n>(O, MOD + 1, mi);
+  cmad_n<n>(E, MOD, mi);
+  O[n - 1] = addc(O[n - 1], 0);
+}
+
+// r = a * b * R^-1 mod p, inputs and output fully reduced
+template <class P> __device__ __forceinline__ void mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  constexpr int n = P::L;
+  uint32_t even[n], odd[n];
+#pragma unroll
+  for (int i = 0; i < n; i += 2) {
+    mad_n_redc<P>(even, odd, a, b[i], i == 0);
+    mad_n_redc<P>(odd, even, a, b[i + 1], false);
+  }
+  // merge: result[k] = even[k] + odd[k+1]
+  even[0] = add_cc(even[0], odd[1]);
+#pragma unroll
+  for (int k = 1; k < n - 1; k++) even[k] = addc_cc(even[k], odd[k + 1]);
+  even[n - 1] = addc(even[n - 1], 0);
+  // final subtraction: result < 2p
+  uint32_t t[n];
+  uint32_t borrow = limbs_sub<n>(t, even, P::p());
+#pragma unroll
+  for (int k = 0; k < n; k++) r[k] = borrow ? even[k] : t[k];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Field wrapper: elements are structs of L limbs in Montgomery form
+// ---------------------------------------------------------------------------------------------
+template <class P_> struct Fp {
+  using P = P_;
+  static constexpr int L = P::L;
+  static constexpr int DEG = 1;
+  static constexpr int NBYTES = P::NBYTES;          // serialized size
+  static constexpr int WORDS = L;                   // uint32 words per element in device arrays
+  struct T { uint32_t v[L]; };
+  using Base = Fp<P_>;
+
+  __device__ __forceinline__ static T zero() { T r;
+#pragma unroll
+    for (int i = 0; i < L; i++) r.v[i] = 0;
+    return r; }
+  __device__ __forceinline__ static T one() { T r;
+#pragma unroll
+    for (int i = 0; i < L; i++) r.v[i] = P::r1()[i];
+    return r; }
+  __device__ __forceinline__ static bool is_zero(const T& a) { return limbs_is_zero<L>(a.v); }
+  __device__ __forceinline__ static bool eq(const T& a, const T& b) { return limbs_eq<L>(a.v, b.v); }
+
+  __device__ __forceinline__ static T add(const T& a, const T& b) {
+    T s, t, r;
+    limbs_add<L>(s.v, a.v, b.v);                    // no overflow: p has spare top bits
+    uint32_t borrow = limbs_sub<L>(t.v, s.v, P::p());
+#pragma unroll
+    for (int i = 0; i < L; i++) r.v[i] = borrow ? s.v[i] : t.v[i];
+    return r;
+  }
+  __device__ __forceinline__ static T dbl(const T& a) { return add(a, a); }
+  __device__ __forceinline__ static T sub(const T& a, const T& b) {
+    T d, t, r;
+    uint32_t borrow = limbs_sub<L>(d.v, a.v, b.v);
+    limbs_add<L>(t.v, d.v, P::p());
+#pragma unroll
+    for (int i = 0; i < L; i++) r.v[i] = borrow ? t.v[i] : d.v[i];
+    return r;
+  }
+  __device__ __forceinline__ static T neg(const T& a) {
+    T t;
+    limbs_sub<L>(t.v, P::p(), a.v);
+    bool z = is_zero(a);
+#pragma unroll
+    for (int i = 0; i < L; i++) t.v[i] = z ? 0u : t.v[i];
+    return t;
+  }
+  // 24-limb multiplications are ~2.5k instructions each: keep one out-of-line copy so that point
+  // formulas do not overflow the instruction cache; 8/12-limb ones are inlined.
+  __device__ __noinline__ static T mul_outlined(const T& a, const T& b) { T r; mont_mul<P>(r.v, a.v, b.v); return r; }
+  __device__ __forceinline__ static T mul(const T& a, const T& b) {
+    if constexpr (L > 12) { return mul_outlined(a, b); } else { T r; mont_mul<P>(r.v, a.v, b.v); return r; }
+  }
+  __device__ __forceinline__ static T sqr(const T& a) { return mul(a, a); }
+  // multiply by a small non-negative integer constant
+  template <int K> __device__ __forceinline__ static T mul_small(const T& a) {
+    static_assert(K >= 0 && K < 64, "small constant");
+    T acc = zero();
+    T base = a;
+    bool started = false;
+#pragma unroll
+    for (int bit = 0; bit < 6; bit++) {
+      if ((K >> bit) & 1) { acc = started ? add(acc, base) : base; started = true; }
+      if ((K >> (bit + 1)) != 0) base = dbl(base);
+    }
+    return acc;
+  }
+
+  // Montgomery <-> canonical
+  __device__ __forceinline__ static T to_mont(const T& a) { T r2;
+#pragma unroll
+    for (int i = 0; i < L; i++) r2.v[i] = P::r2()[i];
+    return mul(a, r2); }
+  __device__ __forceinline__ static T from_mont(const T& a) { T o = zero(); o.v[0] = 1; return mul(a, o); }
+
+  // a^e for a constant-memory exponent of L limbs (not inlined: large, rarely on the hot path)
+  __device__ __noinline__ static T pow_const(const T& a, const uint32_t* e) {
+    T r = one();
+    bool started = false;
+    for (int i = L * 32 - 1; i >= 0; i--) {
+      if (started) r = sqr(r);
+      if ((e[i >> 5] >> (i & 31)) & 1) { r = started ? mul(r, a) : a; started = true; }
+    }
+    return r;
+  }
+  __device__ __forceinline__ static T inv(const T& a) { return pow_const(a, P::pm2()); }
+
+  // canonical-order comparison "a > -a" used by the serialisation sign flag
+  __device__ __forceinline__ static bool is_neg_canonical(const T& canon) { return limbs_gt<L>(canon.v, P::half()); }
+  // lexicographic helper for extension fields: -1 / 0 / +1 for "a vs -a" on a canonical coefficient
+  __device__ __forceinline__ static int sign_canonical(const T& canon) {
+    if (is_zero(canon)) return 0;
+    return is_neg_canonical(canon) ? 1 : -1;
+  }
+  // y > -y (in the field's canonical ordering); input in Montgomery form
+  __device__ __forceinline__ static bool lex_is_neg(const T& a) { return is_neg_canonical(from_mont(a)); }
+
+  // square root (some root) — returns false if a is a non-residue.  p = 3 mod 4 -> one exponentiation,
+  // otherwise Tonelli-Shanks over the 2-Sylow subgroup.
+  __device__ __noinline__ static bool sqrt(const T& a, T& out) {
+    if (is_zero(a)) { out = a; return true; }
+    if (P::P_IS_3_MOD_4) {
+      // (p+1)/4 = (p-3)/4 + 1 = tm1h ... use: w = a^((p-3)/4), x = a*w, check x^2 == a
+      T w = pow_const(a, P::tm1h());                // t = (p-1)/2 odd, (t-1)/2 = (p-3)/4
+      T x = mul(a, w);
+      out = x;
+      return eq(sqr(x), a);
+    }
+    // w = a^((t-1)/2); x = a w; b = x w  (= a^t)
+    T w = pow_const(a, P::tm1h());
+    T x = mul(a, w);
+    T b = mul(x, w);
+    T z;
+#pragma unroll
+    for (int i = 0; i < L; i++) z.v[i] = P::tsz()[i];
+    int m = P::TWO_ADICITY;
+    T o = one();
+    while (!eq(b, o)) {
+      int k = 0;
+      T b2 = b;
+      while (!eq(b2, o)) { b2 = sqr(b2); k++; if (k >= m) return false; }   // non-residue
+      T wz = z;
+      for (int j = 0; j < m - k - 1; j++) wz = sqr(wz);
+      z = sqr(wz);
+      b = mul(b, z);
+      x = mul(x, wz);
+      m = k;
+    }
+    out = x;
+    return true;
+  }
+
+  // ---- byte formats (ark-serialize 0.4.2: canonical little-endian, ceil(bits/8) bytes) ----
+  // Reads NBYTES bytes; the two top bits of the last byte are returned in `flags` and masked off
+  // when with_flags.  Returns false when the integer is >= p.  Output in Montgomery form.
+  __device__ __forceinline__ static bool from_bytes(const uint8_t* src, bool with_flags, uint32_t& flags, T& out) {
+    T c = zero();
+#pragma unroll
+    for (int i = 0; i < NBYTES; i++) {
+      uint32_t byte = src[i];
+      if (i == NBYTES - 1) {
+        flags = with_flags ? (byte & 0xC0u) : 0u;
+        if (with_flags) byte &= 0x3Fu;
+      }
+      c.v[i >> 2] |= byte << ((i & 3) * 8);
+    }
+    T t;
+    uint32_t borrow = limbs_sub<L>(t.v, c.v, P::p());
+    out = to_mont(c);
+    return borrow != 0;                             // c < p
+  }
+  __device__ __forceinline__ static void to_bytes(uint8_t* dst, const T& a, uint32_t flags) {
+    T c = from_mont(a);
+#pragma unroll
+    for (int i = 0; i < NBYTES; i++) {
+      uint32_t byte = (c.v[i >> 2] >> ((i & 3) * 8)) & 0xFFu;
+      if (i == NBYTES - 1) byte |= flags;
+      dst[i] = (uint8_t)byte;
+    }
+  }
+  // word-array I/O for device-resident SoA/AoS buffers (Montgomery form)
+  __device__ __forceinline__ static T load(const uint32_t* p, size_t stride) { T r;
+#pragma unroll
+    for (int i = 0; i < L; i++) r.v[i] = p[i * stride];
+    return r; }
+  __device__ __forceinline__ static void store(uint32_t* p, size_t stride, const T& a) {
+#pragma unroll
+    for (int i = 0; i < L; i++) p[i * stride] = a.v[i];
+  }
+  __device__ __forceinline__ static T from_const(const uint32_t* c) { T r;
+#pragma unroll
+    for (int i = 0; i < L; i++) r.v[i] = c[i];
+    return r; }
+};
+
+}  // namespace sso

@@ -1,0 +1,155 @@
+// Host-side plumbing shared by the per-curve translation units and the C ABI (abi.cu):
+// error strings, Phase1Parameters layout arithmetic, per-call CUDA context (own streams and
+// stream-ordered scratch, so every ABI call is re-entrant — SURVEY.md §8b "Threading").
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sso_b200.h"
+
+namespace sso {
+
+
+inline void set_err(char* err, size_t cap, const char* fmt, ...) {
+  if (!err || cap == 0) return;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(err, cap, fmt, ap);
+  va_end(ap);
+}
+
+#define CUDA_TRY(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t e_ = (expr);                                                                        \
+    if (e_ != cudaSuccess) {                                                                        \
+      set_err(err, errcap, "CUDA error %s at %s:%d (%s)", cudaGetErrorName(e_), __FILE__, __LINE__, \
+              cudaGetErrorString(e_));                                                              \
+      return SSO_E_CUDA;                                                                            \
+    }                                                                                               \
+  } while (0)
+
+struct CurveSizes { uint64_t g1c, g1u, g2c, g2u, fr; };
+inline bool curve_sizes(uint32_t curve, CurveSizes& s) {
+  switch (curve) {
+    case SSO_CURVE_BLS12_377: s = {48, 96, 96, 192, 32}; return true;
+    case SSO_CURVE_BW6_761: s = {96, 192, 96, 192, 48}; return true;
+    case SSO_CURVE_MNT4_753: s = {95, 190, 190, 380, 95}; return true;
+    case SSO_CURVE_MNT6_753: s = {95, 190, 285, 570, 95}; return true;
+  }
+  return false;
+}
+
+// Phase1Parameters arithmetic
+struct P1Layout {
+  uint64_t powers_length, powers_g1_length, g1n, on, acc_size, contrib_size, pk_size, num_chunks, start;
+  uint64_t off_u[6], off_c[6];   // tauG1, tauG2, alphaG1, betaG1, betaG2, end
+  CurveSizes cs;
+};
+inline int p1_layout(const sso_p1_params_t* p, P1Layout& L, char* err, size_t errcap) {
+  if (!p) { set_err(err, errcap, "null parameters"); return SSO_E_ARG; }
+  if (!curve_sizes(p->curve, L.cs)) { set_err(err, errcap, "unknown curve %u", p->curve); return SSO_E_ARG; }
+  if (p->proving_system != SSO_PROVING_GROTH16) { set_err(err, errcap, "only the Groth16 proving system is supported"); return SSO_E_ARG; }
+  if (p->power == 0 || p->power > 32) { set_err(err, errcap, "power out of range"); return SSO_E_ARG; }
+  L.powers_length = 1ull << p->power;
+  L.powers_g1_length = (1ull << (p->power + 1)) - 1;
+  if (p->contribution_mode == SSO_MODE_FULL) {
+    L.start = 0; L.g1n = L.powers_g1_length; L.on = L.powers_length; L.num_chunks = 1;
+  } else {
+    if (p->chunk_size == 0) { set_err(err, errcap, "chunk_size must be positive in chunked mode"); return SSO_E_ARG; }
+    L.start = p->chunk_index * p->chunk_size;
+    L.g1n = L.start >= L.powers_g1_length ? 0 : (L.powers_g1_length - L.start < p->chunk_size ? L.powers_g1_length - L.start : p->chunk_size);
+    L.on = L.start >= L.powers_length ? 0 : (L.powers_length - L.start < p->chunk_size ? L.powers_length - L.start : p->chunk_size);
+    L.num_chunks = (L.powers_g1_length + p->chunk_size - 1) / p->chunk_size;
+  }
+  L.pk_size = 3 * L.cs.g2u + 6 * L.cs.g1u;
+  auto fill = [&](uint64_t* off, uint64_t g1, uint64_t g2) {
+    off[0] = 64; off[1] = off[0] + L.g1n * g1; off[2] = off[1] + L.on * g2; off[3] = off[2] + L.on * g1;
+    off[4] = off[3] + L.on * g1; off[5] = off[4] + g2;
+  };
+  fill(L.off_u, L.cs.g1u, L.cs.g2u);
+  fill(L.off_c, L.cs.g1c, L.cs.g2c);
+  L.acc_size = L.off_u[5];
+  L.contrib_size = L.off_c[5] + L.pk_size;
+  return SSO_OK;
+}
+
+inline const char* status_text(uint32_t code) {
+  switch (code) {
+    case 1: return "field element is not canonical (>= modulus)";
+    case 2: return "invalid point flags";
+    case 3: return "point is not on the curve";
+    case 4: return "point at infinity";
+    case 5: return "point is not in the prime-order subgroup";
+  }
+  return "unknown";
+}
+
+// RAII: device selection + stream + stream-ordered scratch
+struct Ctx {
+  int dev = -1, prev = -1;
+  cudaStream_t s[2] = {nullptr, nullptr};
+  std::vector<void*> allocs;
+  char* err; size_t errcap;
+  Ctx(char* e, size_t c) : err(e), errcap(c) {}
+  int init(int device, int nstreams = 1) {
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) {
+      set_err(err, errcap, "no CUDA device available (this library has no CPU fallback)");
+      return SSO_E_CUDA;
+    }
+    if (device < 0 || device >= cnt) { set_err(err, errcap, "device %d out of range (have %d)", device, cnt); return SSO_E_ARG; }
+    cudaGetDevice(&prev);
+    CUDA_TRY(cudaSetDevice(device));
+    dev = device;
+    for (int i = 0; i < nstreams; i++) CUDA_TRY(cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking));
+    return SSO_OK;
+  }
+  int alloc(void** p, size_t bytes, int si = 0) {
+    CUDA_TRY(cudaMallocAsync(p, bytes ? bytes : 16, s[si]));
+    allocs.push_back(*p);
+    return SSO_OK;
+  }
+  ~Ctx() {
+    if (dev >= 0) {
+      for (void* p : allocs) cudaFreeAsync(p, s[0]);
+      for (auto& st : s) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+      if (prev >= 0) cudaSetDevice(prev);
+    }
+  }
+};
+
+inline uint32_t div_up(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+
+// canonical little-endian scalar bytes -> zero-padded words on the device
+inline int upload_scalar(Ctx& c, const uint8_t* bytes, size_t nbytes, size_t nwords, uint32_t** d_out, int si, char* err, size_t errcap) {
+  std::vector<uint32_t> w(nwords, 0);
+  if (bytes) memcpy(w.data(), bytes, nbytes);
+  else w[0] = 1;
+  int rc = c.alloc((void**)d_out, nwords * 4, si);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(*d_out, w.data(), nwords * 4, cudaMemcpyHostToDevice, c.s[si]));
+  CUDA_TRY(cudaStreamSynchronize(c.s[si]));     // w goes out of scope
+  return SSO_OK;
+}
+
+inline int check_status(Ctx& c, uint32_t* d_status, const char* what, char* err, size_t errcap) {
+  uint32_t h[2] = {0, 0};
+  CUDA_TRY(cudaMemcpy(h, d_status, 8, cudaMemcpyDeviceToHost));
+  if (h[0] != 0) {
+    set_err(err, errcap, "%s: %s (element %u)", what, status_text(h[0]), h[1]);
+    return h[0] == 5u ? SSO_E_VERIFY : SSO_E_INPUT;
+  }
+  return SSO_OK;
+}
+
+inline int sync_all(Ctx& c, char* err, size_t errcap) {
+  for (auto st : c.s) if (st) CUDA_TRY(cudaStreamSynchronize(st));
+  return SSO_OK;
+}
+
+
+}  // namespace sso

@@ -1,0 +1,192 @@
+// Per-thread bodies of the hot-path kernels (the __global__ wrappers live in sso_b200.cu).
+//
+//   K1 tau powers      body_tau_tables / scalar_for_index   (setup_utils::generate_powers_of_tau)
+//   K2 batch_exp       body_batch_exp                        (setup_utils::batch_exp, batch_mul)
+//   K3 read_batch      SW::read_uncompressed / read_compressed + checks
+//   K4 write_batch     body_normalize_write                  (batch normalisation + serialisation)
+// Reference call sites: phase1_cli::contribute at src/bin/contribute.rs:809-824.
+//
+// The bodies take an explicit thread id so that tests/emul can run the very same code under an
+// instruction-level emulation of the PTX carry flag in this GPU-less container.
+#pragma once
+#include "curves.cuh"
+
+namespace sso {
+
+enum : uint32_t { CHECK_NO = 0, CHECK_NONZERO = 1, CHECK_FULL = 2 };   // CheckForCorrectness
+// status codes written by kernels (first failure wins): code in [0], element index in [1]
+enum : uint32_t { ST_OK = 0, ST_NONCANONICAL = 1, ST_BAD_FLAGS = 2, ST_NOT_ON_CURVE = 3, ST_ZERO_POINT = 4,
+                  ST_NOT_IN_SUBGROUP = 5 };
+
+__device__ __forceinline__ void report(uint32_t* status, uint32_t code, uint32_t index) {
+#ifdef SSO_HOST_EMUL
+  if (status[0] == 0) { status[0] = code; status[1] = index; }
+#else
+  if (atomicCAS(&status[0], 0u, code) == 0u) status[1] = index;
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: powers of tau.  Table layout (Montgomery Fr elements, Fr::L words each):
+//   [0..256)    tau^k            [256..512)  tau^(256 k)       [512..768)  tau^(65536 k)
+//   [768]       tau^first_index  [769]       coefficient (alpha / beta / 1)
+// so tau^(first+j) * coeff = T[768] * T[j & 255] * T[256 + ((j >> 8) & 255)] * T[512 + (j >> 16)] * T[769]
+// for j < 2^24: a two/three-level parallel prefix instead of one `pow` per index.
+// ---------------------------------------------------------------------------------------------
+static constexpr int TAU_TABLE_ELEMS = 770;
+
+template <class Fr>
+__device__ __forceinline__ typename Fr::T fr_pow_u64(const typename Fr::T& a, uint64_t e) {
+  typename Fr::T r = Fr::one();
+  for (int i = 63; i >= 0; i--) {
+    r = Fr::sqr(r);
+    if ((e >> i) & 1) r = Fr::mul(r, a);
+  }
+  return r;
+}
+
+// tid in [0, 769): builds one table entry.  tau_canon / coeff_canon: canonical little-endian words.
+template <class Fr>
+__device__ __forceinline__ void body_tau_tables(uint32_t tid, const uint32_t* tau_canon, const uint32_t* coeff_canon,
+                                                uint64_t first_index, uint32_t* table) {
+  typename Fr::T tau = Fr::to_mont(Fr::from_const(tau_canon));
+  typename Fr::T out;
+  if (tid < 768) {
+    uint32_t lvl = tid >> 8, k = tid & 255;
+    out = fr_pow_u64<Fr>(tau, (uint64_t)k << (8 * lvl));
+  } else if (tid == 768) {
+    out = fr_pow_u64<Fr>(tau, first_index);
+  } else {
+    out = Fr::to_mont(Fr::from_const(coeff_canon));
+  }
+  Fr::store(table + (size_t)tid * Fr::L, 1, out);
+}
+
+// canonical scalar for element j of the vector (words in k[0..Fr::L))
+template <class Fr>
+__device__ __forceinline__ void scalar_for_index(const uint32_t* table, uint32_t j, uint32_t n, bool has_coeff, uint32_t* k) {
+  typename Fr::T s = Fr::mul(Fr::load(table + 768 * Fr::L, 1), Fr::load(table + (size_t)(j & 255) * Fr::L, 1));
+  if (n > 256) s = Fr::mul(s, Fr::load(table + (size_t)(256 + ((j >> 8) & 255)) * Fr::L, 1));
+  if (n > 65536) s = Fr::mul(s, Fr::load(table + (size_t)(512 + ((j >> 16) & 255)) * Fr::L, 1));
+  if (has_coeff) s = Fr::mul(s, Fr::load(table + 769 * Fr::L, 1));
+  s = Fr::from_mont(s);
+#pragma unroll
+  for (int i = 0; i < Fr::L; i++) k[i] = s.v[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3 + K2: read one point, validate, multiply by its scalar, leave the Jacobian result in HBM.
+//   in        : n serialized points (uncompressed or compressed), byte-packed as in the chunk file
+//   jac_out   : n * 3 * F::WORDS words, [point][X|Y|Z][limb]
+//   mode      : 0 = scalar from the tau tables (phase 1), 1 = one shared scalar in table[769] (phase 2 batch_mul)
+// ---------------------------------------------------------------------------------------------
+template <class G>
+__device__ __forceinline__ void body_batch_exp(uint32_t tid, uint32_t n, const uint8_t* in, uint32_t in_compressed,
+                                               const uint32_t* table, uint32_t has_coeff, uint32_t mode, uint32_t check,
+                                               uint32_t* jac_out, uint32_t* status) {
+  using C = SW<G>;
+  using F = typename G::F;
+  using Fr = typename G::Fr;
+  if (tid >= n) return;
+  typename C::Affine p;
+  uint32_t st = in_compressed ? C::read_compressed(in + (size_t)tid * C::SIZE_C, p)
+                              : C::read_uncompressed(in + (size_t)tid * C::SIZE_U, p);
+  if (st != C::DESER_OK) { report(status, st, tid); p.inf = true; }
+  if (check != CHECK_NO && st == C::DESER_OK) {
+    if (p.inf) report(status, ST_ZERO_POINT, tid);
+    else if (check == CHECK_FULL && !in_compressed && !C::on_curve(p)) { report(status, ST_NOT_ON_CURVE, tid); p.inf = true; }
+  }
+  uint32_t k[Fr::L];
+  if (mode == 0) {
+    scalar_for_index<Fr>(table, tid, n, has_coeff != 0, k);
+  } else {
+    typename Fr::T s = Fr::from_mont(Fr::load(table + 769 * Fr::L, 1));
+#pragma unroll
+    for (int i = 0; i < Fr::L; i++) k[i] = s.v[i];
+  }
+  typename C::Jac r = C::template scalar_mul<Fr::L, Fr::P::BITS>(p, k);
+  uint32_t* o = jac_out + (size_t)tid * 3 * F::WORDS;
+  F::store(o, 1, r.X);
+  F::store(o + F::WORDS, 1, r.Y);
+  F::store(o + 2 * F::WORDS, 1, r.Z);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: batch normalisation (Montgomery's trick over NB consecutive points per thread: one field
+// inversion per NB points) and serialisation.  tid handles points [tid*NB, tid*NB + NB).
+// ---------------------------------------------------------------------------------------------
+static constexpr int NORM_BATCH = 8;
+
+template <class G>
+__device__ __forceinline__ void body_normalize_write(uint32_t tid, uint32_t n, const uint32_t* jac, uint8_t* out,
+                                                     uint32_t out_compressed) {
+  using C = SW<G>;
+  using F = typename G::F;
+  using FT = typename F::T;
+  uint32_t first = tid * NORM_BATCH;
+  if (first >= n) return;
+  uint32_t cnt = n - first < (uint32_t)NORM_BATCH ? n - first : (uint32_t)NORM_BATCH;
+  FT prefix[NORM_BATCH];
+  FT acc = F::one();
+  for (uint32_t i = 0; i < cnt; i++) {
+    FT z = F::load(jac + ((size_t)(first + i) * 3 + 2) * F::WORDS, 1);
+    prefix[i] = acc;
+    if (!F::is_zero(z)) acc = F::mul(acc, z);
+  }
+  FT inv = F::inv(acc);
+  for (int i = (int)cnt - 1; i >= 0; i--) {
+    const uint32_t* pj = jac + (size_t)(first + i) * 3 * F::WORDS;
+    typename C::Jac p{F::load(pj, 1), F::load(pj + F::WORDS, 1), F::load(pj + 2 * F::WORDS, 1)};
+    typename C::Affine a;
+    if (F::is_zero(p.Z)) {
+      a.inf = true; a.x = F::zero(); a.y = F::zero();
+    } else {
+      FT zinv = F::mul(inv, prefix[i]);
+      inv = F::mul(inv, p.Z);
+      a = C::to_affine_with(p, zinv);
+    }
+    if (out_compressed) C::write_compressed(out + (size_t)(first + i) * C::SIZE_C, a);
+    else C::write_uncompressed(out + (size_t)(first + i) * C::SIZE_U, a);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3 alone: re-encode points (compressed -> uncompressed and so on) with validation — the
+// decompression half of transform_pok_and_correctness / combine.
+//   subgroup != 0 : additionally require [r]P = O
+// Optionally leaves the affine Montgomery coordinates in `aff_out` ([point][x|y] words, inf -> all-zero)
+// for the MSM that follows.
+// ---------------------------------------------------------------------------------------------
+template <class G>
+__device__ __forceinline__ void body_reencode(uint32_t tid, uint32_t n, const uint8_t* in, uint32_t in_compressed,
+                                              uint8_t* out, uint32_t out_compressed, uint32_t check, uint32_t subgroup,
+                                              uint32_t* aff_out, uint32_t* status) {
+  using C = SW<G>;
+  using F = typename G::F;
+  if (tid >= n) return;
+  typename C::Affine p;
+  uint32_t st = in_compressed ? C::read_compressed(in + (size_t)tid * C::SIZE_C, p)
+                              : C::read_uncompressed(in + (size_t)tid * C::SIZE_U, p);
+  if (st != C::DESER_OK) { report(status, st, tid); p.inf = true; p.x = F::zero(); p.y = F::zero(); }
+  else if (check != CHECK_NO) {
+    if (p.inf) report(status, ST_ZERO_POINT, tid);
+    else if (check == CHECK_FULL) {
+      if (!in_compressed && !C::on_curve(p)) report(status, ST_NOT_ON_CURVE, tid);
+      else if (subgroup) {
+        typename C::Jac q = C::mul_const(p, G::order(), (G::Fr::P::BITS + 31) / 32);
+        if (!C::is_identity(q)) report(status, ST_NOT_IN_SUBGROUP, tid);
+      }
+    }
+  }
+  if (out) {
+    if (out_compressed) C::write_compressed(out + (size_t)tid * C::SIZE_C, p);
+    else C::write_uncompressed(out + (size_t)tid * C::SIZE_U, p);
+  }
+  if (aff_out) {
+    uint32_t* o = aff_out + (size_t)tid * 2 * F::WORDS;
+    F::store(o, 1, p.inf ? F::zero() : p.x);
+    F::store(o + F::WORDS, 1, p.inf ? F::zero() : p.y);
+  }
+}
+
+}  // namespace sso

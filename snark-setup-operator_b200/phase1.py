@@ -1,0 +1,147 @@
+"""Host-side mirror of the reference's phase-1 interface over the C ABI.
+
+`Phase1Parameters` follows `phase1::Phase1Parameters` as constructed at reference
+src/utils.rs:326-352 (`new_chunk`, `new_full`); the functions follow the call shapes of
+`phase1_cli::contribute` (src/bin/contribute.rs:809-824) with the RNG-dependent part (key
+generation) factored out: scalars are passed explicitly, as SURVEY.md §8b proposes for the
+`_buf` / `_dev` entry points.  Device buffers are torch uint8 CUDA tensors — torch is only the
+allocator here; every computation happens inside libsso_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+from . import _lib
+from ._lib import P1Params, SsoError, call
+
+CURVES = {"bls12_377": 0, "bw6_761": 1, "bw6": 1, "mnt4_753": 2, "mnt6_753": 3}
+CHECK_NO, CHECK_NONZERO, CHECK_FULL = 0, 1, 2
+G1, G2 = 0, 1
+
+
+def curve_id(curve) -> int:
+    return CURVES[curve] if isinstance(curve, str) else int(curve)
+
+
+def curve_sizes(curve) -> dict:
+    out = (ctypes.c_uint64 * 5)()
+    rc = _lib.lib().sso_curve_sizes(curve_id(curve), out)
+    if rc:
+        raise SsoError(rc, "unknown curve")
+    return {"g1_c": out[0], "g1_u": out[1], "g2_c": out[2], "g2_u": out[3], "fr": out[4]}
+
+
+def scalar_bytes(curve, k: int) -> bytes:
+    return int(k).to_bytes(curve_sizes(curve)["fr"], "little")
+
+
+@dataclass(frozen=True)
+class Phase1Parameters:
+    curve: str
+    power: int
+    chunk_index: int = 0
+    chunk_size: int = 0
+    batch_size: int = 0
+    contribution_mode: int = 0       # 0 chunked, 1 full
+    proving_system: int = 0          # Groth16
+
+    @staticmethod
+    def new_chunk(curve: str, chunk_index: int, chunk_size: int, power: int, batch_size: int) -> "Phase1Parameters":
+        return Phase1Parameters(curve, power, chunk_index, chunk_size, batch_size, 0)
+
+    @staticmethod
+    def new_full(curve: str, power: int, batch_size: int) -> "Phase1Parameters":
+        return Phase1Parameters(curve, power, 0, 0, batch_size, 1)
+
+    def c_struct(self) -> P1Params:
+        return P1Params(curve_id(self.curve), self.proving_system, self.contribution_mode, self.power, self.chunk_index,
+                        self.chunk_size, self.batch_size)
+
+    def sizes(self) -> dict:
+        out = (ctypes.c_uint64 * 8)()
+        call("sso_p1_sizes", ctypes.byref(self.c_struct()), out)
+        keys = ("powers_length", "powers_g1_length", "g1_count", "other_count", "accumulator_size", "contribution_size",
+                "public_key_size", "num_chunks")
+        return dict(zip(keys, out))
+
+    @property
+    def accumulator_size(self) -> int:
+        return self.sizes()["accumulator_size"]
+
+    @property
+    def contribution_size(self) -> int:
+        return self.sizes()["contribution_size"]
+
+
+def _dptr(t) -> int:
+    if not t.is_cuda or not t.is_contiguous():
+        raise ValueError("expected a contiguous CUDA tensor")
+    return t.data_ptr()
+
+
+def _elem_size(curve, group, compressed) -> int:
+    s = curve_sizes(curve)
+    return s[("g1" if group == G1 else "g2") + ("_c" if compressed else "_u")]
+
+
+def batch_exp(curve, group: int, d_in, n: int, first_index: int, tau: int, coeff, d_out, in_compressed=False,
+              out_compressed=True, check=CHECK_NO, device=0):
+    """out[j] = (coeff * tau^(first_index + j)) * in[j] on device buffers (setup_utils::batch_exp)."""
+    assert d_in.numel() == n * _elem_size(curve, group, in_compressed)
+    assert d_out.numel() == n * _elem_size(curve, group, out_compressed)
+    call("sso_batch_exp_dev", curve_id(curve), group, _dptr(d_in), int(in_compressed), n, first_index,
+         scalar_bytes(curve, tau), None if coeff is None else scalar_bytes(curve, coeff), _dptr(d_out),
+         int(out_compressed), check, device)
+
+
+def batch_mul(curve, group: int, d_in, n: int, scalar: int, d_out, in_compressed=False, out_compressed=True,
+              check=CHECK_NO, device=0):
+    """out[j] = scalar * in[j] (phase-2 batch_mul of the H / L queries)."""
+    assert d_in.numel() == n * _elem_size(curve, group, in_compressed)
+    assert d_out.numel() == n * _elem_size(curve, group, out_compressed)
+    call("sso_batch_mul_dev", curve_id(curve), group, _dptr(d_in), int(in_compressed), n, scalar_bytes(curve, scalar),
+         _dptr(d_out), int(out_compressed), check, device)
+
+
+def reencode(curve, group: int, d_in, n: int, d_out, in_compressed=True, out_compressed=False, check=CHECK_FULL,
+             subgroup_check=True, device=0):
+    """Decompress / recompress with the correctness checks of transform_pok_and_correctness."""
+    assert d_in.numel() == n * _elem_size(curve, group, in_compressed)
+    assert d_out.numel() == n * _elem_size(curve, group, out_compressed)
+    call("sso_reencode_dev", curve_id(curve), group, _dptr(d_in), int(in_compressed), n, _dptr(d_out), int(out_compressed),
+         check, int(subgroup_check), device)
+
+
+def contribute_dev(params: Phase1Parameters, d_challenge, d_response, tau: int, alpha: int, beta: int, check=CHECK_NONZERO,
+                   device=0):
+    """Phase1::computation on a device-resident chunk (hash slot and public key untouched)."""
+    assert d_challenge.numel() == params.accumulator_size and d_response.numel() == params.contribution_size
+    c = params.curve
+    call("sso_p1_contribute_dev", ctypes.byref(params.c_struct()), _dptr(d_challenge), _dptr(d_response),
+         scalar_bytes(c, tau), scalar_bytes(c, alpha), scalar_bytes(c, beta), check, device)
+
+
+def _host_ptr(buf):
+    """bytes / bytearray / numpy / pinned CPU torch tensor -> (address, length, keepalive)"""
+    if hasattr(buf, "data_ptr"):
+        return buf.data_ptr(), buf.numel() * buf.element_size(), buf
+    if isinstance(buf, (bytes, bytearray)):
+        arr = (ctypes.c_char * len(buf)).from_buffer(buf) if isinstance(buf, bytearray) else ctypes.c_char_p(buf)
+        return ctypes.cast(arr, ctypes.c_void_p).value, len(buf), arr
+    import numpy as np
+    a = np.ascontiguousarray(buf)
+    return a.ctypes.data, a.nbytes, a
+
+
+def contribute_buf(params: Phase1Parameters, challenge, response, tau: int, alpha: int, beta: int, pubkey: bytes | None = None,
+                   check=CHECK_NONZERO, device=0):
+    """The RNG-free core of phase1_cli::contribute on HOST buffers (H2D, compute, D2H inside).
+    `response` must be a writable buffer of contribution_size bytes."""
+    c = params.curve
+    ch_ptr, ch_len, k1 = _host_ptr(challenge)
+    rs_ptr, rs_len, k2 = _host_ptr(response)
+    call("sso_p1_contribute_buf", ctypes.byref(params.c_struct()), ch_ptr, ch_len, rs_ptr, rs_len, scalar_bytes(c, tau),
+         scalar_bytes(c, alpha), scalar_bytes(c, beta), pubkey, 0 if pubkey is None else len(pubkey), check, device)
+    del k1, k2
+    return response

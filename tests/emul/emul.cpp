@@ -1,0 +1,98 @@
+// TEST-ONLY: runs the per-thread bodies of the CUDA kernels (snark-setup-operator_b200/csrc/*.cuh)
+// on the CPU under an instruction-level emulation of the PTX carry flag, so that the device
+// algorithms can be checked against the oracle in a container without a GPU.  This library is
+// built by tests/test_emul_*.py only; the product library (libsso_b200.so) never contains it
+// and has no CPU path.
+#define SSO_HOST_EMUL 1
+#define __device__
+#define __host__
+#define __global__
+#define __constant__ static const
+#define __forceinline__ inline
+#define __noinline__ __attribute__((noinline))
+#include <cstdint>
+#include <cstddef>
+#include <cstring>
+#include <vector>
+#include "../../snark-setup-operator_b200/csrc/kernels.cuh"
+
+using namespace sso;
+
+template <class F> static int field_op(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+  typename F::T x, y, r;
+  uint32_t fl;
+  if (!F::from_bytes(a, false, fl, x)) return -1;
+  if (!F::from_bytes(b, false, fl, y)) return -1;
+  int rc = 0;
+  switch (op) {
+    case 0: r = F::mul(x, y); break;
+    case 1: r = F::add(x, y); break;
+    case 2: r = F::sub(x, y); break;
+    case 3: r = F::sqr(x); break;
+    case 4: r = F::neg(x); break;
+    case 5: r = F::inv(x); break;
+    case 7: r = x; rc = F::lex_is_neg(x) ? 1 : 0; break;
+    default: return -2;
+  }
+  F::to_bytes(out, r, 0);
+  return rc;
+}
+
+extern "C" int emul_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+  switch (field) {
+    case 0: return field_op<Fr253>(op, a, b, out);
+    case 1: return field_op<Fq377>(op, a, b, out);
+    case 2: return field_op<Fq761>(op, a, b, out);
+    case 3: return field_op<Fq4>(op, a, b, out);
+    case 4: return field_op<Fq6>(op, a, b, out);
+    case 5: return field_op<Fq377x2>(op, a, b, out);
+    case 6: return field_op<Fq4x2>(op, a, b, out);
+    case 7: return field_op<Fq6x3>(op, a, b, out);
+  }
+  return -3;
+}
+
+// out = some sqrt of a (rc 1) or rc 0 if non-square; field ids as above but via the group configs
+template <class G> static int group_sqrt(const uint8_t* a, uint8_t* out) {
+  using F = typename G::F;
+  typename F::T x, r;
+  uint32_t fl;
+  if (!F::from_bytes(a, false, fl, x)) return -1;
+  if (!G::field_sqrt(x, r)) return 0;
+  F::to_bytes(out, r, 0);
+  return 1;
+}
+extern "C" int emul_group_sqrt(uint32_t curve, uint32_t group, const uint8_t* a, uint8_t* out) {
+  int rc = -9;
+  dispatch_group(curve, group, [&](auto g) { rc = group_sqrt<decltype(g)>(a, out); });
+  return rc;
+}
+
+extern "C" int emul_batch_exp(uint32_t curve, uint32_t group, const uint8_t* in, uint32_t in_compressed, uint32_t n,
+                              const uint32_t* tau_canon, const uint32_t* coeff_canon, uint64_t first_index, uint32_t mode,
+                              uint32_t check, uint8_t* out, uint32_t out_compressed, uint32_t* status) {
+  status[0] = status[1] = 0;
+  return dispatch_group(curve, group, [&](auto g) {
+    using G = decltype(g);
+    using Fr = typename G::Fr;
+    using F = typename G::F;
+    std::vector<uint32_t> table((size_t)TAU_TABLE_ELEMS * Fr::L);
+    std::vector<uint32_t> one(Fr::L, 0); one[0] = 1;
+    for (uint32_t t = 0; t < (uint32_t)TAU_TABLE_ELEMS; t++)
+      body_tau_tables<Fr>(t, tau_canon, coeff_canon ? coeff_canon : one.data(), first_index, table.data());
+    std::vector<uint32_t> jac((size_t)n * 3 * F::WORDS);
+    for (uint32_t t = 0; t < n; t++)
+      body_batch_exp<G>(t, n, in, in_compressed, table.data(), coeff_canon != nullptr, mode, check, jac.data(), status);
+    for (uint32_t t = 0; t * NORM_BATCH < n; t++) body_normalize_write<G>(t, n, jac.data(), out, out_compressed);
+  });
+}
+
+extern "C" int emul_reencode(uint32_t curve, uint32_t group, const uint8_t* in, uint32_t in_compressed, uint32_t n,
+                             uint8_t* out, uint32_t out_compressed, uint32_t check, uint32_t subgroup, uint32_t* status) {
+  status[0] = status[1] = 0;
+  return dispatch_group(curve, group, [&](auto g) {
+    using G = decltype(g);
+    for (uint32_t t = 0; t < n; t++)
+      body_reencode<G>(t, n, in, in_compressed, out, out_compressed, check, subgroup, nullptr, status);
+  });
+}

@@ -1,0 +1,132 @@
+"""Runs the per-thread bodies of the CUDA kernels on the CPU (tests/emul/emul.cpp: the same
+.cuh sources compiled by g++ with an instruction-level emulation of the PTX carry flag) and
+compares them with the oracle.  This is how the device algorithms are exercised in the
+GPU-less container; the bit-exact GPU runs are in test_gpu_parity.py."""
+import ctypes
+import os
+import random
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+from oracle import serialize as ser, synth
+from oracle.curves import CURVE_NAMES, get_curve
+
+EMUL_DIR = os.path.join(ROOT, "tests", "emul")
+
+
+@pytest.fixture(scope="module")
+def emul():
+    so = os.path.join(EMUL_DIR, "libsso_emul.so")
+    srcs = [os.path.join(EMUL_DIR, "emul.cpp")] + [os.path.join(ROOT, "snark-setup-operator_b200", "csrc", f)
+                                                    for f in os.listdir(os.path.join(ROOT, "snark-setup-operator_b200", "csrc"))
+                                                    if f.endswith((".cuh", ".h"))]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-o", so, os.path.join(EMUL_DIR, "emul.cpp")])
+    return ctypes.CDLL(so)
+
+
+def words(v, nwords):
+    return (ctypes.c_uint32 * nwords)(*[(v >> (32 * i)) & 0xFFFFFFFF for i in range(nwords)])
+
+
+FIELDS = {0: ("bls12_377", "Fr"), 1: ("bls12_377", "Fq"), 2: ("bw6_761", "Fq"), 3: ("mnt4_753", "Fq"), 4: ("mnt6_753", "Fq"),
+          5: ("bls12_377", "g2"), 6: ("mnt4_753", "g2"), 7: ("mnt6_753", "g2")}
+
+
+def _field(fid):
+    name, which = FIELDS[fid]
+    c = get_curve(name)
+    return c.g2.F if which == "g2" else getattr(c, which)
+
+
+@pytest.mark.parametrize("fid", sorted(FIELDS))
+def test_field_ops(emul, fid):
+    F = _field(fid)
+    rnd = random.Random(fid)
+
+    def relem():
+        return rnd.randrange(F.p) if F.deg == 1 else tuple(rnd.randrange(F.p) for _ in range(F.deg))
+
+    ops = {0: lambda a, b: F.mul(a, b), 1: lambda a, b: F.add(a, b), 2: lambda a, b: F.sub(a, b), 3: lambda a, b: F.sqr(a),
+           4: lambda a, b: F.neg(a), 5: lambda a, b: F.inv(a)}
+    cases = [(relem(), relem()) for _ in range(6)]
+    top = F.p - 1 if F.deg == 1 else (F.p - 1,) * F.deg
+    cases += [(F.zero, relem()), (top, top), (F.one, top)]
+    for a, b in cases:
+        ab, bb = ser.field_to_bytes(F, a), ser.field_to_bytes(F, b)
+        for op, fn in ops.items():
+            if op == 5 and F.is_zero(a):
+                continue
+            out = ctypes.create_string_buffer(len(ab))
+            assert emul.emul_field_op(fid, op, ab, bb, out) == 0
+            assert out.raw == ser.field_to_bytes(F, fn(a, b)), (fid, op)
+        out = ctypes.create_string_buffer(len(ab))
+        assert emul.emul_field_op(fid, 7, ab, ab, out) == (1 if F.gt(a, F.neg(a)) else 0)
+
+
+@pytest.mark.parametrize("name", CURVE_NAMES)
+@pytest.mark.parametrize("gi", [0, 1])
+def test_batch_exp_and_reencode(emul, name, gi):
+    c = get_curve(name)
+    G = (c.g1, c.g2)[gi]
+    if c.Fq.bits > 400 and gi == 1 and name != "bw6_761":
+        n = 3
+    else:
+        n = 4
+    rnd = random.Random(7 * c.cid + gi)
+    Lr = (c.Fr.bits + 31) // 32
+    key = synth.contributor_key(c)
+    pts = [G.mul(G.gen, rnd.randrange(1, G.r)) for _ in range(n - 1)] + [None]
+    buf = ser.points_to_bytes(G, pts, False)
+    first = 1000003
+    want_pts = [G.mul(P, key.beta * pow(key.tau, first + j, c.Fr.p) % c.Fr.p) for j, P in enumerate(pts)]
+    want = ser.points_to_bytes(G, want_pts, True)
+    out = ctypes.create_string_buffer(len(want))
+    st = (ctypes.c_uint32 * 2)()
+    assert emul.emul_batch_exp(c.cid, gi, buf, 0, n, words(key.tau, Lr), words(key.beta, Lr), ctypes.c_uint64(first), 0, 1,
+                               out, 1, st) == 0
+    assert out.raw == want
+    assert list(st) == [4, n - 1]                       # the point at infinity is reported under CHECK_NONZERO
+    # shared-scalar mode (phase-2 batch_mul), uncompressed output
+    want2 = ser.points_to_bytes(G, [G.mul(P, key.alpha) for P in pts], False)
+    out2 = ctypes.create_string_buffer(len(want2))
+    assert emul.emul_batch_exp(c.cid, gi, buf, 0, n, words(1, Lr), words(key.alpha, Lr), ctypes.c_uint64(0), 1, 0, out2, 0,
+                               st) == 0
+    assert out2.raw == want2 and list(st) == [0, 0]
+    # decompression + full checks incl. subgroup membership
+    out3 = ctypes.create_string_buffer(len(buf))
+    assert emul.emul_reencode(c.cid, gi, want, 1, n - 1, out3, 0, 2, 1, st) == 0
+    assert out3.raw[:len(buf) - ser.point_size(G, False)] == ser.points_to_bytes(G, want_pts[:-1], False)
+    assert list(st) == [0, 0]
+
+
+def test_reencode_rejects_bad_points(emul):
+    c = get_curve("bls12_377")
+    G = c.g1
+    from oracle.curves import _some_point
+    rogue = _some_point(G, 11)                           # on the curve, not in the r-torsion
+    st = (ctypes.c_uint32 * 2)()
+    out = ctypes.create_string_buffer(96)
+    emul.emul_reencode(c.cid, 0, ser.point_to_bytes(G, rogue, True), 1, 1, out, 0, 2, 1, st)
+    assert list(st) == [5, 0]
+    emul.emul_reencode(c.cid, 0, ser.point_to_bytes(G, rogue, True), 1, 1, out, 0, 2, 0, st)
+    assert list(st) == [0, 0] and out.raw == ser.point_to_bytes(G, rogue, False)
+    bad = bytearray(ser.point_to_bytes(G, G.gen, True)); bad[-1] |= 0xC0
+    emul.emul_reencode(c.cid, 0, bytes(bad), 1, 1, out, 0, 2, 1, st)
+    assert st[0] == 2
+    noncanon = (c.Fq.p).to_bytes(48, "little")
+    emul.emul_reencode(c.cid, 0, noncanon, 1, 1, out, 0, 2, 1, st)
+    assert st[0] == 1
+    # x with no y on the curve
+    x = 0
+    while G.point_from_x(x, False) is not None:
+        x += 1
+    emul.emul_reencode(c.cid, 0, ser.field_to_bytes(c.Fq, x), 1, 1, out, 0, 2, 1, st)
+    assert st[0] == 3
+    # off-curve uncompressed point
+    offc = ser.field_to_bytes(c.Fq, 5) + ser.field_to_bytes(c.Fq, 7)
+    out2 = ctypes.create_string_buffer(48)
+    emul.emul_reencode(c.cid, 0, offc, 0, 1, out2, 1, 2, 0, st)
+    assert st[0] == 3
