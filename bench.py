@@ -1,0 +1,304 @@
+#!/usr/bin/env python3
+"""Benchmark of the phase-1 hot path (BASELINE.json metric: phase-1 contribute points/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--curve C]
+
+One *step* = Phase1::computation over ONE chunk of the configuration BASELINE.json names for a
+single B200: BLS12-377, 2^20 powers, chunk size 2^16 (262 145 points: 196 608 G1 + 65 537 G2),
+synthetic accumulator (a previous contribution applied to the all-generator accumulator).
+
+  value      points/s with the chunk already resident in HBM (sso_p1_contribute_dev), CUDA events
+  e2e        points/s through the reference-facing host-buffer call (sso_p1_contribute_buf): H2D of
+             the 31 MB challenge, compute, Blake2b hash-chain link, D2H of the 15 MB response
+  roofline   integer-pipe roofline of the dominant kernel (declared multiply-accumulates / event time
+             / measured mad.wide.u32 peak), plus the per-kernel breakdown
+  cpu_baseline  the oracle's C++ restatement of the reference algorithm on the host cores (bounded sample)
+
+N > 1 (torchrun): every rank contributes its own chunk (chunks are independent: no data-path
+collective, weak scaling); time = max over ranks.  --impl reference times the CPU restatement only.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CURVE_BITS = {"bls12_377": (12, 253), "bw6_761": (24, 377), "mnt4_753": (24, 753), "mnt6_753": (24, 753)}
+G2_DEG = {"bls12_377": 2, "bw6_761": 1, "mnt4_753": 2, "mnt6_753": 3}
+A_ZERO = {"bls12_377": True, "bw6_761": True, "mnt4_753": False, "mnt6_753": False}
+
+
+def macs_per_fq_mul(limbs: int) -> int:
+    return 2 * limbs * limbs + limbs            # CIOS on L 32-bit limbs
+
+
+def declared_fq_muls_per_point(curve: str, group: int) -> float:
+    """Closed-form field-multiplication count of k_batch_exp per point:
+    signed 4-bit windows, NW = ceil((bits+2)/4); table = 4 dbl + 3 madd; main loop = 4 (NW-1) dbl +
+    NW * 15/16 full additions; plus 4 multiplications to read the point into Montgomery form.
+    Fq2: mul = 3, sqr = 2 base multiplications; Fq3: mul = sqr = 6."""
+    _, bits = CURVE_BITS[curve]
+    nw = (bits + 2 + 3) // 4
+    deg = G2_DEG[curve] if group == 1 else 1
+    M, S = {1: (1, 1), 2: (3, 2), 3: (6, 6)}[deg]
+    if A_ZERO[curve]:
+        dbl = 2 * M + 5 * S
+    else:
+        dbl = 1 * M + 8 * S                      # dbl-2007-bl: 1M + 8S (+ cheap mul_a)
+    madd = 7 * M + 4 * S
+    add = 11 * M + 5 * S
+    return 4 * dbl + 3 * madd + 4 * (nw - 1) * dbl + nw * (15.0 / 16.0) * add + 4 * deg
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            names = {pynvml.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                     pynvml.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     pynvml.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     pynvml.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+            while not self.stop_flag:
+                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.05)
+        except Exception as e:  # NVML missing: report nothing rather than fail the bench
+            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_reference_run(curve: str, power: int, chunk_log: int, steps: int, warmup: int, target_s: float):
+    """Times the C++ restatement of the reference algorithm (oracle/c) on the host cores on a bounded
+    sample of the workload: a chunk of the same curve and vector mix with fewer points."""
+    from oracle import cport, phase1, synth
+    from oracle.params import Phase1Params
+    threads = cport.hw_threads()
+    # calibrate on 2^6-point vectors, then size the sample for ~target_s per step
+    def one(clog):
+        o = Phase1Params.new_chunk(curve, 1, 1 << clog, clog + 4, 1 << clog)
+        ch = phase1.new_challenge(o)
+        k1 = phase1.PrivateKey(*synth.scalars_from_seed(o.curve, synth.SEED_PREV))
+        t0 = time.perf_counter()
+        cport.contribute_with_key(o, ch, k1, bytes(o.public_key_size), threads=threads)
+        return time.perf_counter() - t0, o.g1_count + 3 * o.other_count + 1
+    t, n = one(8)
+    rate = n / t
+    clog = 8
+    while clog < chunk_log and (4 << (clog + 1)) / rate < target_s:
+        clog += 1
+    times = []
+    for it in range(warmup + steps):
+        t, n = one(clog)
+        if it >= warmup:
+            times.append(t)
+    mean = sum(times) / len(times)
+    return {"value": n / mean, "unit": "points/s", "cores": threads, "kind": "port",
+            "sample": "%s chunk of 2^%d elements per vector (%d points) per step, %d steps; C++ restatement of "
+                      "per-index pow + double-and-add + batch normalisation (oracle/c/oracle.cpp), std::thread over points"
+                      % (curve, clog, n, len(times))}, mean
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--curve", default="bls12_377")
+    ap.add_argument("--power", type=int, default=20)
+    ap.add_argument("--chunk-log", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = "phase-1 %s 2^%d powers, chunk 2^%d: single-chunk contribute" % (args.curve, args.power, args.chunk_log)
+    config = {"workload": workload, "curve": args.curve, "power": args.power, "chunk_size": 1 << args.chunk_log,
+              "sharding": "one chunk per rank, no data-path collective", "l2": "flushed between timed steps (256 MiB write)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb, mean = cpu_reference_run(args.curve, args.power, args.chunk_log, max(1, args.steps), max(0, args.warmup), 6.0)
+        line = {"impl": "reference", "metric": "phase1_contribute_points_per_s", "value": cb["value"], "unit": "points/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 limbs (Montgomery)",
+                "data": "synthetic", "config": config, "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import snark_setup_operator_b200 as sso
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product has no CPU path)")
+    torch.cuda.set_device(local_rank)
+    dev = local_rank
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # ---- synthetic input, built on the device by the product itself (validated by tests/): the
+    # all-generator accumulator, one contribution with the "previous contributor" scalars, decompressed.
+    chunk_index = 1 + rank                      # every rank owns a different (full) chunk
+    cs = 1 << args.chunk_log
+    p = sso.Phase1Parameters.new_chunk(args.curve, chunk_index, cs, args.power, cs)
+    sz = p.sizes()
+    acc, contrib = sz["accumulator_size"], sz["contribution_size"]
+    npts = sz["g1_count"] + 3 * sz["other_count"] + 1
+    from snark_setup_operator_b200.phase1 import curve_sizes
+    es = curve_sizes(args.curve)
+
+    def scalars(seed_byte):
+        # deterministic non-trivial scalars without the oracle: Blake2b of a seed, reduced by truncation
+        import hashlib
+        out = []
+        for i in range(3):
+            h = b"".join(hashlib.blake2b(bytes([seed_byte, i, j]), digest_size=64).digest() for j in range(2))
+            out.append(int.from_bytes(h, "little") >> (1024 - (CURVE_BITS[args.curve][1] - 1)))
+        return out
+
+    prev, mine = scalars(0x5E), scalars(0x01)
+    d_gen = torch.empty(acc, dtype=torch.uint8, device="cuda")
+    sso.new_challenge_dev(p, d_gen, device=dev)
+    d_resp = torch.zeros(contrib, dtype=torch.uint8, device="cuda")
+    sso.contribute_dev(p, d_gen, d_resp, *prev, check=sso.CHECK_NO, device=dev)
+    d_ch = torch.empty(acc, dtype=torch.uint8, device="cuda")
+    d_ch[:64] = d_gen[:64]
+    offs_u = [64]
+    offs_c = [64]
+    counts = (sz["g1_count"], sz["other_count"], sz["other_count"], sz["other_count"], 1)
+    groups = (0, 1, 0, 0, 1)
+    for cnt, g in zip(counts, groups):
+        offs_u.append(offs_u[-1] + cnt * (es["g1_u"] if g == 0 else es["g2_u"]))
+        offs_c.append(offs_c[-1] + cnt * (es["g1_c"] if g == 0 else es["g2_c"]))
+    for i in range(5):
+        if counts[i]:
+            sso.reencode(args.curve, groups[i], d_resp[offs_c[i]:offs_c[i + 1]], counts[i], d_ch[offs_u[i]:offs_u[i + 1]],
+                         check=sso.CHECK_NO, subgroup_check=False, device=dev)
+    del d_gen
+    h_ch = torch.empty(acc, dtype=torch.uint8).pin_memory()
+    h_ch.copy_(d_ch)
+    h_resp = torch.empty(contrib, dtype=torch.uint8).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    pubkey = bytes(sz["public_key_size"])
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run_steps(fn, n, timed):
+        """Each step is bracketed by CUDA events on the current stream; the library call is synchronous
+        (returns when its internal streams drained), so the bracket covers the whole step."""
+        total = 0.0
+        for _ in range(n):
+            flush.zero_()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            total += e0.elapsed_time(e1)
+        return total
+
+    step_dev = lambda: sso.contribute_dev(p, d_ch, d_resp, *mine, check=sso.CHECK_NONZERO, device=dev)
+    step_e2e = lambda: sso.contribute_buf(p, h_ch, h_resp, *mine, pubkey=pubkey, check=sso.CHECK_NONZERO, device=dev)
+
+    # ---- device-resident timing (value) with per-kernel events for the roofline
+    run_steps(step_dev, args.warmup, False)
+    sso.profile_reset()
+    sso.profile_enable(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    ms_total = run_steps(step_dev, args.steps, True)
+    barrier()
+    sso.profile_enable(False)
+    prof = sso.profile_read()
+    # ---- end-to-end timing through the host-buffer entry point
+    run_steps(step_e2e, 1, False)
+    barrier()
+    ms_e2e_total = run_steps(step_e2e, args.steps, True)
+    barrier()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    t = torch.tensor([ms_total, ms_e2e_total], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = t[0].item() / args.steps
+    ms_e2e = t[1].item() / args.steps
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    limbs, _ = CURVE_BITS[args.curve]
+    mac = macs_per_fq_mul(limbs)
+    peak = sso.imad_peak(0, dev)
+    kernels = []
+    for kind, grp in (("batch_exp_g1", 0), ("batch_exp_g2", 1)):
+        k = prof[kind]
+        if k["launches"] and k["ms"] > 0:
+            fm = declared_fq_muls_per_point(args.curve, grp)
+            achieved = k["elems"] * fm * mac / (k["ms"] * 1e-3)
+            kernels.append({"kernel": "k_" + kind, "launches": k["launches"], "ms_total": round(k["ms"], 3),
+                            "points": k["elems"], "fq_muls_per_point": round(fm, 1), "achieved_tmacs": achieved / 1e12,
+                            "frac": achieved / peak})
+    for kind in ("normalize_g1", "normalize_g2", "tau_tables"):
+        k = prof[kind]
+        kernels.append({"kernel": "k_" + kind, "launches": k["launches"], "ms_total": round(k["ms"], 3), "points": k["elems"]})
+    dom = max((k for k in kernels if "frac" in k), key=lambda k: k["ms_total"])
+    launches = sum(v["launches"] for v in prof.values()) // max(1, args.steps)
+    line = {
+        "metric": "phase1_contribute_points_per_s", "value": world * npts / (ms_step * 1e-3), "unit": "points/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (Montgomery, integer pipe)", "data": "synthetic",
+        "config": config,
+        "e2e": {"value": world * npts / (ms_e2e * 1e-3), "unit": "points/s", "h2d_bytes_per_step": acc,
+                "d2h_bytes_per_step": contrib - 64 - sz["public_key_size"], "ms_per_step": ms_e2e},
+        "gpu_launches": launches,
+        "roofline": {"bound": "imad",
+                     "kernel": dom["kernel"], "achieved": dom["achieved_tmacs"], "peak": peak / 1e12, "unit": "TMAC/s",
+                     "frac": dom["frac"], "traffic": None,
+                     "peak_source": "measured live: mad.wide.u32 probe kernel (sso_imad_peak variant 0)",
+                     "macs_per_fq_mul": mac, "kernels": kernels},
+        "clocks": sampler.summary(),
+        "points_per_step": npts,
+    }
+    if not args.no_cpu_baseline:
+        cb, _ = cpu_reference_run(args.curve, args.power, args.chunk_log, 1, 0, 12.0)
+        line["cpu_baseline"] = cb
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

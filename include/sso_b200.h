@@ -123,6 +123,22 @@ int32_t sso_p1_contribute_buf(const sso_p1_params_t* p, const uint8_t* challenge
                               const uint8_t* beta, const uint8_t* pubkey, size_t pubkey_len, uint32_t check_input,
                               int device, char* err, size_t errcap);
 
+/* phase1_cli::new_challenge (reference src/bin/new_setup.rs:105-109, src/bin/verify_transcript.rs:322-326):
+ * the initial accumulator — every element is the group generator, hash slot = Blake2b-512 of the empty
+ * string.  d_challenge: accumulator_size bytes on the device.  NOTE: for MNT4-753 / MNT6-753 G2 the
+ * arkworks generator constant is not recoverable in this environment; a derived order-r point stands
+ * in (DESIGN.md "known gaps"). */
+int32_t sso_p1_new_challenge_dev(const sso_p1_params_t* p, void* d_challenge, int device, char* err, size_t errcap);
+
+/* Kernel accounting.  Launch counts are always kept; with profiling enabled every kernel launch is
+ * bracketed by CUDA events on its own stream.  sso_profile_read fills (launches, nanoseconds, elements)
+ * triples per kernel kind, in the order of SSO_PK_*, and returns the number of kinds. */
+enum { SSO_PK_TAU_TABLES = 0, SSO_PK_BATCH_EXP_G1, SSO_PK_BATCH_EXP_G2, SSO_PK_NORMALIZE_G1, SSO_PK_NORMALIZE_G2,
+       SSO_PK_REENCODE_G1, SSO_PK_REENCODE_G2, SSO_PK_FILL, SSO_PK_MSM, SSO_PK_OTHER, SSO_PK_COUNT };
+int32_t sso_profile_enable(int32_t on);
+int32_t sso_profile_reset(void);
+int32_t sso_profile_read(uint64_t* out, size_t cap);
+
 /* setup_utils::calculate_hash (reference src/utils.rs:618-623): Blake2b-512, unkeyed. Host only. */
 int32_t sso_blake2b_512(const uint8_t* data, size_t len, uint8_t out[64]);
 

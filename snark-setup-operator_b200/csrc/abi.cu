@@ -94,6 +94,11 @@ __global__ void k_imad_probe(uint32_t iters, uint32_t variant, uint32_t seed, ui
   }
 }
 
+namespace sso {
+ProfSlot g_prof[PK_COUNT];
+std::atomic<int> g_prof_enabled{0};
+}  // namespace sso
+
 namespace {
 
 const CurveOps* ops_for(uint32_t curve) {
@@ -283,6 +288,45 @@ int32_t sso_p1_contribute_buf(const sso_p1_params_t* p, const uint8_t* challenge
   CUDA_TRY(cudaMemcpy(response + 64, d_resp + 64, L.off_c[5] - 64, cudaMemcpyDeviceToHost));
   if (pubkey) memcpy(response + L.off_c[5], pubkey, L.pk_size);
   return SSO_OK;
+}
+
+int32_t sso_p1_new_challenge_dev(const sso_p1_params_t* p, void* d_challenge, int device, char* err, size_t errcap) {
+  P1Layout L;
+  int rc = p1_layout(p, L, err, errcap);
+  if (rc) return rc;
+  const CurveOps* ops = ops_for(p->curve);
+  Ctx c(err, errcap);
+  if ((rc = c.init(device, 2))) return rc;
+  uint8_t* d = (uint8_t*)d_challenge;
+  uint8_t blank[64];
+  blake2b_512(nullptr, 0, blank);
+  CUDA_TRY(cudaMemcpyAsync(d, blank, 64, cudaMemcpyHostToDevice, c.s[0]));
+  if ((rc = ops->fill_generator(c, 0, GROUP_G1, L.g1n, d + L.off_u[0], 0, err, errcap))) return rc;
+  if ((rc = ops->fill_generator(c, 1, GROUP_G2, L.on, d + L.off_u[1], 0, err, errcap))) return rc;
+  if ((rc = ops->fill_generator(c, 0, GROUP_G1, 2 * L.on, d + L.off_u[2], 0, err, errcap))) return rc;
+  if ((rc = ops->fill_generator(c, 1, GROUP_G2, 1, d + L.off_u[4], 0, err, errcap))) return rc;
+  return sync_all(c, err, errcap);
+}
+
+int32_t sso_profile_enable(int32_t on) {
+  g_prof_enabled.store(on ? 1 : 0);
+  return SSO_OK;
+}
+
+int32_t sso_profile_reset(void) {
+  for (auto& s : g_prof) { s.launches.store(0); s.ns.store(0); s.elems.store(0); }
+  return SSO_OK;
+}
+
+int32_t sso_profile_read(uint64_t* out, size_t cap) {
+  size_t need = (size_t)PK_COUNT * 3;
+  if (cap < need) return SSO_E_ARG;
+  for (int i = 0; i < PK_COUNT; i++) {
+    out[3 * i] = g_prof[i].launches.load();
+    out[3 * i + 1] = g_prof[i].ns.load();
+    out[3 * i + 2] = g_prof[i].elems.load();
+  }
+  return (int32_t)PK_COUNT;
 }
 
 int32_t sso_imad_peak(int device, int variant, double* macs_per_s, char* err, size_t errcap) {

@@ -3,6 +3,7 @@
 // stream-ordered scratch, so every ABI call is re-entrant — SURVEY.md §8b "Threading").
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -88,11 +89,22 @@ inline const char* status_text(uint32_t code) {
   return "unknown";
 }
 
-// RAII: device selection + stream + stream-ordered scratch
+// Per-kernel launch accounting (always on) and optional CUDA-event timing on the launching stream
+// (sso_profile_enable) — the source of bench.py's roofline.achieved and gpu_launches.
+enum ProfKind { PK_TAU_TABLES = 0, PK_BATCH_EXP_G1, PK_BATCH_EXP_G2, PK_NORMALIZE_G1, PK_NORMALIZE_G2, PK_REENCODE_G1,
+                PK_REENCODE_G2, PK_FILL, PK_MSM, PK_OTHER, PK_COUNT };
+struct ProfSlot { std::atomic<uint64_t> launches{0}; std::atomic<uint64_t> ns{0}; std::atomic<uint64_t> elems{0}; };
+extern ProfSlot g_prof[PK_COUNT];
+extern std::atomic<int> g_prof_enabled;
+
+// RAII: device selection + streams + stream-ordered scratch; one per ABI call (re-entrant)
 struct Ctx {
   int dev = -1, prev = -1;
   cudaStream_t s[2] = {nullptr, nullptr};
   std::vector<void*> allocs;
+  std::vector<std::vector<uint32_t>> staging;     // host copies that must outlive async H2D
+  struct Timed { int kind; cudaEvent_t e0, e1; };
+  std::vector<Timed> timed;
   char* err; size_t errcap;
   Ctx(char* e, size_t c) : err(e), errcap(c) {}
   int init(int device, int nstreams = 1) {
@@ -113,8 +125,35 @@ struct Ctx {
     allocs.push_back(*p);
     return SSO_OK;
   }
+  // bracket a kernel launch: counts it, and times it with events on its own stream when profiling is on
+  void begin(int kind, int si, uint64_t elems) {
+    g_prof[kind].launches.fetch_add(1, std::memory_order_relaxed);
+    g_prof[kind].elems.fetch_add(elems, std::memory_order_relaxed);
+    if (g_prof_enabled.load(std::memory_order_relaxed)) {
+      Timed t{kind, nullptr, nullptr};
+      cudaEventCreate(&t.e0);
+      cudaEventCreate(&t.e1);
+      cudaEventRecord(t.e0, s[si]);
+      timed.push_back(t);
+    }
+  }
+  void end(int si) {
+    if (!timed.empty() && g_prof_enabled.load(std::memory_order_relaxed)) cudaEventRecord(timed.back().e1, s[si]);
+  }
+  void resolve_timings() {
+    for (auto& t : timed) {
+      float ms = 0;
+      if (cudaEventSynchronize(t.e1) == cudaSuccess && cudaEventElapsedTime(&ms, t.e0, t.e1) == cudaSuccess)
+        g_prof[t.kind].ns.fetch_add((uint64_t)(ms * 1e6), std::memory_order_relaxed);
+      cudaEventDestroy(t.e0);
+      cudaEventDestroy(t.e1);
+    }
+    timed.clear();
+  }
   ~Ctx() {
     if (dev >= 0) {
+      for (auto& st : s) if (st) cudaStreamSynchronize(st);
+      resolve_timings();
       for (void* p : allocs) cudaFreeAsync(p, s[0]);
       for (auto& st : s) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
       if (prev >= 0) cudaSetDevice(prev);
@@ -126,13 +165,13 @@ inline uint32_t div_up(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) /
 
 // canonical little-endian scalar bytes -> zero-padded words on the device
 inline int upload_scalar(Ctx& c, const uint8_t* bytes, size_t nbytes, size_t nwords, uint32_t** d_out, int si, char* err, size_t errcap) {
-  std::vector<uint32_t> w(nwords, 0);
+  c.staging.emplace_back(nwords, 0u);
+  std::vector<uint32_t>& w = c.staging.back();    // kept alive by the context until the call ends
   if (bytes) memcpy(w.data(), bytes, nbytes);
   else w[0] = 1;
   int rc = c.alloc((void**)d_out, nwords * 4, si);
   if (rc) return rc;
   CUDA_TRY(cudaMemcpyAsync(*d_out, w.data(), nwords * 4, cudaMemcpyHostToDevice, c.s[si]));
-  CUDA_TRY(cudaStreamSynchronize(c.s[si]));     // w goes out of scope
   return SSO_OK;
 }
 
@@ -148,6 +187,7 @@ inline int check_status(Ctx& c, uint32_t* d_status, const char* what, char* err,
 
 inline int sync_all(Ctx& c, char* err, size_t errcap) {
   for (auto st : c.s) if (st) CUDA_TRY(cudaStreamSynchronize(st));
+  c.resolve_timings();
   return SSO_OK;
 }
 

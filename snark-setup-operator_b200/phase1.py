@@ -145,3 +145,37 @@ def contribute_buf(params: Phase1Parameters, challenge, response, tau: int, alph
          scalar_bytes(c, alpha), scalar_bytes(c, beta), pubkey, 0 if pubkey is None else len(pubkey), check, device)
     del k1, k2
     return response
+
+
+def new_challenge_dev(params: Phase1Parameters, d_challenge, device=0):
+    """phase1_cli::new_challenge on a device buffer (all-generator accumulator, blank hash)."""
+    assert d_challenge.numel() == params.accumulator_size
+    call("sso_p1_new_challenge_dev", ctypes.byref(params.c_struct()), _dptr(d_challenge), device)
+
+
+PROFILE_KINDS = ("tau_tables", "batch_exp_g1", "batch_exp_g2", "normalize_g1", "normalize_g2", "reencode_g1", "reencode_g2",
+                 "fill", "msm", "other")
+
+
+def profile_enable(on: bool = True):
+    _lib.lib().sso_profile_enable(1 if on else 0)
+
+
+def profile_reset():
+    _lib.lib().sso_profile_reset()
+
+
+def profile_read() -> dict:
+    """{kind: {"launches": n, "ms": total device milliseconds (0 unless profiling), "elems": n}}"""
+    out = (ctypes.c_uint64 * (3 * 16))()
+    n = _lib.lib().sso_profile_read(out, len(out))
+    if n < 0:
+        raise SsoError(n, "profile buffer too small")
+    return {PROFILE_KINDS[i]: {"launches": out[3 * i], "ms": out[3 * i + 1] / 1e6, "elems": out[3 * i + 2]} for i in range(n)}
+
+
+def imad_peak(variant: int = 0, device=0) -> float:
+    """Measured multiply-accumulate peak (MAC/s) of the probe kernel; variant 0 = mad.wide.u32."""
+    out = ctypes.c_double(0)
+    call("sso_imad_peak", device, variant, ctypes.byref(out))
+    return out.value
