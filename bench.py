@@ -233,9 +233,10 @@ def main():
     # ---- device-resident timing (value) with per-kernel events for the roofline
     run_steps(step_dev, args.warmup, False)
     sso.profile_reset()
-    sso.profile_enable(True)
+    sso.profile_enable(not os.environ.get("SSO_BENCH_NOPROF"))
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if not os.environ.get("SSO_BENCH_NOSAMPLER"):
+        sampler.start()
     barrier()
     ms_total = run_steps(step_dev, args.steps, True)
     barrier()
@@ -247,7 +248,8 @@ def main():
     ms_e2e_total = run_steps(step_e2e, args.steps, True)
     barrier()
     sampler.stop_flag = True
-    sampler.join(timeout=2)
+    if sampler.is_alive():
+        sampler.join(timeout=2)
 
     t = torch.tensor([ms_total, ms_e2e_total], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -274,7 +276,7 @@ def main():
     for kind in ("normalize_g1", "normalize_g2", "tau_tables"):
         k = prof[kind]
         kernels.append({"kernel": "k_" + kind, "launches": k["launches"], "ms_total": round(k["ms"], 3), "points": k["elems"]})
-    dom = max((k for k in kernels if "frac" in k), key=lambda k: k["ms_total"])
+    dom = max((k for k in kernels if "frac" in k), key=lambda k: k["ms_total"], default={"kernel": None, "achieved_tmacs": None, "frac": None})
     launches = sum(v["launches"] for v in prof.values()) // max(1, args.steps)
     line = {
         "metric": "phase1_contribute_points_per_s", "value": world * npts / (ms_step * 1e-3), "unit": "points/s",

@@ -111,25 +111,58 @@ const CurveOps* ops_for(uint32_t curve) {
   return nullptr;
 }
 
-// Phase1::computation on the five vectors of one chunk; G1 vectors on stream 0, G2 on stream 1.
+inline VecSeg seg(const uint8_t* in, uint8_t* out, uint64_t n, uint32_t slot, uint32_t has_coeff, uint32_t mode) {
+  VecSeg s;
+  s.in = in; s.out = out; s.n = (uint32_t)n; s.coeff_slot = slot; s.has_coeff = has_coeff; s.mode = mode;
+  return s;
+}
+inline VecBatch batch_of(std::initializer_list<VecSeg> segs) {
+  VecBatch b;
+  memset(&b, 0, sizeof b);
+  for (const VecSeg& s : segs) {
+    if (s.n == 0) continue;
+    b.seg[b.nseg++] = s;
+    b.total += s.n;
+  }
+  return b;
+}
+
+// Phase1::computation on the five vectors of one chunk: ONE tau-table launch, ONE launch pair for the
+// three G1 vectors (stream 0) and ONE for tauG2 + betaG2 (stream 1).  Coefficient slots: 0 = 1, 1 = alpha, 2 = beta.
 int p1_contribute_streams(Ctx& c, const CurveOps* ops, const P1Layout& L, const uint8_t* d_ch, uint8_t* d_resp,
                           const uint8_t* tau, const uint8_t* alpha, const uint8_t* beta, uint32_t check, uint32_t* d_status,
                           char* err, size_t errcap) {
   int rc;
-  if ((rc = ops->batch_exp(c, 0, GROUP_G1, d_ch + L.off_u[0], 0, L.g1n, L.start, tau, nullptr, 0, d_resp + L.off_c[0], 1, check, d_status, err, errcap))) return rc;
-  if ((rc = ops->batch_exp(c, 1, GROUP_G2, d_ch + L.off_u[1], 0, L.on, L.start, tau, nullptr, 0, d_resp + L.off_c[1], 1, check, d_status, err, errcap))) return rc;
-  if ((rc = ops->batch_exp(c, 0, GROUP_G1, d_ch + L.off_u[2], 0, L.on, L.start, tau, alpha, 0, d_resp + L.off_c[2], 1, check, d_status, err, errcap))) return rc;
-  if ((rc = ops->batch_exp(c, 0, GROUP_G1, d_ch + L.off_u[3], 0, L.on, L.start, tau, beta, 0, d_resp + L.off_c[3], 1, check, d_status, err, errcap))) return rc;
-  // beta_g2 *= beta : one element, shared-scalar mode
-  std::vector<uint8_t> one(ops->fr_bytes, 0);
-  one[0] = 1;
-  return ops->batch_exp(c, 1, GROUP_G2, d_ch + L.off_u[4], 0, 1, 0, one.data(), beta, 1, d_resp + L.off_c[4], 1, check, d_status, err, errcap);
+  const uint8_t* coeffs[TAU_COEFF_SLOTS] = {nullptr, alpha, beta};
+  uint32_t* d_table;
+  if ((rc = ops->tau_tables(c, 0, L.start, tau, coeffs, &d_table, err, errcap))) return rc;
+  if ((rc = c.fork(0, 1))) return rc;
+  VecBatch g2 = batch_of({seg(d_ch + L.off_u[1], d_resp + L.off_c[1], L.on, 0, 0, 0),
+                          seg(d_ch + L.off_u[4], d_resp + L.off_c[4], 1, 2, 1, 1)});
+  VecBatch g1 = batch_of({seg(d_ch + L.off_u[0], d_resp + L.off_c[0], L.g1n, 0, 0, 0),
+                          seg(d_ch + L.off_u[2], d_resp + L.off_c[2], L.on, 1, 1, 0),
+                          seg(d_ch + L.off_u[3], d_resp + L.off_c[3], L.on, 2, 1, 0)});
+  // the G2 launch holds the longest-running threads: enqueue it first
+  if ((rc = ops->batch_exp(c, 1, GROUP_G2, g2, 0, d_table, 1, check, d_status, err, errcap))) return rc;
+  return ops->batch_exp(c, 0, GROUP_G1, g1, 0, d_table, 1, check, d_status, err, errcap);
+}
+
+// one vector, one scalar rule
+int single_vector(Ctx& c, const CurveOps* ops, uint32_t group, const uint8_t* d_in, uint32_t in_compressed, uint64_t n,
+                  uint64_t first_index, const uint8_t* tau, const uint8_t* coeff, uint32_t mode, uint8_t* d_out,
+                  uint32_t out_compressed, uint32_t check, uint32_t* d_status, char* err, size_t errcap) {
+  int rc;
+  const uint8_t* coeffs[TAU_COEFF_SLOTS] = {coeff, nullptr, nullptr};
+  uint32_t* d_table;
+  if ((rc = ops->tau_tables(c, 0, first_index, tau, coeffs, &d_table, err, errcap))) return rc;
+  VecBatch b = batch_of({seg(d_in, d_out, n, 0, coeff != nullptr, mode)});
+  return ops->batch_exp(c, 0, group, b, in_compressed, d_table, out_compressed, check, d_status, err, errcap);
 }
 
 int status_buffer(Ctx& c, uint32_t** d_status, char* err, size_t errcap) {
-  int rc = c.alloc((void**)d_status, 8);
+  int rc = c.alloc((void**)d_status, STATUS_BYTES);
   if (rc) return rc;
-  CUDA_TRY(cudaMemsetAsync(*d_status, 0, 8, c.s[0]));
+  CUDA_TRY(cudaMemsetAsync(*d_status, 0, STATUS_BYTES, c.s[0]));
   CUDA_TRY(cudaStreamSynchronize(c.s[0]));
   return SSO_OK;
 }
@@ -193,8 +226,9 @@ int32_t sso_batch_exp_dev(uint32_t curve, uint32_t group, const void* d_in, uint
   if (rc) return rc;
   uint32_t* d_status;
   if ((rc = status_buffer(c, &d_status, err, errcap))) return rc;
-  if ((rc = ops->batch_exp(c, 0, group, (const uint8_t*)d_in, in_compressed, n, first_index, tau, coeff, 0, (uint8_t*)d_out,
-                           out_compressed, check_input, d_status, err, errcap))) return rc;
+  if (group > 1) { set_err(err, errcap, "unknown group %u", group); return SSO_E_ARG; }
+  if ((rc = single_vector(c, ops, group, (const uint8_t*)d_in, in_compressed, n, first_index, tau, coeff, 0, (uint8_t*)d_out,
+                          out_compressed, check_input, d_status, err, errcap))) return rc;
   if ((rc = sync_all(c, err, errcap))) return rc;
   return check_status(c, d_status, "batch_exp input", err, errcap);
 }
@@ -209,6 +243,7 @@ int32_t sso_batch_mul_dev(uint32_t curve, uint32_t group, const void* d_in, uint
   if (rc) return rc;
   uint32_t* d_status;
   if ((rc = status_buffer(c, &d_status, err, errcap))) return rc;
+  if (group > 1) { set_err(err, errcap, "unknown group %u", group); return SSO_E_ARG; }
   std::vector<uint8_t> one(ops->fr_bytes, 0);
   one[0] = 1;
   // vectors longer than the table span are processed in segments (the scalar is index-independent)
@@ -219,8 +254,8 @@ int32_t sso_batch_mul_dev(uint32_t curve, uint32_t group, const void* d_in, uint
   const uint64_t SEG = 1ull << 22;
   for (uint64_t off = 0; off < n; off += SEG) {
     uint64_t m = n - off < SEG ? n - off : SEG;
-    if ((rc = ops->batch_exp(c, 0, group, (const uint8_t*)d_in + off * in_sz, in_compressed, m, 0, one.data(), scalar, 1,
-                             (uint8_t*)d_out + off * out_sz, out_compressed, check_input, d_status, err, errcap))) return rc;
+    if ((rc = single_vector(c, ops, group, (const uint8_t*)d_in + off * in_sz, in_compressed, m, 0, one.data(), scalar, 1,
+                            (uint8_t*)d_out + off * out_sz, out_compressed, check_input, d_status, err, errcap))) return rc;
   }
   if ((rc = sync_all(c, err, errcap))) return rc;
   return check_status(c, d_status, "batch_mul input", err, errcap);
@@ -278,14 +313,19 @@ int32_t sso_p1_contribute_buf(const sso_p1_params_t* p, const uint8_t* challenge
   if ((rc = c.alloc((void**)&d_ch, L.acc_size))) return rc;
   if ((rc = c.alloc((void**)&d_resp, L.contrib_size))) return rc;
   if ((rc = status_buffer(c, &d_status, err, errcap))) return rc;
+  c.mark("scratch allocated");
   CUDA_TRY(cudaMemcpyAsync(d_ch, challenge, L.acc_size, cudaMemcpyHostToDevice, c.s[0]));
   CUDA_TRY(cudaStreamSynchronize(c.s[0]));
+  c.mark("challenge H2D");
   if ((rc = p1_contribute_streams(c, ops, L, d_ch, d_resp, tau, alpha, beta, check_input, d_status, err, errcap))) return rc;
+  c.mark("kernels enqueued");
   // the hash-chain link is computed on the host while the GPU works
   blake2b_512(challenge, challenge_len, response);
+  c.mark("blake2b(challenge)");
   if ((rc = sync_all(c, err, errcap))) return rc;
   if ((rc = check_status(c, d_status, "challenge", err, errcap))) return rc;
   CUDA_TRY(cudaMemcpy(response + 64, d_resp + 64, L.off_c[5] - 64, cudaMemcpyDeviceToHost));
+  c.mark("response D2H");
   if (pubkey) memcpy(response + L.off_c[5], pubkey, L.pk_size);
   return SSO_OK;
 }

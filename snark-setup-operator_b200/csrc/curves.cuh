@@ -28,6 +28,8 @@ using Fq6x3 = Fp3<Fq6, SmallNR<Fq6, 11, false>>;          // u^3 = 11
   __device__ __forceinline__ static typename F::T gen_y() { return F::from_const(c_##NAME##_gy); }
 
 struct Bls12_377_G1 {
+  static constexpr bool HAS_GLV = true;
+  using Glv = GLV_bls12_377_g1;
   static constexpr uint32_t GROUP = 0;
   SSO_GROUP_COMMON(bls12_377_g1, Fq377, Fr253)
   static constexpr bool A_IS_ZERO = true;
@@ -35,6 +37,8 @@ struct Bls12_377_G1 {
   __device__ __forceinline__ static bool field_sqrt(const F::T& a, F::T& o) { return F::sqrt(a, o); }
 };
 struct Bls12_377_G2 {
+  static constexpr bool HAS_GLV = true;
+  using Glv = GLV_bls12_377_g2;
   static constexpr uint32_t GROUP = 1;
   SSO_GROUP_COMMON(bls12_377_g2, Fq377x2, Fr253)
   static constexpr bool A_IS_ZERO = true;
@@ -42,6 +46,8 @@ struct Bls12_377_G2 {
   __device__ __forceinline__ static bool field_sqrt(const F::T& a, F::T& o) { return F::sqrt(a, o); }
 };
 struct Bw6_761_G1 {
+  static constexpr bool HAS_GLV = true;
+  using Glv = GLV_bw6_761_g1;
   static constexpr uint32_t GROUP = 0;
   SSO_GROUP_COMMON(bw6_761_g1, Fq761, Fq377)
   static constexpr bool A_IS_ZERO = true;
@@ -49,6 +55,8 @@ struct Bw6_761_G1 {
   __device__ __forceinline__ static bool field_sqrt(const F::T& a, F::T& o) { return F::sqrt(a, o); }
 };
 struct Bw6_761_G2 {
+  static constexpr bool HAS_GLV = true;
+  using Glv = GLV_bw6_761_g2;
   static constexpr uint32_t GROUP = 1;
   SSO_GROUP_COMMON(bw6_761_g2, Fq761, Fq377)
   static constexpr bool A_IS_ZERO = true;
@@ -56,6 +64,7 @@ struct Bw6_761_G2 {
   __device__ __forceinline__ static bool field_sqrt(const F::T& a, F::T& o) { return F::sqrt(a, o); }
 };
 struct Mnt4_753_G1 {
+  static constexpr bool HAS_GLV = false;
   static constexpr uint32_t GROUP = 0;                                         // a = 2
   SSO_GROUP_COMMON(mnt4_753_g1, Fq4, Fq6)
   static constexpr bool A_IS_ZERO = false;
@@ -63,6 +72,7 @@ struct Mnt4_753_G1 {
   __device__ __forceinline__ static bool field_sqrt(const F::T& a, F::T& o) { return F::sqrt(a, o); }
 };
 struct Mnt4_753_G2 {
+  static constexpr bool HAS_GLV = false;
   static constexpr uint32_t GROUP = 1;                                         // a' = (26, 0)
   SSO_GROUP_COMMON(mnt4_753_g2, Fq4x2, Fq6)
   static constexpr bool A_IS_ZERO = false;
@@ -70,6 +80,7 @@ struct Mnt4_753_G2 {
   __device__ __forceinline__ static bool field_sqrt(const F::T& a, F::T& o) { return F::sqrt(a, o); }
 };
 struct Mnt6_753_G1 {
+  static constexpr bool HAS_GLV = false;
   static constexpr uint32_t GROUP = 0;                                         // a = 11
   SSO_GROUP_COMMON(mnt6_753_g1, Fq6, Fq4)
   static constexpr bool A_IS_ZERO = false;
@@ -77,6 +88,7 @@ struct Mnt6_753_G1 {
   __device__ __forceinline__ static bool field_sqrt(const F::T& a, F::T& o) { return F::sqrt(a, o); }
 };
 struct Mnt6_753_G2 {
+  static constexpr bool HAS_GLV = false;
   static constexpr uint32_t GROUP = 1;                                         // a' = (0, 0, 11) = 11 u^2, u^3 = 11
   SSO_GROUP_COMMON(mnt6_753_g2, Fq6x3, Fq4)
   static constexpr bool A_IS_ZERO = false;

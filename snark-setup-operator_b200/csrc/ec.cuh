@@ -122,32 +122,28 @@ template <class Cfg> struct SW {
     return r;
   }
 
-  // Signed fixed-window scalar multiplication.  `k` = canonical scalar, KL little-endian words,
-  // value < 2^KBITS; the bias trick k' = k + 0x88..8 makes every window digit = nibble(k') - 8
-  // with no carry propagation, so digits can be read MSB-first.
-  template <int KL, int KBITS>
-  __device__ __forceinline__ static Jac scalar_mul(const Affine& base, const uint32_t* k) {
-    constexpr int NW = (KBITS + 2 + 3) / 4;                 // 4*NW >= KBITS + 2
-    constexpr int BL = (4 * NW + 31) / 32;                  // words of the biased scalar
-    static_assert(BL >= KL, "window count must cover the scalar");
-    if (base.inf) return identity();
-    // biased scalar
-    uint32_t kb[BL];
-    {
-      uint32_t carry = 0;
+  // ---- signed fixed-window machinery -------------------------------------------------------------
+  // The bias trick k' = k + 0x88..8 (one 8 per window) makes every window digit = nibble(k') - 8 in
+  // [-8, 7] with no carry propagation, so digits can be read MSB-first.  NW windows need 4 NW >= bits + 2.
+  template <int KL, int NW>
+  __device__ __forceinline__ static void bias_scalar(const uint32_t* k, uint32_t* kb) {
+    constexpr int BL = (4 * NW + 31) / 32;
+    uint32_t carry = 0;
 #pragma unroll
-      for (int i = 0; i < BL; i++) {
-        uint32_t ki = i < KL ? k[i] : 0u;
-        int lo = 32 * i, hi = 32 * i + 32;
-        uint32_t c = 0x88888888u;
-        if (4 * NW < hi) c = (4 * NW <= lo) ? 0u : (0x88888888u & ((1u << (4 * NW - lo)) - 1u));
-        uint64_t s = (uint64_t)ki + c + carry;
-        kb[i] = (uint32_t)s;
-        carry = (uint32_t)(s >> 32);
-      }
+    for (int i = 0; i < BL; i++) {
+      uint32_t ki = i < KL ? k[i] : 0u;
+      int lo = 32 * i, hi = 32 * i + 32;
+      uint32_t c = 0x88888888u;
+      if (4 * NW < hi) c = (4 * NW <= lo) ? 0u : (0x88888888u & ((1u << (4 * NW - lo)) - 1u));
+      uint64_t s = (uint64_t)ki + c + carry;
+      kb[i] = (uint32_t)s;
+      carry = (uint32_t)(s >> 32);
     }
-    // table 1P .. 8P
-    Jac tab[8];
+  }
+  __device__ __forceinline__ static int digit(const uint32_t* kb, int w) { return (int)((kb[w >> 3] >> ((w & 7) * 4)) & 15u) - 8; }
+
+  // table 1P .. 8P (Jacobian): 4 dbl + 3 madd
+  __device__ __forceinline__ static void build_table(const Affine& base, Jac* tab) {
     tab[0] = Jac{base.x, base.y, F::one()};
     tab[1] = dbl(tab[0]);
     tab[2] = madd(tab[1], base);
@@ -156,6 +152,19 @@ template <class Cfg> struct SW {
     tab[5] = dbl(tab[2]);
     tab[6] = madd(tab[5], base);
     tab[7] = dbl(tab[3]);
+  }
+
+  // `k` = canonical scalar, KL little-endian words, value < 2^KBITS
+  template <int KL, int KBITS>
+  __device__ __forceinline__ static Jac scalar_mul(const Affine& base, const uint32_t* k) {
+    constexpr int NW = (KBITS + 2 + 3) / 4;
+    constexpr int BL = (4 * NW + 31) / 32;
+    static_assert(BL >= KL, "window count must cover the scalar");
+    if (base.inf) return identity();
+    uint32_t kb[BL];
+    bias_scalar<KL, NW>(k, kb);
+    Jac tab[8];
+    build_table(base, tab);
     Jac acc = identity();
 #pragma unroll 1
     for (int w = NW - 1; w >= 0; w--) {
@@ -163,12 +172,101 @@ template <class Cfg> struct SW {
 #pragma unroll 1
         for (int d = 0; d < 4; d++) acc = dbl(acc);
       }
-      int nib = (int)((kb[w >> 3] >> ((w & 7) * 4)) & 15u);
-      int dgt = nib - 8;
+      int dgt = digit(kb, w);
       if (dgt != 0) {
-        int idx = (dgt < 0 ? -dgt : dgt) - 1;
-        Jac q = tab[idx];
+        Jac q = tab[(dgt < 0 ? -dgt : dgt) - 1];
         if (dgt < 0) q.Y = F::neg(q.Y);
+        acc = add(acc, q);
+      }
+    }
+    return acc;
+  }
+
+  // ---- GLV (j = 0 curves): k = k1 + k2 lambda with |k1|, |k2| < 2^KBITS ~ sqrt(r), and
+  // [k]P = [k1]P + [k2]phi(P), phi(x, y) = (beta x, y).  Halves the number of doublings.
+  // low OUT words of a (NA words) * b (NB words)
+  template <int NA, int NB, int OUT>
+  __device__ __forceinline__ static void mul_low(const uint32_t* a, const uint32_t* b, uint32_t* out) {
+#pragma unroll
+    for (int i = 0; i < OUT; i++) out[i] = 0;
+#pragma unroll
+    for (int i = 0; i < NA; i++) {
+      uint32_t carry = 0;
+#pragma unroll
+      for (int j = 0; j < NB; j++) {
+        if (i + j < OUT) {
+          uint64_t t = (uint64_t)a[i] * b[j] + out[i + j] + carry;
+          out[i + j] = (uint32_t)t;
+          carry = (uint32_t)(t >> 32);
+        }
+      }
+      if (i + NB < OUT) out[i + NB] = carry;
+    }
+  }
+  template <class GLV, int KL>
+  __device__ __forceinline__ static void glv_split(const uint32_t* k, uint32_t* k1, uint32_t* k2, bool& neg1, bool& neg2) {
+    constexpr int KW = GLV::KW, GL = GLV::GL, SW = GLV::SH_WORDS;
+    uint32_t prod[KL + GL], c1[KW], c2[KW], t[KW];
+    mul_low<KL, GL, KL + GL>(k, GLV::g1(), prod);
+#pragma unroll
+    for (int i = 0; i < KW; i++) c1[i] = SW + i < KL + GL ? prod[SW + i] : 0u;
+    mul_low<KL, GL, KL + GL>(k, GLV::g2(), prod);
+#pragma unroll
+    for (int i = 0; i < KW; i++) c2[i] = SW + i < KL + GL ? prod[SW + i] : 0u;
+    // k1 = k - c1 a1 - c2 a2 ; k2 = -c1 b1 - c2 b2   (mod 2^(32 KW), two's complement)
+#pragma unroll
+    for (int i = 0; i < KW; i++) k1[i] = i < KL ? k[i] : 0u;
+    mul_low<KW, KW, KW>(c1, GLV::a1(), t); limbs_sub<KW>(k1, k1, t);
+    mul_low<KW, KW, KW>(c2, GLV::a2(), t); limbs_sub<KW>(k1, k1, t);
+#pragma unroll
+    for (int i = 0; i < KW; i++) k2[i] = 0u;
+    mul_low<KW, KW, KW>(c1, GLV::b1(), t); limbs_sub<KW>(k2, k2, t);
+    mul_low<KW, KW, KW>(c2, GLV::b2(), t); limbs_sub<KW>(k2, k2, t);
+    uint32_t z[KW];
+#pragma unroll
+    for (int i = 0; i < KW; i++) z[i] = 0u;
+    neg1 = (k1[KW - 1] >> 31) != 0;
+    neg2 = (k2[KW - 1] >> 31) != 0;
+    if (neg1) limbs_sub<KW>(k1, z, k1);
+    if (neg2) limbs_sub<KW>(k2, z, k2);
+  }
+  __device__ __forceinline__ static FT mul_beta(const FT& x, const uint32_t* beta) {
+    typename F::Base::T b = F::Base::from_const(beta);
+    if constexpr (F::DEG == 1) return F::mul(x, b);
+    else return F::mul_base(x, b);
+  }
+
+  template <class GLV, int KL>
+  __device__ __forceinline__ static Jac scalar_mul_glv(const Affine& base, const uint32_t* k) {
+    constexpr int KW = GLV::KW;
+    constexpr int NW = (GLV::KBITS + 2 + 3) / 4;
+    constexpr int BL = (4 * NW + 31) / 32;
+    static_assert(BL >= KW, "window count must cover the half-size scalars");
+    if (base.inf) return identity();
+    uint32_t k1[KW], k2[KW], kb1[BL], kb2[BL];
+    bool neg1, neg2;
+    glv_split<GLV, KL>(k, k1, k2, neg1, neg2);
+    bias_scalar<KW, NW>(k1, kb1);
+    bias_scalar<KW, NW>(k2, kb2);
+    Jac tab[8];
+    build_table(base, tab);
+    Jac acc = identity();
+#pragma unroll 1
+    for (int w = NW - 1; w >= 0; w--) {
+      if (w != NW - 1) {
+#pragma unroll 1
+        for (int d = 0; d < 4; d++) acc = dbl(acc);
+      }
+      int d1 = digit(kb1, w), d2 = digit(kb2, w);
+      if (d1 != 0) {
+        Jac q = tab[(d1 < 0 ? -d1 : d1) - 1];
+        if ((d1 < 0) != neg1) q.Y = F::neg(q.Y);
+        acc = add(acc, q);
+      }
+      if (d2 != 0) {
+        Jac q = tab[(d2 < 0 ? -d2 : d2) - 1];
+        q.X = mul_beta(q.X, GLV::beta());
+        if ((d2 < 0) != neg2) q.Y = F::neg(q.Y);
         acc = add(acc, q);
       }
     }

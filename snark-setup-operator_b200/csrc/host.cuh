@@ -4,6 +4,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <atomic>
+#include <chrono>
+#include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -106,7 +108,22 @@ struct Ctx {
   struct Timed { int kind; cudaEvent_t e0, e1; };
   std::vector<Timed> timed;
   char* err; size_t errcap;
-  Ctx(char* e, size_t c) : err(e), errcap(c) {}
+  // SSO_TRACE=1: host-side timeline of the call on stderr (debugging aid)
+  bool trace = false;
+  std::chrono::steady_clock::time_point t_start, t_last;
+  void mark(const char* what) {
+    if (!trace) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[sso trace] %-28s +%8.3f ms (total %8.3f ms)\n", what,
+            std::chrono::duration<double, std::milli>(now - t_last).count(),
+            std::chrono::duration<double, std::milli>(now - t_start).count());
+    t_last = now;
+  }
+  Ctx(char* e, size_t c) : err(e), errcap(c) {
+    const char* tr = getenv("SSO_TRACE");
+    trace = tr && tr[0] == '1';
+    t_start = t_last = std::chrono::steady_clock::now();
+  }
   int init(int device, int nstreams = 1) {
     int cnt = 0;
     if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) {
@@ -117,12 +134,34 @@ struct Ctx {
     cudaGetDevice(&prev);
     CUDA_TRY(cudaSetDevice(device));
     dev = device;
+    // keep stream-ordered scratch cached in the device's default pool between calls: with the default
+    // release threshold (0) every synchronisation hands the memory back to the driver and the next
+    // call pays tens of milliseconds to map it again (measured: 5-80 ms per call on B200)
+    static std::atomic<uint64_t> pool_configured{0};
+    if (device < 64 && !(pool_configured.load() & (1ull << device))) {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      pool_configured.fetch_or(1ull << device);
+    }
     for (int i = 0; i < nstreams; i++) CUDA_TRY(cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking));
+    mark("init: device + streams");
     return SSO_OK;
   }
   int alloc(void** p, size_t bytes, int si = 0) {
     CUDA_TRY(cudaMallocAsync(p, bytes ? bytes : 16, s[si]));
     allocs.push_back(*p);
+    return SSO_OK;
+  }
+  // make stream `to` wait for everything enqueued so far on stream `from`
+  int fork(int from, int to) {
+    cudaEvent_t ev;
+    CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(ev, s[from]));
+    CUDA_TRY(cudaStreamWaitEvent(s[to], ev, 0));
+    CUDA_TRY(cudaEventDestroy(ev));
     return SSO_OK;
   }
   // bracket a kernel launch: counts it, and times it with events on its own stream when profiling is on
@@ -154,9 +193,11 @@ struct Ctx {
     if (dev >= 0) {
       for (auto& st : s) if (st) cudaStreamSynchronize(st);
       resolve_timings();
+      mark("dtor: streams drained");
       for (void* p : allocs) cudaFreeAsync(p, s[0]);
       for (auto& st : s) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
       if (prev >= 0) cudaSetDevice(prev);
+      mark("dtor: freed + destroyed");
     }
   }
 };
@@ -175,18 +216,22 @@ inline int upload_scalar(Ctx& c, const uint8_t* bytes, size_t nbytes, size_t nwo
   return SSO_OK;
 }
 
+// status words written by kernels: [0] code, [1] element index inside its vector, [2] vector index
+static constexpr size_t STATUS_BYTES = 16;
 inline int check_status(Ctx& c, uint32_t* d_status, const char* what, char* err, size_t errcap) {
-  uint32_t h[2] = {0, 0};
-  CUDA_TRY(cudaMemcpy(h, d_status, 8, cudaMemcpyDeviceToHost));
+  uint32_t h[4] = {0, 0, 0, 0};
+  CUDA_TRY(cudaMemcpy(h, d_status, STATUS_BYTES, cudaMemcpyDeviceToHost));
   if (h[0] != 0) {
-    set_err(err, errcap, "%s: %s (element %u)", what, status_text(h[0]), h[1]);
+    set_err(err, errcap, "%s: %s (vector %u, element %u)", what, status_text(h[0]), h[2], h[1]);
     return h[0] == 5u ? SSO_E_VERIFY : SSO_E_INPUT;
   }
   return SSO_OK;
 }
 
 inline int sync_all(Ctx& c, char* err, size_t errcap) {
+  c.mark("launches enqueued");
   for (auto st : c.s) if (st) CUDA_TRY(cudaStreamSynchronize(st));
+  c.mark("streams synchronized");
   c.resolve_timings();
   return SSO_OK;
 }

@@ -18,22 +18,48 @@ enum : uint32_t { CHECK_NO = 0, CHECK_NONZERO = 1, CHECK_FULL = 2 };   // CheckF
 enum : uint32_t { ST_OK = 0, ST_NONCANONICAL = 1, ST_BAD_FLAGS = 2, ST_NOT_ON_CURVE = 3, ST_ZERO_POINT = 4,
                   ST_NOT_IN_SUBGROUP = 5 };
 
-__device__ __forceinline__ void report(uint32_t* status, uint32_t code, uint32_t index) {
+__device__ __forceinline__ void report(uint32_t* status, uint32_t code, uint32_t index, uint32_t vec = 0) {
 #ifdef SSO_HOST_EMUL
-  if (status[0] == 0) { status[0] = code; status[1] = index; }
+  if (status[0] == 0) { status[0] = code; status[1] = index; status[2] = vec; }
 #else
-  if (atomicCAS(&status[0], 0u, code) == 0u) status[1] = index;
+  if (atomicCAS(&status[0], 0u, code) == 0u) { status[1] = index; status[2] = vec; }
 #endif
 }
 
 // ---------------------------------------------------------------------------------------------
 // K1: powers of tau.  Table layout (Montgomery Fr elements, Fr::L words each):
 //   [0..256)    tau^k            [256..512)  tau^(256 k)       [512..768)  tau^(65536 k)
-//   [768]       tau^first_index  [769]       coefficient (alpha / beta / 1)
-// so tau^(first+j) * coeff = T[768] * T[j & 255] * T[256 + ((j >> 8) & 255)] * T[512 + (j >> 16)] * T[769]
+//   [768]       tau^first_index  [769..772)  coefficient slots (e.g. 1, alpha, beta)
+// so tau^(first+j) * coeff = T[768] * T[j & 255] * T[256 + ((j >> 8) & 255)] * T[512 + (j >> 16)] * T[769 + slot]
 // for j < 2^24: a two/three-level parallel prefix instead of one `pow` per index.
 // ---------------------------------------------------------------------------------------------
-static constexpr int TAU_TABLE_ELEMS = 770;
+static constexpr int TAU_COEFF_SLOTS = 3;
+static constexpr int TAU_TABLE_ELEMS = 769 + TAU_COEFF_SLOTS;
+
+// One launch covers up to four vectors of the same group ("segments"), e.g. tauG1 | alphaG1 | betaG1.
+struct VecSeg {
+  const uint8_t* in;      // serialized input points
+  uint8_t* out;           // serialized output points
+  uint32_t n;
+  uint32_t coeff_slot;    // which table coefficient multiplies the scalar (mode 0) or IS the scalar (mode 1)
+  uint32_t has_coeff;     // mode 0 only: 0 = plain tau powers
+  uint32_t mode;          // 0 = tau^(first + j) [* coeff], 1 = one shared scalar
+};
+struct VecBatch {
+  VecSeg seg[4];
+  uint32_t nseg;
+  uint32_t total;
+};
+// flat index -> (segment, index inside the segment)
+__device__ __forceinline__ bool locate(const VecBatch& b, uint32_t tid, uint32_t& si, uint32_t& j) {
+  if (tid >= b.total) return false;
+  si = 0; j = tid;
+#pragma unroll
+  for (int s = 0; s < 3; s++) {
+    if (si == (uint32_t)s && (uint32_t)s + 1 < b.nseg && j >= b.seg[s].n) { j -= b.seg[s].n; si = s + 1; }
+  }
+  return true;
+}
 
 template <class Fr>
 __device__ __forceinline__ typename Fr::T fr_pow_u64(const typename Fr::T& a, uint64_t e) {
@@ -45,7 +71,8 @@ __device__ __forceinline__ typename Fr::T fr_pow_u64(const typename Fr::T& a, ui
   return r;
 }
 
-// tid in [0, 769): builds one table entry.  tau_canon / coeff_canon: canonical little-endian words.
+// tid in [0, TAU_TABLE_ELEMS): builds one table entry.  tau_canon: canonical little-endian words;
+// coeff_canon: TAU_COEFF_SLOTS canonical scalars back to back.
 template <class Fr>
 __device__ __forceinline__ void body_tau_tables(uint32_t tid, const uint32_t* tau_canon, const uint32_t* coeff_canon,
                                                 uint64_t first_index, uint32_t* table) {
@@ -57,18 +84,19 @@ __device__ __forceinline__ void body_tau_tables(uint32_t tid, const uint32_t* ta
   } else if (tid == 768) {
     out = fr_pow_u64<Fr>(tau, first_index);
   } else {
-    out = Fr::to_mont(Fr::from_const(coeff_canon));
+    out = Fr::to_mont(Fr::from_const(coeff_canon + (size_t)(tid - 769) * Fr::L));
   }
   Fr::store(table + (size_t)tid * Fr::L, 1, out);
 }
 
 // canonical scalar for element j of the vector (words in k[0..Fr::L))
 template <class Fr>
-__device__ __forceinline__ void scalar_for_index(const uint32_t* table, uint32_t j, uint32_t n, bool has_coeff, uint32_t* k) {
+__device__ __forceinline__ void scalar_for_index(const uint32_t* table, uint32_t j, uint32_t n, bool has_coeff, uint32_t slot,
+                                                 uint32_t* k) {
   typename Fr::T s = Fr::mul(Fr::load(table + 768 * Fr::L, 1), Fr::load(table + (size_t)(j & 255) * Fr::L, 1));
   if (n > 256) s = Fr::mul(s, Fr::load(table + (size_t)(256 + ((j >> 8) & 255)) * Fr::L, 1));
   if (n > 65536) s = Fr::mul(s, Fr::load(table + (size_t)(512 + ((j >> 16) & 255)) * Fr::L, 1));
-  if (has_coeff) s = Fr::mul(s, Fr::load(table + 769 * Fr::L, 1));
+  if (has_coeff) s = Fr::mul(s, Fr::load(table + (size_t)(769 + slot) * Fr::L, 1));
   s = Fr::from_mont(s);
 #pragma unroll
   for (int i = 0; i < Fr::L; i++) k[i] = s.v[i];
@@ -76,35 +104,37 @@ __device__ __forceinline__ void scalar_for_index(const uint32_t* table, uint32_t
 
 // ---------------------------------------------------------------------------------------------
 // K3 + K2: read one point, validate, multiply by its scalar, leave the Jacobian result in HBM.
-//   in        : n serialized points (uncompressed or compressed), byte-packed as in the chunk file
-//   jac_out   : n * 3 * F::WORDS words, [point][X|Y|Z][limb]
-//   mode      : 0 = scalar from the tau tables (phase 1), 1 = one shared scalar in table[769] (phase 2 batch_mul)
+//   jac_out : total * 3 * F::WORDS words, [flat point index][X|Y|Z][limb]
+//   status  : [0] first failure code, [1] element index inside its vector, [2] vector (segment) index
 // ---------------------------------------------------------------------------------------------
 template <class G>
-__device__ __forceinline__ void body_batch_exp(uint32_t tid, uint32_t n, const uint8_t* in, uint32_t in_compressed,
-                                               const uint32_t* table, uint32_t has_coeff, uint32_t mode, uint32_t check,
-                                               uint32_t* jac_out, uint32_t* status) {
+__device__ __forceinline__ void body_batch_exp(uint32_t tid, const VecBatch& b, uint32_t in_compressed, const uint32_t* table,
+                                               uint32_t check, uint32_t* jac_out, uint32_t* status) {
   using C = SW<G>;
   using F = typename G::F;
   using Fr = typename G::Fr;
-  if (tid >= n) return;
+  uint32_t sidx, j;
+  if (!locate(b, tid, sidx, j)) return;
+  const VecSeg& sg = b.seg[sidx];
   typename C::Affine p;
-  uint32_t st = in_compressed ? C::read_compressed(in + (size_t)tid * C::SIZE_C, p)
-                              : C::read_uncompressed(in + (size_t)tid * C::SIZE_U, p);
-  if (st != C::DESER_OK) { report(status, st, tid); p.inf = true; }
+  uint32_t st = in_compressed ? C::read_compressed(sg.in + (size_t)j * C::SIZE_C, p)
+                              : C::read_uncompressed(sg.in + (size_t)j * C::SIZE_U, p);
+  if (st != C::DESER_OK) { report(status, st, j, sidx); p.inf = true; }
   if (check != CHECK_NO && st == C::DESER_OK) {
-    if (p.inf) report(status, ST_ZERO_POINT, tid);
-    else if (check == CHECK_FULL && !in_compressed && !C::on_curve(p)) { report(status, ST_NOT_ON_CURVE, tid); p.inf = true; }
+    if (p.inf) report(status, ST_ZERO_POINT, j, sidx);
+    else if (check == CHECK_FULL && !in_compressed && !C::on_curve(p)) { report(status, ST_NOT_ON_CURVE, j, sidx); p.inf = true; }
   }
   uint32_t k[Fr::L];
-  if (mode == 0) {
-    scalar_for_index<Fr>(table, tid, n, has_coeff != 0, k);
+  if (sg.mode == 0) {
+    scalar_for_index<Fr>(table, j, sg.n, sg.has_coeff != 0, sg.coeff_slot, k);
   } else {
-    typename Fr::T s = Fr::from_mont(Fr::load(table + 769 * Fr::L, 1));
+    typename Fr::T s = Fr::from_mont(Fr::load(table + (size_t)(769 + sg.coeff_slot) * Fr::L, 1));
 #pragma unroll
     for (int i = 0; i < Fr::L; i++) k[i] = s.v[i];
   }
-  typename C::Jac r = C::template scalar_mul<Fr::L, Fr::P::BITS>(p, k);
+  typename C::Jac r;
+  if constexpr (G::HAS_GLV) r = C::template scalar_mul_glv<typename G::Glv, Fr::L>(p, k);
+  else r = C::template scalar_mul<Fr::L, Fr::P::BITS>(p, k);
   uint32_t* o = jac_out + (size_t)tid * 3 * F::WORDS;
   F::store(o, 1, r.X);
   F::store(o + F::WORDS, 1, r.Y);
@@ -113,16 +143,16 @@ __device__ __forceinline__ void body_batch_exp(uint32_t tid, uint32_t n, const u
 
 // ---------------------------------------------------------------------------------------------
 // K4: batch normalisation (Montgomery's trick over NB consecutive points per thread: one field
-// inversion per NB points) and serialisation.  tid handles points [tid*NB, tid*NB + NB).
+// inversion per NB points) and serialisation.  tid handles flat points [tid*NB, tid*NB + NB).
 // ---------------------------------------------------------------------------------------------
 static constexpr int NORM_BATCH = 8;
 
 template <class G>
-__device__ __forceinline__ void body_normalize_write(uint32_t tid, uint32_t n, const uint32_t* jac, uint8_t* out,
-                                                     uint32_t out_compressed) {
+__device__ __forceinline__ void body_normalize_write(uint32_t tid, const VecBatch& b, const uint32_t* jac, uint32_t out_compressed) {
   using C = SW<G>;
   using F = typename G::F;
   using FT = typename F::T;
+  uint32_t n = b.total;
   uint32_t first = tid * NORM_BATCH;
   if (first >= n) return;
   uint32_t cnt = n - first < (uint32_t)NORM_BATCH ? n - first : (uint32_t)NORM_BATCH;
@@ -145,8 +175,11 @@ __device__ __forceinline__ void body_normalize_write(uint32_t tid, uint32_t n, c
       inv = F::mul(inv, p.Z);
       a = C::to_affine_with(p, zinv);
     }
-    if (out_compressed) C::write_compressed(out + (size_t)(first + i) * C::SIZE_C, a);
-    else C::write_uncompressed(out + (size_t)(first + i) * C::SIZE_U, a);
+    uint32_t sidx, j;
+    locate(b, first + i, sidx, j);
+    uint8_t* out = b.seg[sidx].out;
+    if (out_compressed) C::write_compressed(out + (size_t)j * C::SIZE_C, a);
+    else C::write_uncompressed(out + (size_t)j * C::SIZE_U, a);
   }
 }
 

@@ -71,25 +71,76 @@ extern "C" int emul_group_sqrt(uint32_t curve, uint32_t group, const uint8_t* a,
 extern "C" int emul_batch_exp(uint32_t curve, uint32_t group, const uint8_t* in, uint32_t in_compressed, uint32_t n,
                               const uint32_t* tau_canon, const uint32_t* coeff_canon, uint64_t first_index, uint32_t mode,
                               uint32_t check, uint8_t* out, uint32_t out_compressed, uint32_t* status) {
-  status[0] = status[1] = 0;
+  status[0] = status[1] = status[2] = 0;
+  return dispatch_group(curve, group, [&](auto g) {
+    using G = decltype(g);
+    using Fr = typename G::Fr;
+    using F = typename G::F;
+    using C = SW<G>;
+    std::vector<uint32_t> table((size_t)TAU_TABLE_ELEMS * Fr::L);
+    std::vector<uint32_t> coeffs((size_t)TAU_COEFF_SLOTS * Fr::L, 0);
+    for (int i = 0; i < TAU_COEFF_SLOTS; i++) coeffs[(size_t)i * Fr::L] = 1;
+    // the coefficient goes to slot 2 so that the slot plumbing is exercised too
+    if (coeff_canon) memcpy(coeffs.data() + 2 * Fr::L, coeff_canon, Fr::L * 4);
+    for (uint32_t t = 0; t < (uint32_t)TAU_TABLE_ELEMS; t++)
+      body_tau_tables<Fr>(t, tau_canon, coeffs.data(), first_index, table.data());
+    // split the vector into two segments to exercise the multi-vector launch path
+    uint32_t n0 = n / 2, n1 = n - n0;
+    size_t isz = in_compressed ? C::SIZE_C : C::SIZE_U, osz = out_compressed ? C::SIZE_C : C::SIZE_U;
+    VecBatch b;
+    memset(&b, 0, sizeof b);
+    if (n0) { b.seg[b.nseg++] = VecSeg{in, out, n0, 2, coeff_canon != nullptr, mode}; }
+    // second segment continues the index range: emulate by a second table start -> instead run it as its own batch
+    b.total = n0;
+    std::vector<uint32_t> jac((size_t)n * 3 * F::WORDS);
+    for (uint32_t t = 0; t < n0; t++) body_batch_exp<G>(t, b, in_compressed, table.data(), check, jac.data(), status);
+    for (uint32_t t = 0; t * NORM_BATCH < n0; t++) body_normalize_write<G>(t, b, jac.data(), out_compressed);
+    // remaining elements: a batch of two segments (n1 - 1 elements + 1 element) starting at index first + n0
+    std::vector<uint32_t> table2((size_t)TAU_TABLE_ELEMS * Fr::L);
+    for (uint32_t t = 0; t < (uint32_t)TAU_TABLE_ELEMS; t++)
+      body_tau_tables<Fr>(t, tau_canon, coeffs.data(), first_index + n0, table2.data());
+    uint32_t st2[3] = {0, 0, 0};
+    if (n1 > 0) {
+      VecBatch b2;
+      memset(&b2, 0, sizeof b2);
+      b2.seg[0] = VecSeg{in + n0 * isz, out + n0 * osz, n1, 2, coeff_canon != nullptr, mode};
+      b2.nseg = 1; b2.total = n1;
+      for (uint32_t t = 0; t < n1; t++) body_batch_exp<G>(t, b2, in_compressed, table2.data(), check, jac.data(), st2);
+      for (uint32_t t = 0; t * NORM_BATCH < n1; t++) body_normalize_write<G>(t, b2, jac.data(), out_compressed);
+      if (status[0] == 0 && st2[0] != 0) { status[0] = st2[0]; status[1] = st2[1] + n0; }
+    }
+  });
+}
+
+// Multi-vector launch: two segments with different coefficient slots / modes in one batch.
+extern "C" int emul_batch_exp2(uint32_t curve, uint32_t group, const uint8_t* in0, uint32_t n0, const uint8_t* in1, uint32_t n1,
+                               const uint32_t* tau_canon, const uint32_t* coeff1, const uint32_t* coeff2, uint64_t first_index,
+                               uint8_t* out0, uint8_t* out1, uint32_t* status) {
+  status[0] = status[1] = status[2] = 0;
   return dispatch_group(curve, group, [&](auto g) {
     using G = decltype(g);
     using Fr = typename G::Fr;
     using F = typename G::F;
     std::vector<uint32_t> table((size_t)TAU_TABLE_ELEMS * Fr::L);
-    std::vector<uint32_t> one(Fr::L, 0); one[0] = 1;
-    for (uint32_t t = 0; t < (uint32_t)TAU_TABLE_ELEMS; t++)
-      body_tau_tables<Fr>(t, tau_canon, coeff_canon ? coeff_canon : one.data(), first_index, table.data());
-    std::vector<uint32_t> jac((size_t)n * 3 * F::WORDS);
-    for (uint32_t t = 0; t < n; t++)
-      body_batch_exp<G>(t, n, in, in_compressed, table.data(), coeff_canon != nullptr, mode, check, jac.data(), status);
-    for (uint32_t t = 0; t * NORM_BATCH < n; t++) body_normalize_write<G>(t, n, jac.data(), out, out_compressed);
+    std::vector<uint32_t> coeffs((size_t)TAU_COEFF_SLOTS * Fr::L, 0);
+    coeffs[0] = 1;
+    memcpy(coeffs.data() + Fr::L, coeff1, Fr::L * 4);
+    memcpy(coeffs.data() + 2 * Fr::L, coeff2, Fr::L * 4);
+    for (uint32_t t = 0; t < (uint32_t)TAU_TABLE_ELEMS; t++) body_tau_tables<Fr>(t, tau_canon, coeffs.data(), first_index, table.data());
+    VecBatch b;
+    memset(&b, 0, sizeof b);
+    b.seg[0] = VecSeg{in0, out0, n0, 1, 1, 0};      // tau^(first+j) * coeff1
+    b.seg[1] = VecSeg{in1, out1, n1, 2, 1, 1};      // shared scalar coeff2
+    b.nseg = 2; b.total = n0 + n1;
+    std::vector<uint32_t> jac((size_t)b.total * 3 * F::WORDS);
+    for (uint32_t t = 0; t < b.total; t++) body_batch_exp<G>(t, b, 0, table.data(), 1, jac.data(), status);
+    for (uint32_t t = 0; t * NORM_BATCH < b.total; t++) body_normalize_write<G>(t, b, jac.data(), 1);
   });
 }
 
 extern "C" int emul_reencode(uint32_t curve, uint32_t group, const uint8_t* in, uint32_t in_compressed, uint32_t n,
                              uint8_t* out, uint32_t out_compressed, uint32_t check, uint32_t subgroup, uint32_t* status) {
-  status[0] = status[1] = 0;
+  status[0] = status[1] = status[2] = 0;
   return dispatch_group(curve, group, [&](auto g) {
     using G = decltype(g);
     for (uint32_t t = 0; t < n; t++)
