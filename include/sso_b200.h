@@ -107,6 +107,25 @@ int32_t sso_reencode_dev(uint32_t curve, uint32_t group, const void* d_in, uint3
                          void* d_out, uint32_t out_compressed, uint32_t check, uint32_t subgroup_check,
                          int device, char* err, size_t errcap);
 
+/* setup_utils::power_pairs (K3 + K5): decode and check n points, draw scalars r_i, return the pair
+ * (sum r_i v_i, sum r_i v_{i+1}) over i < n-1 as two uncompressed points in out_pair (host).  The reference
+ * draws r_i from thread_rng, so only the verdict downstream is comparable; seed32 == NULL uses fresh host
+ * entropy, a 32-byte seed makes the scalars reproducible (tests): r_i = first bits(r)-1 bits of the
+ * ChaCha20(seed32) keystream blocks 2i, 2i+1. */
+int32_t sso_power_pairs_dev(uint32_t curve, uint32_t group, const void* d_in, uint32_t in_compressed, uint64_t n,
+                            uint32_t check, uint32_t subgroup_check, const uint8_t* seed32, uint8_t* out_pair, size_t out_len,
+                            int device, char* err, size_t errcap);
+/* setup_utils::merge_pairs: (sum r_i a_i, sum r_i b_i) for two vectors of n points (same conventions). */
+int32_t sso_merge_pairs_dev(uint32_t curve, uint32_t group, const void* d_a, const void* d_b, uint32_t in_compressed, uint64_t n,
+                            uint32_t check, uint32_t subgroup_check, const uint8_t* seed32, uint8_t* out_pair, size_t out_len,
+                            int device, char* err, size_t errcap);
+
+/* setup_utils::same_ratio / check_same_ratio (K8) for n checks on HOST buffers.  Check i occupies
+ * 2 * |G1 uncompressed| + 2 * |G2 uncompressed| bytes laid out a | b | c | d and asks e(a, d) == e(b, c);
+ * verdicts[i] = 1 (same ratio) or 0.  Undecodable or off-curve inputs are SSO_E_INPUT. */
+int32_t sso_same_ratio(uint32_t curve, const uint8_t* checks, uint64_t n, uint32_t* verdicts, int device, char* err,
+                       size_t errcap);
+
 /* Phase1::computation for one chunk, device-resident: d_challenge holds the challenge file image
  * (accumulator_size bytes, uncompressed), d_response receives the compressed vectors at their
  * response-file offsets (contribution_size bytes; the 64-byte hash slot and the public key tail

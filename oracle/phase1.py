@@ -283,3 +283,18 @@ def verify_chunk_with_key(params: Phase1Params, challenge: bytes, response: byte
             if not G.eq(P, Q):
                 raise VerificationError("ratio check failed")
     return write_chunk(params, calculate_hash(response), vout, False)
+
+
+def rlc_scalars(curve: Curve, seed32: bytes, n: int):
+    """The product's reproducible random-linear-combination scalars (include/sso_b200.h,
+    sso_power_pairs_dev): r_i = first bits(r)-1 bits of the ChaCha20(seed32) keystream blocks 2i, 2i+1."""
+    import struct
+    from .chacha import chacha20_block
+    key = struct.unpack("<8I", seed32)
+    sbits = curve.Fr.bits - 1
+    out = []
+    for i in range(n):
+        words = chacha20_block(key, 2 * i) + chacha20_block(key, 2 * i + 1)
+        v = sum(w << (32 * j) for j, w in enumerate(words))
+        out.append(v & ((1 << sbits) - 1))
+    return out

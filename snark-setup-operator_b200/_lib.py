@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libsso_b200.so")
+_LIB_PATH = os.environ.get("SSO_B200_LIB") or os.path.join(_HERE, "libsso_b200.so")   # override: kernel A/B experiments
 _lib = None
 
 
@@ -50,6 +50,9 @@ def lib() -> ctypes.CDLL:
         L.sso_reencode_dev.argtypes = [u32, u32, vp, u32, u64, vp, u32, u32, u32, i32, cp, sz]
         L.sso_p1_contribute_dev.argtypes = [ctypes.POINTER(P1Params), vp, vp, u8p, u8p, u8p, u32, i32, cp, sz]
         L.sso_p1_contribute_buf.argtypes = [ctypes.POINTER(P1Params), vp, sz, vp, sz, u8p, u8p, u8p, u8p, sz, u32, i32, cp, sz]
+        L.sso_power_pairs_dev.argtypes = [u32, u32, vp, u32, u64, u32, u32, u8p, cp, sz, i32, cp, sz]
+        L.sso_merge_pairs_dev.argtypes = [u32, u32, vp, vp, u32, u64, u32, u32, u8p, cp, sz, i32, cp, sz]
+        L.sso_same_ratio.argtypes = [u32, u8p, u64, ctypes.POINTER(ctypes.c_uint32), i32, cp, sz]
         L.sso_p1_new_challenge_dev.argtypes = [ctypes.POINTER(P1Params), vp, i32, cp, sz]
         L.sso_profile_enable.argtypes = [ctypes.c_int32]
         L.sso_profile_read.argtypes = [ctypes.POINTER(u64), sz]
@@ -58,7 +61,7 @@ def lib() -> ctypes.CDLL:
         for name in ("sso_device_name", "sso_curve_sizes", "sso_p1_sizes", "sso_blake2b_512", "sso_batch_exp_dev",
                      "sso_batch_mul_dev", "sso_reencode_dev", "sso_p1_contribute_dev", "sso_p1_contribute_buf", "sso_imad_peak",
                      "sso_test_field_mul", "sso_p1_new_challenge_dev", "sso_profile_enable", "sso_profile_reset",
-                     "sso_profile_read"):
+                     "sso_profile_read", "sso_power_pairs_dev", "sso_merge_pairs_dev", "sso_same_ratio"):
             getattr(L, name).restype = ctypes.c_int32
         _lib = L
     return _lib

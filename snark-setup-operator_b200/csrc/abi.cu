@@ -277,6 +277,87 @@ int32_t sso_reencode_dev(uint32_t curve, uint32_t group, const void* d_in, uint3
   return check_status(c, d_status, "point", err, errcap);
 }
 
+// K3 + K5: validate/decode n points and return (sum r_i v_i, sum r_i v_{i+1}) [power_pairs] as two uncompressed points
+int32_t sso_power_pairs_dev(uint32_t curve, uint32_t group, const void* d_in, uint32_t in_compressed, uint64_t n,
+                            uint32_t check, uint32_t subgroup_check, const uint8_t* seed32, uint8_t* out_pair, size_t out_len,
+                            int device, char* err, size_t errcap) {
+  const CurveOps* ops = ops_for(curve);
+  if (!ops || group > 1) { set_err(err, errcap, "unknown curve/group %u/%u", curve, group); return SSO_E_ARG; }
+  if (n < 2) { set_err(err, errcap, "power_pairs needs at least two elements"); return SSO_E_ARG; }
+  CurveSizes cs;
+  curve_sizes(curve, cs);
+  uint64_t usz = group == GROUP_G1 ? cs.g1u : cs.g2u;
+  if (out_len != 2 * usz) { set_err(err, errcap, "output buffer must hold two uncompressed points (%llu bytes)", (unsigned long long)(2 * usz)); return SSO_E_ARG; }
+  Ctx c(err, errcap);
+  int rc = c.init(device);
+  if (rc) return rc;
+  uint32_t *d_status, *d_aff;
+  uint8_t* d_out;
+  if ((rc = status_buffer(c, &d_status, err, errcap))) return rc;
+  if ((rc = c.alloc((void**)&d_aff, n * ops->aff_words[group] * 4))) return rc;
+  if ((rc = c.alloc((void**)&d_out, 2 * usz))) return rc;
+  if ((rc = ops->reencode(c, 0, group, (const uint8_t*)d_in, in_compressed, n, nullptr, 0, check, subgroup_check, d_aff, d_status, err, errcap))) return rc;
+  if ((rc = ops->msm_pairs(c, 0, group, d_aff, d_aff + ops->aff_words[group], n - 1, seed32, d_out, err, errcap))) return rc;
+  if ((rc = sync_all(c, err, errcap))) return rc;
+  if ((rc = check_status(c, d_status, "point", err, errcap))) return rc;
+  CUDA_TRY(cudaMemcpy(out_pair, d_out, 2 * usz, cudaMemcpyDeviceToHost));
+  return SSO_OK;
+}
+
+// K3 + K5: (sum r_i a_i, sum r_i b_i) [merge_pairs] for two vectors of n points each
+int32_t sso_merge_pairs_dev(uint32_t curve, uint32_t group, const void* d_a, const void* d_b, uint32_t in_compressed, uint64_t n,
+                            uint32_t check, uint32_t subgroup_check, const uint8_t* seed32, uint8_t* out_pair, size_t out_len,
+                            int device, char* err, size_t errcap) {
+  const CurveOps* ops = ops_for(curve);
+  if (!ops || group > 1) { set_err(err, errcap, "unknown curve/group %u/%u", curve, group); return SSO_E_ARG; }
+  if (n < 1) { set_err(err, errcap, "merge_pairs needs at least one element"); return SSO_E_ARG; }
+  CurveSizes cs;
+  curve_sizes(curve, cs);
+  uint64_t usz = group == GROUP_G1 ? cs.g1u : cs.g2u;
+  if (out_len != 2 * usz) { set_err(err, errcap, "output buffer must hold two uncompressed points (%llu bytes)", (unsigned long long)(2 * usz)); return SSO_E_ARG; }
+  Ctx c(err, errcap);
+  int rc = c.init(device);
+  if (rc) return rc;
+  uint32_t *d_status, *d_aff_a, *d_aff_b;
+  uint8_t* d_out;
+  if ((rc = status_buffer(c, &d_status, err, errcap))) return rc;
+  if ((rc = c.alloc((void**)&d_aff_a, n * ops->aff_words[group] * 4))) return rc;
+  if ((rc = c.alloc((void**)&d_aff_b, n * ops->aff_words[group] * 4))) return rc;
+  if ((rc = c.alloc((void**)&d_out, 2 * usz))) return rc;
+  if ((rc = ops->reencode(c, 0, group, (const uint8_t*)d_a, in_compressed, n, nullptr, 0, check, subgroup_check, d_aff_a, d_status, err, errcap))) return rc;
+  if ((rc = ops->reencode(c, 0, group, (const uint8_t*)d_b, in_compressed, n, nullptr, 0, check, subgroup_check, d_aff_b, d_status, err, errcap))) return rc;
+  if ((rc = ops->msm_pairs(c, 0, group, d_aff_a, d_aff_b, n, seed32, d_out, err, errcap))) return rc;
+  if ((rc = sync_all(c, err, errcap))) return rc;
+  if ((rc = check_status(c, d_status, "point", err, errcap))) return rc;
+  CUDA_TRY(cudaMemcpy(out_pair, d_out, 2 * usz, cudaMemcpyDeviceToHost));
+  return SSO_OK;
+}
+
+// K8: batch of same_ratio checks on host buffers
+int32_t sso_same_ratio(uint32_t curve, const uint8_t* checks, uint64_t n, uint32_t* verdicts, int device, char* err,
+                       size_t errcap) {
+  const CurveOps* ops = ops_for(curve);
+  if (!ops || !checks || !verdicts) { set_err(err, errcap, "unknown curve %u or null buffer", curve); return SSO_E_ARG; }
+  if (n == 0) return SSO_OK;
+  Ctx c(err, errcap);
+  int rc = c.init(device);
+  if (rc) return rc;
+  uint8_t* d_checks;
+  uint32_t* d_verdicts;
+  if ((rc = c.alloc((void**)&d_checks, n * ops->check_bytes))) return rc;
+  if ((rc = c.alloc((void**)&d_verdicts, n * 4))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(d_checks, checks, n * ops->check_bytes, cudaMemcpyHostToDevice, c.s[0]));
+  if ((rc = ops->same_ratio(c, 0, d_checks, n, d_verdicts, err, errcap))) return rc;
+  if ((rc = sync_all(c, err, errcap))) return rc;
+  CUDA_TRY(cudaMemcpy(verdicts, d_verdicts, n * 4, cudaMemcpyDeviceToHost));
+  for (uint64_t i = 0; i < n; i++)
+    if (verdicts[i] >= 0x100u) {
+      set_err(err, errcap, "same_ratio check %llu: %s", (unsigned long long)i, status_text(verdicts[i] - 0x100u));
+      return SSO_E_INPUT;
+    }
+  return SSO_OK;
+}
+
 int32_t sso_p1_contribute_dev(const sso_p1_params_t* p, const void* d_challenge, void* d_response,
                               const uint8_t* tau, const uint8_t* alpha, const uint8_t* beta,
                               uint32_t check_input, int device, char* err, size_t errcap) {

@@ -4,6 +4,10 @@
 #include <type_traits>
 #include "host.cuh"
 #include "kernels.cuh"
+#include "msm.cuh"
+#include "pairing.cuh"
+#include <cub/device/device_radix_sort.cuh>
+#include <random>
 
 namespace sso {
 
@@ -18,9 +22,18 @@ struct CurveOps {
   int (*reencode)(Ctx& c, int si, uint32_t group, const uint8_t* d_in, uint32_t in_compressed, uint64_t n, uint8_t* d_out,
                   uint32_t out_compressed, uint32_t check, uint32_t subgroup, uint32_t* d_aff, uint32_t* d_status, char* err,
                   size_t errcap);
+  // K5: (sum r_i a_i, sum r_i b_i) for two affine Montgomery point arrays ([point][x|y] words, zero = infinity) with
+  // ChaCha20(seed32) scalars; writes the two points uncompressed to d_out (2 * uncompressed size bytes)
+  int (*msm_pairs)(Ctx& c, int si, uint32_t group, const uint32_t* d_aff_a, const uint32_t* d_aff_b, uint64_t n,
+                   const uint8_t seed32[32], uint8_t* d_out, char* err, size_t errcap);
+  // K8: same_ratio verdicts for n checks laid out a | b | c | d (uncompressed); verdict 1 = equal ratios,
+  // 0 = different, 0x100 + code = undecodable input
+  int (*same_ratio)(Ctx& c, int si, const uint8_t* d_checks, uint64_t n, uint32_t* d_verdicts, char* err, size_t errcap);
+  uint32_t check_bytes;
   // phase1_cli::new_challenge: n copies of the group generator, uncompressed or compressed
   int (*fill_generator)(Ctx& c, int si, uint32_t group, uint64_t n, uint8_t* d_out, uint32_t out_compressed, char* err, size_t errcap);
   uint32_t fr_bytes;
+  uint32_t aff_words[2];     // words per affine point (x|y) in device arrays, per group
 };
 
 template <class Fr>
@@ -120,6 +133,116 @@ inline int run_fill_generator(Ctx& c, int si, uint64_t n, uint8_t* d_out, uint32
 }
 
 template <class G>
+__global__ void k_random_scalars(uint32_t n, const uint32_t* key, uint32_t* scalars) {
+  body_random_scalars<G::Fr::L, G::Fr::P::BITS - 1>(blockIdx.x * blockDim.x + threadIdx.x, n, key, scalars);
+}
+template <class G>
+__global__ void k_msm_keys(uint32_t n, uint32_t nwin, uint32_t c, const uint32_t* scalars, uint32_t* keys, uint32_t* vals) {
+  body_msm_keys<G::Fr::L>(blockIdx.x * blockDim.x + threadIdx.x, n, nwin, c, scalars, keys, vals);
+}
+template <class G>
+__global__ void __launch_bounds__(128) k_msm_buckets(uint32_t n, uint32_t nwin, uint32_t c, const uint32_t* keys, const uint32_t* vals,
+                                                      const uint32_t* aff_a, const uint32_t* aff_b, uint32_t* buckets) {
+  body_msm_buckets<G>(blockIdx.x * blockDim.x + threadIdx.x, n, nwin, c, keys, vals, aff_a, aff_b, buckets);
+}
+template <class G>
+__global__ void __launch_bounds__(128) k_msm_fold(uint32_t nwin, uint32_t c, const uint32_t* buckets, uint32_t* seg_out) {
+  body_msm_fold<G>(blockIdx.x * blockDim.x + threadIdx.x, nwin, c, buckets, seg_out);
+}
+template <class G>
+__global__ void __launch_bounds__(128) k_msm_window(uint32_t nwin, uint32_t c, const uint32_t* seg_in, uint32_t* win_out) {
+  body_msm_window<G>(blockIdx.x * blockDim.x + threadIdx.x, nwin, c, seg_in, win_out);
+}
+template <class G>
+__global__ void __launch_bounds__(128) k_msm_final(uint32_t nwin, uint32_t c, const uint32_t* win_in, uint8_t* out) {
+  body_msm_final<G>(blockIdx.x * blockDim.x + threadIdx.x, nwin, c, win_in, out);
+}
+
+template <class G1, class G2, class PP>
+__global__ void __launch_bounds__(64) k_same_ratio(const uint8_t* checks, uint32_t* verdicts) {
+  using PR = Pairing<G1, G2, PP>;
+  using Fq = typename G1::F;
+  __shared__ typename PR::Ws ws[2];
+  __shared__ uint32_t st[2];
+  int side = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t s = PR::run_side(lane, ws[side], checks + (size_t)blockIdx.x * PR::CHECK_BYTES, side);
+  if (lane == 0) st[side] = s;
+  __syncthreads();
+  if (side == 0) {
+    bool eq = lane < PR::K ? Fq::eq(ws[0].f[lane], ws[1].f[lane]) : true;
+    uint32_t all = __all_sync(0xffffffffu, eq);
+    if (lane == 0) verdicts[blockIdx.x] = (st[0] | st[1]) ? 0x100u + (st[0] ? st[0] : st[1]) : (all ? 1u : 0u);
+  }
+}
+
+template <class G1, class G2, class PP>
+inline int run_same_ratio(Ctx& c, int si, const uint8_t* d_checks, uint64_t n, uint32_t* d_verdicts, char* err, size_t errcap) {
+  if (n == 0) return SSO_OK;
+  if (n > 65535) { set_err(err, errcap, "too many same_ratio checks in one call"); return SSO_E_ARG; }
+  c.begin(PK_OTHER, si, n);
+  k_same_ratio<G1, G2, PP><<<(uint32_t)n, 64, 0, c.s[si]>>>(d_checks, d_verdicts);
+  c.end(si);
+  CUDA_TRY(cudaGetLastError());
+  return SSO_OK;
+}
+
+inline uint32_t msm_window_bits(uint64_t n) {
+  uint32_t lg = 0;
+  while ((2ull << lg) <= n) lg++;
+  int c = (int)lg - 6;
+  return (uint32_t)(c < 4 ? 4 : (c > 14 ? 14 : c));
+}
+
+template <class G>
+inline int run_msm_pairs(Ctx& c, int si, const uint32_t* d_aff_a, const uint32_t* d_aff_b, uint64_t n, const uint8_t seed32[32],
+                         uint8_t* d_out, char* err, size_t errcap) {
+  using F = typename G::F;
+  using Fr = typename G::Fr;
+  constexpr int KL = Fr::L;
+  constexpr int SBITS = Fr::P::BITS - 1;
+  if (n == 0 || n > (1ull << 26)) { set_err(err, errcap, "msm length out of range"); return SSO_E_ARG; }
+  cudaStream_t st = c.s[si];
+  uint32_t wb = msm_window_bits(n), nwin = (SBITS + wb - 1) / wb, nb = 1u << wb;
+  uint32_t seg = nb < MSM_SEG ? nb : MSM_SEG, nseg = nb / seg;
+  size_t pairs = (size_t)n * nwin;
+  if (pairs > 0xffffffffull) { set_err(err, errcap, "msm too large for 32-bit indexing: split the vector"); return SSO_E_ARG; }
+  // scalar key: caller-supplied (tests) or fresh host entropy
+  c.staging.emplace_back(8, 0u);
+  std::vector<uint32_t>& key = c.staging.back();
+  if (seed32) memcpy(key.data(), seed32, 32);
+  else { std::random_device rd; for (auto& w : key) w = rd(); }
+  uint32_t *d_key, *d_sc, *d_keys, *d_vals, *d_keys2, *d_vals2, *d_buckets, *d_seg, *d_win;
+  void* d_tmp = nullptr;
+  int rc;
+  if ((rc = c.alloc((void**)&d_key, 32, si))) return rc;
+  if ((rc = c.alloc((void**)&d_sc, (size_t)n * KL * 4, si))) return rc;
+  if ((rc = c.alloc((void**)&d_keys, pairs * 4, si))) return rc;
+  if ((rc = c.alloc((void**)&d_vals, pairs * 4, si))) return rc;
+  if ((rc = c.alloc((void**)&d_keys2, pairs * 4, si))) return rc;
+  if ((rc = c.alloc((void**)&d_vals2, pairs * 4, si))) return rc;
+  if ((rc = c.alloc((void**)&d_buckets, (size_t)2 * nwin * nb * 3 * F::WORDS * 4, si))) return rc;
+  if ((rc = c.alloc((void**)&d_seg, (size_t)2 * nwin * nseg * 6 * F::WORDS * 4, si))) return rc;
+  if ((rc = c.alloc((void**)&d_win, (size_t)2 * nwin * 3 * F::WORDS * 4, si))) return rc;
+  size_t tmp_bytes = 0;
+  uint32_t key_bits = wb;
+  while ((1u << (key_bits - wb)) < nwin) key_bits++;
+  CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, (int)pairs, 0, (int)key_bits, st));
+  if ((rc = c.alloc(&d_tmp, tmp_bytes, si))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(d_key, key.data(), 32, cudaMemcpyHostToDevice, st));
+  c.begin(PK_MSM, si, n);
+  k_random_scalars<G><<<div_up(n, 128), 128, 0, st>>>((uint32_t)n, d_key, d_sc);
+  k_msm_keys<G><<<div_up(n, 128), 128, 0, st>>>((uint32_t)n, nwin, wb, d_sc, d_keys, d_vals);
+  CUDA_TRY(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, (int)pairs, 0, (int)key_bits, st));
+  k_msm_buckets<G><<<div_up((uint64_t)nwin * nb, 128), 128, 0, st>>>((uint32_t)n, nwin, wb, d_keys2, d_vals2, d_aff_a, d_aff_b, d_buckets);
+  k_msm_fold<G><<<div_up((uint64_t)2 * nwin * nseg, 128), 128, 0, st>>>(nwin, wb, d_buckets, d_seg);
+  k_msm_window<G><<<div_up((uint64_t)2 * nwin, 128), 128, 0, st>>>(nwin, wb, d_seg, d_win);
+  k_msm_final<G><<<1, 32, 0, st>>>(nwin, wb, d_win, d_out);
+  c.end(si);
+  CUDA_TRY(cudaGetLastError());
+  return SSO_OK;
+}
+
+template <class G>
 inline int run_reencode(Ctx& c, int si, const uint8_t* d_in, uint32_t in_compressed, uint64_t n, uint8_t* d_out,
                         uint32_t out_compressed, uint32_t check, uint32_t subgroup, uint32_t* d_aff, uint32_t* d_status,
                         char* err, size_t errcap) {
@@ -133,7 +256,10 @@ inline int run_reencode(Ctx& c, int si, const uint8_t* d_in, uint32_t in_compres
   return SSO_OK;
 }
 
-template <class G1, class G2> struct CurveImpl {
+template <class G1, class G2, class PP> struct CurveImpl {
+  static int same_ratio(Ctx& c, int si, const uint8_t* d_checks, uint64_t n, uint32_t* d_verdicts, char* err, size_t errcap) {
+    return run_same_ratio<G1, G2, PP>(c, si, d_checks, n, d_verdicts, err, errcap);
+  }
   static int tau_tables(Ctx& c, int si, uint64_t first_index, const uint8_t* tau, const uint8_t* const coeffs[TAU_COEFF_SLOTS],
                         uint32_t** d_table, char* err, size_t errcap) {
     return run_tau_tables<typename G1::Fr>(c, si, first_index, tau, coeffs, d_table, err, errcap);
@@ -153,6 +279,13 @@ template <class G1, class G2> struct CurveImpl {
     set_err(err, errcap, "unknown group %u", group);
     return SSO_E_ARG;
   }
+  static int msm_pairs(Ctx& c, int si, uint32_t group, const uint32_t* d_aff_a, const uint32_t* d_aff_b, uint64_t n,
+                       const uint8_t seed32[32], uint8_t* d_out, char* err, size_t errcap) {
+    if (group == GROUP_G1) return run_msm_pairs<G1>(c, si, d_aff_a, d_aff_b, n, seed32, d_out, err, errcap);
+    if (group == GROUP_G2) return run_msm_pairs<G2>(c, si, d_aff_a, d_aff_b, n, seed32, d_out, err, errcap);
+    set_err(err, errcap, "unknown group %u", group);
+    return SSO_E_ARG;
+  }
   static int fill_generator(Ctx& c, int si, uint32_t group, uint64_t n, uint8_t* d_out, uint32_t out_compressed, char* err, size_t errcap) {
     if (group == GROUP_G1) return run_fill_generator<G1>(c, si, n, d_out, out_compressed, err, errcap);
     if (group == GROUP_G2) return run_fill_generator<G2>(c, si, n, d_out, out_compressed, err, errcap);
@@ -160,7 +293,7 @@ template <class G1, class G2> struct CurveImpl {
     return SSO_E_ARG;
   }
   static const CurveOps* ops() {
-    static const CurveOps o = {&tau_tables, &batch_exp, &reencode, &fill_generator, (uint32_t)G1::Fr::NBYTES};
+    static const CurveOps o = {&tau_tables, &batch_exp, &reencode, &msm_pairs, &same_ratio, (uint32_t)Pairing<G1, G2, PP>::CHECK_BYTES, &fill_generator, (uint32_t)G1::Fr::NBYTES, {2u * G1::F::WORDS, 2u * G2::F::WORDS}};
     return &o;
   }
 };

@@ -13,6 +13,11 @@
 #include <cstdint>
 #include "constants.cuh"
 
+// field multiplications wider than this many limbs are kept out of line (one copy per field)
+#ifndef SSO_INLINE_MUL_MAX_L
+#define SSO_INLINE_MUL_MAX_L 12
+#endif
+
 namespace sso {
 
 // ---------------------------------------------------------------------------------------------
@@ -216,7 +221,7 @@ template <class P_> struct Fp {
   // formulas do not overflow the instruction cache; 8/12-limb ones are inlined.
   __device__ __noinline__ static T mul_outlined(const T& a, const T& b) { T r; mont_mul<P>(r.v, a.v, b.v); return r; }
   __device__ __forceinline__ static T mul(const T& a, const T& b) {
-    if constexpr (L > 12) { return mul_outlined(a, b); } else { T r; mont_mul<P>(r.v, a.v, b.v); return r; }
+    if constexpr (L > SSO_INLINE_MUL_MAX_L) { return mul_outlined(a, b); } else { T r; mont_mul<P>(r.v, a.v, b.v); return r; }
   }
   __device__ __forceinline__ static T sqr(const T& a) { return mul(a, a); }
   // multiply by a small non-negative integer constant

@@ -179,3 +179,32 @@ def imad_peak(variant: int = 0, device=0) -> float:
     out = ctypes.c_double(0)
     call("sso_imad_peak", device, variant, ctypes.byref(out))
     return out.value
+
+
+def power_pairs(curve, group: int, d_in, n: int, in_compressed=False, check=CHECK_NO, subgroup_check=False, seed32=None,
+                device=0) -> bytes:
+    """setup_utils::power_pairs on a device vector -> the two result points, uncompressed."""
+    usz = _elem_size(curve, group, False)
+    out = ctypes.create_string_buffer(2 * usz)
+    call("sso_power_pairs_dev", curve_id(curve), group, _dptr(d_in), int(in_compressed), n, check, int(subgroup_check), seed32,
+         out, len(out), device)
+    return out.raw
+
+
+def merge_pairs(curve, group: int, d_a, d_b, n: int, in_compressed=False, check=CHECK_NO, subgroup_check=False, seed32=None,
+                device=0) -> bytes:
+    """setup_utils::merge_pairs on two device vectors -> the two result points, uncompressed."""
+    usz = _elem_size(curve, group, False)
+    out = ctypes.create_string_buffer(2 * usz)
+    call("sso_merge_pairs_dev", curve_id(curve), group, _dptr(d_a), _dptr(d_b), int(in_compressed), n, check,
+         int(subgroup_check), seed32, out, len(out), device)
+    return out.raw
+
+
+def same_ratio(curve, checks, device=0):
+    """Batch of setup_utils::same_ratio checks.  `checks`: list of (a, b, c, d) uncompressed point byte
+    strings (a, b in G1; c, d in G2).  Returns a list of booleans e(a, d) == e(b, c)."""
+    buf = b"".join(a + b + c + d for a, b, c, d in checks)
+    verdicts = (ctypes.c_uint32 * max(1, len(checks)))()
+    call("sso_same_ratio", curve_id(curve), buf, len(checks), verdicts, device)
+    return [bool(v) for v in verdicts[:len(checks)]]

@@ -14,7 +14,11 @@
 #include <cstddef>
 #include <cstring>
 #include <vector>
+#include <algorithm>
+#include <numeric>
 #include "../../snark-setup-operator_b200/csrc/kernels.cuh"
+#include "../../snark-setup-operator_b200/csrc/msm.cuh"
+#include "../../snark-setup-operator_b200/csrc/pairing.cuh"
 
 using namespace sso;
 
@@ -146,4 +150,64 @@ extern "C" int emul_reencode(uint32_t curve, uint32_t group, const uint8_t* in, 
     for (uint32_t t = 0; t < n; t++)
       body_reencode<G>(t, n, in, in_compressed, out, out_compressed, check, subgroup, nullptr, status);
   });
+}
+
+// power_pairs on n serialized points with ChaCha20(seed) scalars; the CUB sort is replaced by std::sort.
+extern "C" int emul_power_pairs(uint32_t curve, uint32_t group, const uint8_t* in, uint32_t in_compressed, uint32_t n,
+                                const uint32_t* seed_words, uint32_t wb, uint8_t* out_pair, uint32_t* scalars_out, uint32_t* status) {
+  status[0] = status[1] = status[2] = 0;
+  return dispatch_group(curve, group, [&](auto g) {
+    using G = decltype(g);
+    using F = typename G::F;
+    using Fr = typename G::Fr;
+    constexpr int KL = Fr::L;
+    constexpr int SBITS = Fr::P::BITS - 1;
+    std::vector<uint32_t> aff((size_t)n * 2 * F::WORDS);
+    for (uint32_t t = 0; t < n; t++) body_reencode<G>(t, n, in, in_compressed, nullptr, 0, 0, 0, aff.data(), status);
+    uint32_t m = n - 1;
+    std::vector<uint32_t> sc((size_t)m * KL);
+    for (uint32_t t = 0; t < m; t++) body_random_scalars<KL, SBITS>(t, m, seed_words, sc.data());
+    if (scalars_out) memcpy(scalars_out, sc.data(), sc.size() * 4);
+    uint32_t nwin = (SBITS + wb - 1) / wb, nb = 1u << wb;
+    uint32_t seg = nb < MSM_SEG ? nb : MSM_SEG, nseg = nb / seg;
+    size_t pairs = (size_t)m * nwin;
+    std::vector<uint32_t> keys(pairs), vals(pairs);
+    for (uint32_t t = 0; t < m; t++) body_msm_keys<KL>(t, m, nwin, wb, sc.data(), keys.data(), vals.data());
+    std::vector<size_t> order(pairs);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return keys[a] < keys[b]; });
+    std::vector<uint32_t> k2(pairs), v2(pairs);
+    for (size_t i = 0; i < pairs; i++) { k2[i] = keys[order[i]]; v2[i] = vals[order[i]]; }
+    std::vector<uint32_t> buckets((size_t)2 * nwin * nb * 3 * F::WORDS), segs((size_t)2 * nwin * nseg * 6 * F::WORDS),
+        wins((size_t)2 * nwin * 3 * F::WORDS);
+    for (uint32_t t = 0; t < nwin * nb; t++)
+      body_msm_buckets<G>(t, m, nwin, wb, k2.data(), v2.data(), aff.data(), aff.data() + 2 * F::WORDS, buckets.data());
+    for (uint32_t t = 0; t < 2 * nwin * nseg; t++) body_msm_fold<G>(t, nwin, wb, buckets.data(), segs.data());
+    for (uint32_t t = 0; t < 2 * nwin; t++) body_msm_window<G>(t, nwin, wb, segs.data(), wins.data());
+    for (uint32_t t = 0; t < 2; t++) body_msm_final<G>(t, nwin, wb, wins.data(), out_pair);
+  });
+}
+
+// same_ratio: verdicts[i] = 1 if e(a, d) == e(b, c), 0 if not, 0x100 + status on undecodable input
+template <class G1, class G2, class PP> static void same_ratio_emul(const uint8_t* checks, uint32_t n, uint32_t* verdicts) {
+  using PR = Pairing<G1, G2, PP>;
+  using Fq = typename G1::F;
+  for (uint32_t i = 0; i < n; i++) {
+    typename PR::Ws w0, w1;
+    uint32_t s0 = PR::run_side(0, w0, checks + (size_t)i * PR::CHECK_BYTES, 0);
+    uint32_t s1 = PR::run_side(0, w1, checks + (size_t)i * PR::CHECK_BYTES, 1);
+    if (s0 || s1) { verdicts[i] = 0x100 + (s0 ? s0 : s1); continue; }
+    bool eq = true;
+    for (int l = 0; l < PR::K; l++) eq = eq && Fq::eq(w0.f[l], w1.f[l]);
+    verdicts[i] = eq ? 1 : 0;
+  }
+}
+extern "C" int emul_same_ratio(uint32_t curve, const uint8_t* checks, uint32_t n, uint32_t* verdicts) {
+  switch (curve) {
+    case 0: same_ratio_emul<Bls12_377_G1, Bls12_377_G2, PAIR_bls12_377>(checks, n, verdicts); return 0;
+    case 1: same_ratio_emul<Bw6_761_G1, Bw6_761_G2, PAIR_bw6_761>(checks, n, verdicts); return 0;
+    case 2: same_ratio_emul<Mnt4_753_G1, Mnt4_753_G2, PAIR_mnt4_753>(checks, n, verdicts); return 0;
+    case 3: same_ratio_emul<Mnt6_753_G1, Mnt6_753_G2, PAIR_mnt6_753>(checks, n, verdicts); return 0;
+  }
+  return -1;
 }

@@ -174,3 +174,50 @@ def test_multi_vector_launch(emul, name, gi):
                                 words(key.tau, Lr), words(key.alpha, Lr), words(key.beta, Lr), ctypes.c_uint64(first), out0, out1,
                                 st) == 0
     assert out0.raw == want0 and out1.raw == want1 and st[0] == 0
+
+
+@pytest.mark.parametrize("name,gi,wb", [("bls12_377", 0, 4), ("bls12_377", 1, 7), ("bw6_761", 0, 5), ("mnt4_753", 0, 6)])
+def test_power_pairs_msm(emul, name, gi, wb):
+    """Pippenger pipeline (keys, buckets, segmented fold, window sums, Horner) against the oracle's
+    plain sum r_i P_i with the same ChaCha20-derived scalars."""
+    from oracle import phase1
+    c = get_curve(name)
+    G = (c.g1, c.g2)[gi]
+    rnd = random.Random(5 + gi)
+    n = 9
+    pts = [G.mul(G.gen, rnd.randrange(1, G.r)) for _ in range(n)]
+    pts[3] = None                                           # infinity inside the vector
+    seed = bytes(range(100, 132))
+    rs = phase1.rlc_scalars(c, seed, n - 1)
+    a, b = phase1.power_pairs_with(G, pts, rs)
+    want = ser.point_to_bytes(G, a, False) + ser.point_to_bytes(G, b, False)
+    out = ctypes.create_string_buffer(len(want))
+    st = (ctypes.c_uint32 * 3)()
+    seed_words = (ctypes.c_uint32 * 8).from_buffer_copy(seed)
+    assert emul.emul_power_pairs(c.cid, gi, ser.points_to_bytes(G, pts, True), 1, n, seed_words, wb, out, None, st) == 0
+    assert out.raw == want
+
+
+@pytest.mark.parametrize("name", CURVE_NAMES)
+def test_same_ratio_pairing(emul, name):
+    """Device Tate pairing (lane-per-coefficient Fq^k arithmetic, Miller loop, final exponentiation)
+    against the oracle's verdicts: equal ratios accept, unequal reject, infinity handled."""
+    from oracle import pairing
+    c = get_curve(name)
+    g1, g2 = c.g1, c.g2
+    P = g1.mul(g1.gen, 0x1234567)
+    Q = g2.mul(g2.gen, 0x7654321)
+    x = 0xABCDEF0123456789
+    cases = [((P, g1.mul(P, x)), (Q, g2.mul(Q, x)), True),
+             ((P, g1.mul(P, x)), (Q, g2.mul(Q, x + 1)), False),
+             ((g1.gen, g1.gen), (g2.gen, g2.gen), True)]
+    buf = b""
+    for (a, b), (cc, d), _ in cases:
+        buf += ser.point_to_bytes(g1, a, False) + ser.point_to_bytes(g1, b, False)
+        buf += ser.point_to_bytes(g2, cc, False) + ser.point_to_bytes(g2, d, False)
+    verdicts = (ctypes.c_uint32 * len(cases))()
+    assert emul.emul_same_ratio(c.cid, buf, len(cases), verdicts) == 0
+    assert [int(v) for v in verdicts] == [1 if w else 0 for _, _, w in cases]
+    if name == "bls12_377":
+        for (a, b), (cc, d), want in cases[:2]:
+            assert pairing.same_ratio(c, (a, b), (cc, d)) == want

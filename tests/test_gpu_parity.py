@@ -169,3 +169,47 @@ def test_imad_probe_runs():
     for variant in (0, 1, 2):
         sso._lib.call("sso_imad_peak", 0, variant, ctypes.byref(out))
         assert out.value > 1e11
+
+
+@pytest.mark.parametrize("name,gi,n", [("bls12_377", 0, 300), ("bls12_377", 1, 70), ("bw6_761", 0, 40), ("mnt4_753", 1, 20),
+                                        ("mnt6_753", 1, 12)])
+def test_power_and_merge_pairs_match_oracle(name, gi, n):
+    """Pippenger MSM on the GPU (CUB-sorted buckets) against the oracle's plain sum r_i P_i with the same
+    ChaCha20-derived scalars; inputs are decompressed and checked on the way in."""
+    c = get_curve(name)
+    G = (c.g1, c.g2)[gi]
+    rnd = random.Random(n)
+    base = [G.mul(G.gen, rnd.randrange(1, G.r)) for _ in range(6)]
+    pts = [base[i % 6] if i % 7 else G.add(base[i % 6], base[(i + 1) % 6]) for i in range(n)]
+    seed = bytes(range(7, 39))
+    rs = phase1.rlc_scalars(c, seed, n)
+    a, b = phase1.power_pairs_with(G, pts, rs[:n - 1])
+    got = sso.power_pairs(name, gi, dev_bytes(ser.points_to_bytes(G, pts, True)), n, in_compressed=True, check=sso.CHECK_FULL,
+                          subgroup_check=True, seed32=seed)
+    assert got == ser.point_to_bytes(G, a, False) + ser.point_to_bytes(G, b, False)
+    pts2 = [G.mul(P, 3) for P in pts]
+    a2, b2 = phase1.merge_pairs_with(G, pts, pts2, rs)
+    got2 = sso.merge_pairs(name, gi, dev_bytes(ser.points_to_bytes(G, pts, False)), dev_bytes(ser.points_to_bytes(G, pts2, False)), n,
+                           seed32=seed)
+    assert got2 == ser.point_to_bytes(G, a2, False) + ser.point_to_bytes(G, b2, False)
+    assert G.eq(G.mul(a2, 3), b2)                        # the pair has the ratio the vectors have
+
+
+@pytest.mark.parametrize("name", CURVE_NAMES)
+def test_same_ratio_verdicts(name):
+    c = get_curve(name)
+    g1, g2 = c.g1, c.g2
+    P, Q = g1.mul(g1.gen, 0x1234567), g2.mul(g2.gen, 0x7654321)
+    x = 0xABCDEF0123456789
+
+    def u(G, pt):
+        return ser.point_to_bytes(G, pt, False)
+
+    checks = [(u(g1, P), u(g1, g1.mul(P, x)), u(g2, Q), u(g2, g2.mul(Q, x))),
+              (u(g1, P), u(g1, g1.mul(P, x)), u(g2, Q), u(g2, g2.mul(Q, x + 1))),
+              (u(g1, g1.gen), u(g1, g1.gen), u(g2, g2.gen), u(g2, g2.gen))]
+    assert sso.same_ratio(name, checks) == [True, False, True]
+    bad = bytearray(checks[0][0]); bad[3] ^= 1                      # not on the curve any more
+    with pytest.raises(sso.SsoError) as e:
+        sso.same_ratio(name, [(bytes(bad),) + checks[0][1:]])
+    assert e.value.code == -3
