@@ -158,6 +158,42 @@ int32_t sso_profile_enable(int32_t on);
 int32_t sso_profile_reset(void);
 int32_t sso_profile_read(uint64_t* out, size_t cap);
 
+/* Phase1::key_generation (reached from phase1_cli::contribute, reference src/bin/contribute.rs:789, 811-823): the
+ * contributor RNG is ChaCha20 seeded with seed32 (setup_utils::derive_rng_from_seed); digest64 = Blake2b(challenge).
+ * scalars_out: tau | alpha | beta canonical little-endian (3 * Fr bytes); pubkey_out: the serialized PublicKey
+ * (tau_g1.0, tau_g1.1, alpha_g1.0, alpha_g1.1, beta_g1.0, beta_g1.1, tau_g2, alpha_g2, beta_g2, all uncompressed). */
+int32_t sso_p1_keygen(uint32_t curve, const uint8_t seed32[32], const uint8_t digest64[64], uint8_t* scalars_out, size_t scalars_len,
+                      uint8_t* pubkey_out, size_t pubkey_len, int device, char* err, size_t errcap);
+
+/* phase1_cli::contribute on host buffers, including hashing, key generation from the seeded RNG and the public key. */
+int32_t sso_p1_contribute_seeded_buf(const sso_p1_params_t* p, const uint8_t* challenge, size_t challenge_len, uint8_t* response,
+                                     size_t response_len, const uint8_t seed32[32], uint32_t check_input, int device, char* err,
+                                     size_t errcap);
+
+/* phase1_cli::contribute(challenge_fn, challenge_hash_fn, response_fn, response_hash_fn, check_input, batch_exp_mode,
+ * &parameters, rng) — reference src/bin/contribute.rs:811-823, src/bin/verify_transcript.rs:678-696,
+ * src/bin/control.rs:793-808.  The rng argument becomes its 32-byte seed.  Output files must not exist. */
+int32_t sso_p1_contribute_file(const sso_p1_params_t* p, const char* challenge_fn, const char* challenge_hash_fn,
+                               const char* response_fn, const char* response_hash_fn, uint32_t check_input, uint32_t batch_exp_mode,
+                               const uint8_t seed32[32], int device, char* err, size_t errcap);
+
+/* Phase1::verification of one chunk on host buffers (row a5): hash chain, proofs of knowledge, per-element checks of
+ * the response (check_output, subgroup_check_mode), chunk-0 update checks, optional power-ratio checks via random
+ * linear combinations (ratio_check), and the decompressed new challenge whose hash slot is Blake2b(response).
+ * A rejected contribution is SSO_E_VERIFY with the failed check named in err.  rlc_seed32 == NULL: fresh entropy. */
+int32_t sso_p1_verify_chunk_buf(const sso_p1_params_t* p, const uint8_t* challenge, size_t challenge_len, const uint8_t* response,
+                                size_t response_len, uint8_t* new_challenge, size_t new_challenge_len, uint32_t check_input,
+                                uint32_t check_output, uint32_t subgroup_check_mode, uint32_t ratio_check, const uint8_t* rlc_seed32,
+                                int device, char* err, size_t errcap);
+
+/* phase1_cli::transform_pok_and_correctness(challenge_fn, challenge_hash_fn, check_input, response_fn, response_hash_fn,
+ * check_output, new_challenge_fn, new_challenge_hash_fn, subgroup_check_mode, ratio_check, &parameters) —
+ * reference src/bin/contribute.rs:968-986, src/bin/verify_transcript.rs:466-484, 746-776, src/bin/control.rs:841-865. */
+int32_t sso_p1_verify_chunk_file(const sso_p1_params_t* p, const char* challenge_fn, const char* challenge_hash_fn, uint32_t check_input,
+                                 const char* response_fn, const char* response_hash_fn, uint32_t check_output,
+                                 const char* new_challenge_fn, const char* new_challenge_hash_fn, uint32_t subgroup_check_mode,
+                                 uint32_t ratio_check, int device, char* err, size_t errcap);
+
 /* setup_utils::calculate_hash (reference src/utils.rs:618-623): Blake2b-512, unkeyed. Host only. */
 int32_t sso_blake2b_512(const uint8_t* data, size_t len, uint8_t out[64]);
 

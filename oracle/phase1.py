@@ -298,3 +298,57 @@ def rlc_scalars(curve: Curve, seed32: bytes, n: int):
         v = sum(w << (32 * j) for j, w in enumerate(words))
         out.append(v & ((1 << sbits) - 1))
     return out
+
+
+def verify_chunk(params: Phase1Params, challenge: bytes, response: bytes, check_out: int = CHECK_FULL, subgroup: bool = True,
+                 ratio_check: bool = True, rlc_seed32: bytes = bytes(32)) -> bytes:
+    """Phase1::verification of one chunk with real pairings (oracle/pairing.py): hash chain, the three proofs of
+    knowledge, per-element checks, chunk-0 update checks, power-ratio checks on random linear combinations.
+    Returns the new challenge; raises VerificationError naming the failed check.  [UP] for the exact list of
+    checks; the product (csrc/flows.cuh) performs the same list."""
+    from .pairing import same_ratio
+    c = params.curve
+    g1, g2 = c.g1, c.g2
+    if len(response) != params.contribution_size or len(challenge) != params.accumulator_size:
+        raise VerificationError("wrong size")
+    digest = calculate_hash(challenge)
+    if response[:HASH_SIZE] != digest:
+        raise VerificationError("hash chain broken: response does not continue the challenge")
+    body = response[:len(response) - params.public_key_size]
+    pub = PublicKey.from_bytes(c, response[len(body):])
+    try:
+        vout = read_chunk(params, body, True)
+    except ser.FormatError as e:
+        raise VerificationError(str(e))
+    for G, pts in ((g1, vout.tau_g1), (g2, vout.tau_g2), (g1, vout.alpha_g1), (g1, vout.beta_g1), (g2, [vout.beta_g2])):
+        for P in pts:
+            check_point(G, P, check_out, subgroup)
+    vin = read_chunk(params, challenge, False)
+    g2_s = [compute_g2_s(c, digest, pair[0], pair[1], i) for i, pair in enumerate((pub.tau_g1, pub.alpha_g1, pub.beta_g1))]
+    g2_sx = [pub.tau_g2, pub.alpha_g2, pub.beta_g2]
+    checks = [("proof of knowledge: tau", pub.tau_g1, (g2_s[0], g2_sx[0])),
+              ("proof of knowledge: alpha", pub.alpha_g1, (g2_s[1], g2_sx[1])),
+              ("proof of knowledge: beta", pub.beta_g1, (g2_s[2], g2_sx[2]))]
+    if params.chunk_index == 0 and params.other_count >= 2:
+        if not g1.eq(vout.tau_g1[0], g1.gen):
+            raise VerificationError("tau_g1[0] is not the G1 generator")
+        if not g2.eq(vout.tau_g2[0], g2.gen):
+            raise VerificationError("tau_g2[0] is not the G2 generator")
+        checks += [("before/after: tau_g1[1] vs tau proof", (vin.tau_g1[1], vout.tau_g1[1]), (g2_s[0], g2_sx[0])),
+                   ("before/after: alpha_g1[0] vs alpha proof", (vin.alpha_g1[0], vout.alpha_g1[0]), (g2_s[1], g2_sx[1])),
+                   ("before/after: beta_g1[0] vs beta proof", (vin.beta_g1[0], vout.beta_g1[0]), (g2_s[2], g2_sx[2])),
+                   ("before/after: beta_g2 vs beta_g1[0]", (vin.beta_g1[0], vout.beta_g1[0]), (vin.beta_g2, vout.beta_g2))]
+    if ratio_check and params.other_count >= 2:
+        def pp(G, v):
+            return power_pairs_with(G, v, rlc_scalars(c, rlc_seed32, len(v) - 1))
+        g2p = pp(g2, vout.tau_g2)
+        g2_exact = (vout.tau_g2[0], vout.tau_g2[1]) if params.chunk_index == 0 else g2p
+        checks.append(("power ratio: tau_g1", pp(g1, vout.tau_g1), g2_exact))
+        checks.append(("power ratio: alpha_g1", pp(g1, vout.alpha_g1), g2_exact))
+        checks.append(("power ratio: beta_g1", pp(g1, vout.beta_g1), g2_exact))
+        if params.chunk_index == 0:
+            checks.append(("power ratio: tau_g2", (vout.tau_g1[0], vout.tau_g1[1]), g2p))
+    for name, p1, p2 in checks:
+        if not same_ratio(c, p1, p2):
+            raise VerificationError("same_ratio check failed: " + name)
+    return write_chunk(params, calculate_hash(response), vout, False)

@@ -4,8 +4,7 @@
 // phase1_cli / phase2_cli on this path is computed on the GPU; the host side
 // only moves bytes, hashes (Blake2b, sequential by construction) and checks sizes.
 // There is no CPU fallback: without a device every compute entry returns SSO_E_CUDA.
-#include "blake2b.h"
-#include "curve_ops.cuh"
+#include "flows.cuh"
 
 using namespace sso;
 
@@ -448,6 +447,110 @@ int32_t sso_profile_read(uint64_t* out, size_t cap) {
     out[3 * i + 2] = g_prof[i].elems.load();
   }
   return (int32_t)PK_COUNT;
+}
+
+// Phase1::key_generation from the contributor seed (a3, a13)
+int32_t sso_p1_keygen(uint32_t curve, const uint8_t seed32[32], const uint8_t digest64[64], uint8_t* scalars_out, size_t scalars_len,
+                      uint8_t* pubkey_out, size_t pubkey_len, int device, char* err, size_t errcap) {
+  const CurveOps* ops = ops_for(curve);
+  CurveSizes cs;
+  if (!ops || !curve_sizes(curve, cs) || !seed32 || !digest64) { set_err(err, errcap, "unknown curve %u or null argument", curve); return SSO_E_ARG; }
+  if (scalars_len != 3 * cs.fr || pubkey_len != 6 * cs.g1u + 3 * cs.g2u) { set_err(err, errcap, "keygen: wrong output sizes"); return SSO_E_ARG; }
+  Ctx c(err, errcap);
+  int rc = c.init(device);
+  if (rc) return rc;
+  return keygen_host(c, ops, cs, seed32, digest64, 3, scalars_out, pubkey_out, err, errcap);
+}
+
+// phase1_cli::contribute on host buffers: hash, key generation from the seeded RNG, computation, public key
+int32_t sso_p1_contribute_seeded_buf(const sso_p1_params_t* p, const uint8_t* challenge, size_t challenge_len, uint8_t* response,
+                                     size_t response_len, const uint8_t seed32[32], uint32_t check_input, int device, char* err,
+                                     size_t errcap) {
+  P1Layout L;
+  int rc = p1_layout(p, L, err, errcap);
+  if (rc) return rc;
+  if (!challenge || !response || !seed32) { set_err(err, errcap, "null argument"); return SSO_E_ARG; }
+  if (challenge_len != L.acc_size) { set_err(err, errcap, "challenge has %zu bytes, expected accumulator_size %llu", challenge_len, (unsigned long long)L.acc_size); return SSO_E_ARG; }
+  if (response_len != L.contrib_size) { set_err(err, errcap, "response has %zu bytes, expected contribution_size %llu", response_len, (unsigned long long)L.contrib_size); return SSO_E_ARG; }
+  const CurveOps* ops = ops_for(p->curve);
+  uint8_t digest[64];
+  blake2b_512(challenge, challenge_len, digest);
+  std::vector<uint8_t> scalars(3 * L.cs.fr), pubkey(L.pk_size);
+  {
+    Ctx c(err, errcap);
+    if ((rc = c.init(device))) return rc;
+    if ((rc = keygen_host(c, ops, L.cs, seed32, digest, 3, scalars.data(), pubkey.data(), err, errcap))) return rc;
+  }
+  return sso_p1_contribute_buf(p, challenge, challenge_len, response, response_len, scalars.data(), scalars.data() + L.cs.fr,
+                               scalars.data() + 2 * L.cs.fr, pubkey.data(), pubkey.size(), check_input, device, err, errcap);
+}
+
+// phase1_cli::contribute(challenge_fn, challenge_hash_fn, response_fn, response_hash_fn, check_input, batch_exp_mode, params, rng)
+int32_t sso_p1_contribute_file(const sso_p1_params_t* p, const char* challenge_fn, const char* challenge_hash_fn,
+                               const char* response_fn, const char* response_hash_fn, uint32_t check_input, uint32_t batch_exp_mode,
+                               const uint8_t seed32[32], int device, char* err, size_t errcap) {
+  (void)batch_exp_mode;                                    // outputs are mode-independent
+  P1Layout L;
+  int rc = p1_layout(p, L, err, errcap);
+  if (rc) return rc;
+  std::vector<uint8_t> challenge;
+  if ((rc = read_file(challenge_fn, challenge, err, errcap))) return rc;
+  if (challenge.size() != L.acc_size) { set_err(err, errcap, "The size of challenge file should be correct: %zu != %llu", challenge.size(), (unsigned long long)L.acc_size); return SSO_E_ARG; }
+  std::vector<uint8_t> response(L.contrib_size);
+  if ((rc = sso_p1_contribute_seeded_buf(p, challenge.data(), challenge.size(), response.data(), response.size(), seed32, check_input,
+                                         device, err, errcap))) return rc;
+  uint8_t h[64];
+  if ((rc = write_new_file(challenge_hash_fn, response.data(), 64, err, errcap))) return rc;     // response[0..64) = hash(challenge)
+  if ((rc = write_new_file(response_fn, response.data(), response.size(), err, errcap))) return rc;
+  blake2b_512(response.data(), response.size(), h);
+  return write_new_file(response_hash_fn, h, 64, err, errcap);
+}
+
+// Phase1::verification for one chunk on host buffers (a5)
+int32_t sso_p1_verify_chunk_buf(const sso_p1_params_t* p, const uint8_t* challenge, size_t challenge_len, const uint8_t* response,
+                                size_t response_len, uint8_t* new_challenge, size_t new_challenge_len, uint32_t check_input,
+                                uint32_t check_output, uint32_t subgroup_check_mode, uint32_t ratio_check, const uint8_t* rlc_seed32,
+                                int device, char* err, size_t errcap) {
+  (void)check_input;   // the challenge was produced (and checked) by the previous verification; kept for signature parity
+  P1Layout L;
+  int rc = p1_layout(p, L, err, errcap);
+  if (rc) return rc;
+  if (!challenge || !response || !new_challenge) { set_err(err, errcap, "null argument"); return SSO_E_ARG; }
+  if (challenge_len != L.acc_size || new_challenge_len != L.acc_size) { set_err(err, errcap, "challenge / new challenge must have accumulator_size %llu bytes", (unsigned long long)L.acc_size); return SSO_E_ARG; }
+  if (response_len != L.contrib_size) { set_err(err, errcap, "response has %zu bytes, expected contribution_size %llu", response_len, (unsigned long long)L.contrib_size); return SSO_E_ARG; }
+  const CurveOps* ops = ops_for(p->curve);
+  Ctx c(err, errcap);
+  if ((rc = c.init(device, 2))) return rc;
+  uint64_t chunk_index = p->contribution_mode == SSO_MODE_FULL ? 0 : p->chunk_index;
+  return verify_chunk_host(c, ops, L, p->curve, chunk_index, challenge, response, new_challenge, check_output, subgroup_check_mode,
+                           ratio_check, rlc_seed32, err, errcap);
+}
+
+// phase1_cli::transform_pok_and_correctness(challenge_fn, challenge_hash_fn, check_input, response_fn, response_hash_fn,
+//                                           check_output, new_challenge_fn, new_challenge_hash_fn, subgroup_check_mode, ratio_check, params)
+int32_t sso_p1_verify_chunk_file(const sso_p1_params_t* p, const char* challenge_fn, const char* challenge_hash_fn, uint32_t check_input,
+                                 const char* response_fn, const char* response_hash_fn, uint32_t check_output,
+                                 const char* new_challenge_fn, const char* new_challenge_hash_fn, uint32_t subgroup_check_mode,
+                                 uint32_t ratio_check, int device, char* err, size_t errcap) {
+  P1Layout L;
+  int rc = p1_layout(p, L, err, errcap);
+  if (rc) return rc;
+  std::vector<uint8_t> challenge, response;
+  if ((rc = read_file(challenge_fn, challenge, err, errcap))) return rc;
+  if ((rc = read_file(response_fn, response, err, errcap))) return rc;
+  if (challenge.size() != L.acc_size) { set_err(err, errcap, "The size of challenge file should be correct: %zu != %llu", challenge.size(), (unsigned long long)L.acc_size); return SSO_E_ARG; }
+  if (response.size() != L.contrib_size) { set_err(err, errcap, "The size of response file should be correct: %zu != %llu", response.size(), (unsigned long long)L.contrib_size); return SSO_E_ARG; }
+  std::vector<uint8_t> new_challenge(L.acc_size);
+  if ((rc = sso_p1_verify_chunk_buf(p, challenge.data(), challenge.size(), response.data(), response.size(), new_challenge.data(),
+                                    new_challenge.size(), check_input, check_output, subgroup_check_mode, ratio_check, nullptr, device,
+                                    err, errcap))) return rc;
+  uint8_t h[64];
+  blake2b_512(challenge.data(), challenge.size(), h);
+  if ((rc = write_new_file(challenge_hash_fn, h, 64, err, errcap))) return rc;
+  if ((rc = write_new_file(response_hash_fn, new_challenge.data(), 64, err, errcap))) return rc;   // new_challenge[0..64) = hash(response)
+  if ((rc = write_new_file(new_challenge_fn, new_challenge.data(), new_challenge.size(), err, errcap))) return rc;
+  blake2b_512(new_challenge.data(), new_challenge.size(), h);
+  return write_new_file(new_challenge_hash_fn, h, 64, err, errcap);
 }
 
 int32_t sso_imad_peak(int device, int variant, double* macs_per_s, char* err, size_t errcap) {

@@ -6,6 +6,7 @@
 #include "kernels.cuh"
 #include "msm.cuh"
 #include "pairing.cuh"
+#include "keygen.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <random>
 
@@ -30,6 +31,13 @@ struct CurveOps {
   // 0 = different, 0x100 + code = undecodable input
   int (*same_ratio)(Ctx& c, int si, const uint8_t* d_checks, uint64_t n, uint32_t* d_verdicts, char* err, size_t errcap);
   uint32_t check_bytes;
+  // a3: key generation pieces.  keygen_g1: nscalars Fr::rand draws then, per scalar, g1_s <- G1::rand and
+  // g1_s_x; d_scalars: nscalars * Fr words (canonical), d_g1: 2 * nscalars uncompressed G1 points.
+  int (*keygen_g1)(Ctx& c, int si, const uint32_t* d_seed, uint32_t nscalars, uint32_t* d_scalars, uint8_t* d_g1, char* err, size_t errcap);
+  // hash_to_g2 for n seeds (8 words each); d_scalars / d_g2_sx may be null (verification only needs g2_s)
+  int (*hash_to_g2)(Ctx& c, int si, uint32_t n, const uint32_t* d_seeds, const uint32_t* d_scalars, uint8_t* d_g2_s, uint8_t* d_g2_sx,
+                    char* err, size_t errcap);
+  uint32_t fr_words;
   // phase1_cli::new_challenge: n copies of the group generator, uncompressed or compressed
   int (*fill_generator)(Ctx& c, int si, uint32_t group, uint64_t n, uint8_t* d_out, uint32_t out_compressed, char* err, size_t errcap);
   uint32_t fr_bytes;
@@ -186,6 +194,16 @@ inline int run_same_ratio(Ctx& c, int si, const uint8_t* d_checks, uint64_t n, u
   return SSO_OK;
 }
 
+template <class G1>
+__global__ void k_keygen_g1(const uint32_t* seed, uint32_t nscalars, uint32_t* scalars_out, uint8_t* g1_out) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) body_keygen_g1<G1>(seed, nscalars, scalars_out, g1_out);
+}
+template <class G2>
+__global__ void k_hash_to_g2(uint32_t n, const uint32_t* seeds, const uint32_t* scalars, uint8_t* g2_s, uint8_t* g2_sx) {
+  // one point per block so that the long single-thread chains land on different SMs
+  if (threadIdx.x == 0) body_hash_to_g2<G2>(blockIdx.x, n, seeds, scalars, g2_s, g2_sx);
+}
+
 inline uint32_t msm_window_bits(uint64_t n) {
   uint32_t lg = 0;
   while ((2ull << lg) <= n) lg++;
@@ -286,6 +304,23 @@ template <class G1, class G2, class PP> struct CurveImpl {
     set_err(err, errcap, "unknown group %u", group);
     return SSO_E_ARG;
   }
+  static int keygen_g1(Ctx& c, int si, const uint32_t* d_seed, uint32_t nscalars, uint32_t* d_scalars, uint8_t* d_g1, char* err, size_t errcap) {
+    if (nscalars < 1 || nscalars > 3) { set_err(err, errcap, "keygen: 1..3 scalars"); return SSO_E_ARG; }
+    c.begin(PK_OTHER, si, nscalars);
+    k_keygen_g1<G1><<<1, 32, 0, c.s[si]>>>(d_seed, nscalars, d_scalars, d_g1);
+    c.end(si);
+    CUDA_TRY(cudaGetLastError());
+    return SSO_OK;
+  }
+  static int hash_to_g2(Ctx& c, int si, uint32_t n, const uint32_t* d_seeds, const uint32_t* d_scalars, uint8_t* d_g2_s, uint8_t* d_g2_sx,
+                        char* err, size_t errcap) {
+    if (n == 0) return SSO_OK;
+    c.begin(PK_OTHER, si, n);
+    k_hash_to_g2<G2><<<n, 32, 0, c.s[si]>>>(n, d_seeds, d_scalars, d_g2_s, d_g2_sx);
+    c.end(si);
+    CUDA_TRY(cudaGetLastError());
+    return SSO_OK;
+  }
   static int fill_generator(Ctx& c, int si, uint32_t group, uint64_t n, uint8_t* d_out, uint32_t out_compressed, char* err, size_t errcap) {
     if (group == GROUP_G1) return run_fill_generator<G1>(c, si, n, d_out, out_compressed, err, errcap);
     if (group == GROUP_G2) return run_fill_generator<G2>(c, si, n, d_out, out_compressed, err, errcap);
@@ -293,7 +328,7 @@ template <class G1, class G2, class PP> struct CurveImpl {
     return SSO_E_ARG;
   }
   static const CurveOps* ops() {
-    static const CurveOps o = {&tau_tables, &batch_exp, &reencode, &msm_pairs, &same_ratio, (uint32_t)Pairing<G1, G2, PP>::CHECK_BYTES, &fill_generator, (uint32_t)G1::Fr::NBYTES, {2u * G1::F::WORDS, 2u * G2::F::WORDS}};
+    static const CurveOps o = {&tau_tables, &batch_exp, &reencode, &msm_pairs, &same_ratio, (uint32_t)Pairing<G1, G2, PP>::CHECK_BYTES, &keygen_g1, &hash_to_g2, (uint32_t)G1::Fr::L, &fill_generator, (uint32_t)G1::Fr::NBYTES, {2u * G1::F::WORDS, 2u * G2::F::WORDS}};
     return &o;
   }
 };

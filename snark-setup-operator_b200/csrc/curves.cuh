@@ -25,7 +25,9 @@ using Fq6x3 = Fp3<Fq6, SmallNR<Fq6, 11, false>>;          // u^3 = 11
   __device__ __forceinline__ static typename F::T coeff_b() { return F::from_const(c_##NAME##_b); } \
   __device__ __forceinline__ static const uint32_t* order() { return c_##NAME##_order; }           \
   __device__ __forceinline__ static typename F::T gen_x() { return F::from_const(c_##NAME##_gx); }  \
-  __device__ __forceinline__ static typename F::T gen_y() { return F::from_const(c_##NAME##_gy); }
+  __device__ __forceinline__ static typename F::T gen_y() { return F::from_const(c_##NAME##_gy); }  \
+  __device__ __forceinline__ static const uint32_t* cofactor() { return c_##NAME##_cofactor; }      \
+  static constexpr int COFACTOR_WORDS = COFACTOR_WORDS_##NAME;
 
 struct Bls12_377_G1 {
   static constexpr bool HAS_GLV = true;

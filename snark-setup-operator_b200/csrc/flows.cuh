@@ -1,0 +1,240 @@
+// Host-side orchestration of the file-level ceremony calls:
+// what phase1_cli::contribute and phase1_cli::transform_pok_and_correctness do around the kernels —
+// size asserts, the Blake2b hash chain, key generation from the seeded RNG, the proof-of-knowledge and
+// ratio checks — expressed over the CurveOps table.  All arithmetic runs on the device.
+#pragma once
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include "blake2b.h"
+#include "curve_ops.cuh"
+
+namespace sso {
+
+// ---- small file helpers (the reference CLI mmaps inputs and creates outputs with create_new) ----
+inline int read_file(const char* path, std::vector<uint8_t>& out, char* err, size_t errcap) {
+  int fd = open(path, O_RDONLY);
+  if (fd < 0) { set_err(err, errcap, "cannot open %s", path); return SSO_E_IO; }
+  struct stat st;
+  if (fstat(fd, &st) != 0) { close(fd); set_err(err, errcap, "cannot stat %s", path); return SSO_E_IO; }
+  out.resize((size_t)st.st_size);
+  size_t got = 0;
+  while (got < out.size()) {
+    ssize_t r = read(fd, out.data() + got, out.size() - got);
+    if (r <= 0) { close(fd); set_err(err, errcap, "short read on %s", path); return SSO_E_IO; }
+    got += (size_t)r;
+  }
+  close(fd);
+  return SSO_OK;
+}
+inline int write_new_file(const char* path, const uint8_t* data, size_t len, char* err, size_t errcap) {
+  int fd = open(path, O_WRONLY | O_CREAT | O_EXCL, 0644);
+  if (fd < 0) { set_err(err, errcap, "cannot create %s (outputs must not exist)", path); return SSO_E_IO; }
+  size_t put = 0;
+  while (put < len) {
+    ssize_t w = write(fd, data + put, len - put);
+    if (w <= 0) { close(fd); unlink(path); set_err(err, errcap, "short write on %s", path); return SSO_E_IO; }
+    put += (size_t)w;
+  }
+  close(fd);
+  return SSO_OK;
+}
+
+// ---- key generation (Phase1::key_generation) ---------------------------------------------------
+// seed32: ChaCha20 seed of the contributor RNG; digest64: Blake2b(challenge).
+// scalars_out: nscalars canonical scalars (fr_bytes each); pubkey_out: 2*nscalars G1 + nscalars G2 uncompressed.
+inline int keygen_host(Ctx& c, const CurveOps* ops, const CurveSizes& cs, const uint8_t seed32[32], const uint8_t digest64[64],
+                       uint32_t nscalars, uint8_t* scalars_out, uint8_t* pubkey_out, char* err, size_t errcap) {
+  int rc;
+  uint32_t *d_seed, *d_scalars, *d_seeds2;
+  uint8_t *d_g1, *d_g2s, *d_g2sx;
+  const size_t g1u = cs.g1u, g2u = cs.g2u;
+  if ((rc = c.alloc((void**)&d_seed, 32))) return rc;
+  if ((rc = c.alloc((void**)&d_scalars, (size_t)nscalars * ops->fr_words * 4))) return rc;
+  if ((rc = c.alloc((void**)&d_g1, 2 * nscalars * g1u))) return rc;
+  if ((rc = c.alloc((void**)&d_seeds2, (size_t)nscalars * 32))) return rc;
+  if ((rc = c.alloc((void**)&d_g2s, nscalars * g2u))) return rc;
+  if ((rc = c.alloc((void**)&d_g2sx, nscalars * g2u))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(d_seed, seed32, 32, cudaMemcpyHostToDevice, c.s[0]));
+  if ((rc = ops->keygen_g1(c, 0, d_seed, nscalars, d_scalars, d_g1, err, errcap))) return rc;
+  std::vector<uint8_t> g1(2 * nscalars * g1u);
+  std::vector<uint32_t> sc((size_t)nscalars * ops->fr_words);
+  CUDA_TRY(cudaMemcpyAsync(g1.data(), d_g1, g1.size(), cudaMemcpyDeviceToHost, c.s[0]));
+  CUDA_TRY(cudaMemcpyAsync(sc.data(), d_scalars, sc.size() * 4, cudaMemcpyDeviceToHost, c.s[0]));
+  CUDA_TRY(cudaStreamSynchronize(c.s[0]));
+  // compute_g2_s: Blake2b(personalization || digest || g1_s || g1_s_x)[..32] seeds hash_to_g2
+  std::vector<uint8_t> seeds2((size_t)nscalars * 32);
+  for (uint32_t i = 0; i < nscalars; i++) {
+    Blake2b h(64);
+    uint8_t pers = (uint8_t)i, full[64];
+    h.update(&pers, 1);
+    h.update(digest64, 64);
+    h.update(g1.data() + (size_t)2 * i * g1u, 2 * g1u);
+    h.final(full, 64);
+    memcpy(seeds2.data() + 32 * i, full, 32);
+  }
+  CUDA_TRY(cudaMemcpyAsync(d_seeds2, seeds2.data(), seeds2.size(), cudaMemcpyHostToDevice, c.s[0]));
+  if ((rc = ops->hash_to_g2(c, 0, nscalars, d_seeds2, d_scalars, d_g2s, d_g2sx, err, errcap))) return rc;
+  memcpy(pubkey_out, g1.data(), g1.size());
+  CUDA_TRY(cudaMemcpyAsync(pubkey_out + g1.size(), d_g2sx, nscalars * g2u, cudaMemcpyDeviceToHost, c.s[0]));
+  CUDA_TRY(cudaStreamSynchronize(c.s[0]));
+  for (uint32_t i = 0; i < nscalars; i++)
+    memcpy(scalars_out + (size_t)i * ops->fr_bytes, sc.data() + (size_t)i * ops->fr_words, ops->fr_bytes);
+  return SSO_OK;
+}
+
+// ---- chunk verification (Phase1::verification, chunked mode) --------------------------------------
+struct RatioCheck { std::string name; std::vector<uint8_t> bytes; };
+
+inline void add_check(std::vector<RatioCheck>& v, const char* name, const uint8_t* a, const uint8_t* b, size_t g1u, const uint8_t* cc,
+                      const uint8_t* d, size_t g2u) {
+  RatioCheck r;
+  r.name = name;
+  r.bytes.resize(2 * g1u + 2 * g2u);
+  memcpy(r.bytes.data(), a, g1u);
+  memcpy(r.bytes.data() + g1u, b, g1u);
+  memcpy(r.bytes.data() + 2 * g1u, cc, g2u);
+  memcpy(r.bytes.data() + 2 * g1u + g2u, d, g2u);
+  v.push_back(std::move(r));
+}
+
+// runs all collected same_ratio checks in one launch; SSO_E_VERIFY names the first failing one
+inline int run_checks(Ctx& c, const CurveOps* ops, const std::vector<RatioCheck>& checks, char* err, size_t errcap) {
+  if (checks.empty()) return SSO_OK;
+  size_t cb = ops->check_bytes, n = checks.size();
+  std::vector<uint8_t> flat(n * cb);
+  for (size_t i = 0; i < n; i++) memcpy(flat.data() + i * cb, checks[i].bytes.data(), cb);
+  uint8_t* d_checks;
+  uint32_t* d_verdicts;
+  int rc;
+  if ((rc = c.alloc((void**)&d_checks, flat.size()))) return rc;
+  if ((rc = c.alloc((void**)&d_verdicts, n * 4))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(d_checks, flat.data(), flat.size(), cudaMemcpyHostToDevice, c.s[0]));
+  if ((rc = ops->same_ratio(c, 0, d_checks, n, d_verdicts, err, errcap))) return rc;
+  std::vector<uint32_t> v(n);
+  CUDA_TRY(cudaMemcpyAsync(v.data(), d_verdicts, n * 4, cudaMemcpyDeviceToHost, c.s[0]));
+  CUDA_TRY(cudaStreamSynchronize(c.s[0]));
+  for (size_t i = 0; i < n; i++) {
+    if (v[i] >= 0x100u) { set_err(err, errcap, "same_ratio check '%s': %s", checks[i].name.c_str(), status_text(v[i] - 0x100u)); return SSO_E_VERIFY; }
+    if (v[i] != 1u) { set_err(err, errcap, "same_ratio check failed: %s", checks[i].name.c_str()); return SSO_E_VERIFY; }
+  }
+  return SSO_OK;
+}
+
+// challenge (uncompressed, host) + response (compressed + pubkey, host) -> new_challenge (uncompressed, host).
+// rlc_seed32: NULL = fresh entropy for the random linear combinations.
+inline int verify_chunk_host(Ctx& c, const CurveOps* ops, const P1Layout& L, uint32_t curve, uint64_t chunk_index,
+                             const uint8_t* challenge, const uint8_t* response, uint8_t* new_challenge, uint32_t check_output,
+                             uint32_t subgroup_mode, uint32_t ratio_check, const uint8_t* rlc_seed32, char* err, size_t errcap) {
+  int rc;
+  const size_t g1u = L.cs.g1u, g2u = L.cs.g2u;
+  // 1. hash chain: the response must continue the challenge it claims to be based on
+  uint8_t ch_hash[64];
+  blake2b_512(challenge, L.acc_size, ch_hash);
+  if (memcmp(ch_hash, response, 64) != 0) { set_err(err, errcap, "hash chain broken: response does not continue the challenge"); return SSO_E_VERIFY; }
+  // 2. decode + check the response vectors on the device, producing the new challenge image
+  uint8_t *d_resp, *d_new;
+  uint32_t* d_status;
+  if ((rc = c.alloc((void**)&d_resp, L.contrib_size))) return rc;
+  if ((rc = c.alloc((void**)&d_new, L.acc_size))) return rc;
+  if ((rc = c.alloc((void**)&d_status, STATUS_BYTES))) return rc;
+  CUDA_TRY(cudaMemsetAsync(d_status, 0, STATUS_BYTES, c.s[0]));
+  CUDA_TRY(cudaMemcpyAsync(d_resp, response, L.contrib_size, cudaMemcpyHostToDevice, c.s[0]));
+  CUDA_TRY(cudaStreamSynchronize(c.s[0]));
+  const uint64_t counts[5] = {L.g1n, L.on, L.on, L.on, 1};
+  const uint32_t groups[5] = {GROUP_G1, GROUP_G2, GROUP_G1, GROUP_G1, GROUP_G2};
+  const uint32_t subgroup = subgroup_mode == SSO_SUBGROUP_NO ? 0u : 1u;
+  uint32_t* d_aff[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  if ((rc = c.fork(0, 1))) return rc;
+  for (int v = 0; v < 5; v++) {
+    if (counts[v] == 0) continue;
+    int si = groups[v] == GROUP_G2 ? 1 : 0;
+    if (ratio_check && v < 4 && counts[v] >= 2)
+      if ((rc = c.alloc((void**)&d_aff[v], counts[v] * ops->aff_words[groups[v]] * 4, si))) return rc;
+    if ((rc = ops->reencode(c, si, groups[v], d_resp + L.off_c[v], 1, counts[v], d_new + L.off_u[v], 0, check_output, subgroup,
+                            d_aff[v], d_status, err, errcap))) return rc;
+  }
+  // 3. random-linear-combination pairs for the power-ratio checks
+  uint8_t* d_pairs[4] = {nullptr, nullptr, nullptr, nullptr};
+  for (int v = 0; v < 4; v++) {
+    if (!d_aff[v]) continue;
+    int si = groups[v] == GROUP_G2 ? 1 : 0;
+    size_t usz = groups[v] == GROUP_G1 ? g1u : g2u;
+    if ((rc = c.alloc((void**)&d_pairs[v], 2 * usz, si))) return rc;
+    if ((rc = ops->msm_pairs(c, si, groups[v], d_aff[v], d_aff[v] + ops->aff_words[groups[v]], counts[v] - 1, rlc_seed32, d_pairs[v],
+                             err, errcap))) return rc;
+  }
+  // 4. proof-of-knowledge seeds while the GPU works: g2_s = hash_to_g2(Blake2b(pers || digest || g1_s || g1_s_x))
+  const uint8_t* pk = response + L.off_c[5];
+  std::vector<uint8_t> seeds2(3 * 32);
+  for (uint32_t i = 0; i < 3; i++) {
+    Blake2b h(64);
+    uint8_t pers = (uint8_t)i, full[64];
+    h.update(&pers, 1);
+    h.update(ch_hash, 64);
+    h.update(pk + (size_t)2 * i * g1u, 2 * g1u);
+    h.final(full, 64);
+    memcpy(seeds2.data() + 32 * i, full, 32);
+  }
+  uint32_t* d_seeds2;
+  uint8_t* d_g2s;
+  if ((rc = c.alloc((void**)&d_seeds2, 96))) return rc;
+  if ((rc = c.alloc((void**)&d_g2s, 3 * g2u))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(d_seeds2, seeds2.data(), 96, cudaMemcpyHostToDevice, c.s[0]));
+  if ((rc = ops->hash_to_g2(c, 0, 3, d_seeds2, nullptr, d_g2s, nullptr, err, errcap))) return rc;
+  // the new challenge's hash slot chains the response
+  blake2b_512(response, L.contrib_size, new_challenge);
+  if ((rc = sync_all(c, err, errcap))) return rc;
+  if ((rc = check_status(c, d_status, "response", err, errcap))) return rc == SSO_E_INPUT ? SSO_E_VERIFY : rc;
+  CUDA_TRY(cudaMemcpy(new_challenge + 64, d_new + 64, L.acc_size - 64, cudaMemcpyDeviceToHost));
+  std::vector<uint8_t> g2s(3 * g2u);
+  CUDA_TRY(cudaMemcpy(g2s.data(), d_g2s, g2s.size(), cudaMemcpyDeviceToHost));
+  std::vector<uint8_t> pairs[4];
+  for (int v = 0; v < 4; v++) {
+    if (!d_pairs[v]) continue;
+    pairs[v].resize(2 * (groups[v] == GROUP_G1 ? g1u : g2u));
+    CUDA_TRY(cudaMemcpy(pairs[v].data(), d_pairs[v], pairs[v].size(), cudaMemcpyDeviceToHost));
+  }
+  // 5. collect the same_ratio checks
+  std::vector<RatioCheck> checks;
+  const uint8_t* pk_g2 = pk + 6 * g1u;                       // tau_g2, alpha_g2, beta_g2 (= g2_s_x)
+  static const char* pok_names[3] = {"proof of knowledge: tau", "proof of knowledge: alpha", "proof of knowledge: beta"};
+  for (int i = 0; i < 3; i++)
+    add_check(checks, pok_names[i], pk + (size_t)2 * i * g1u, pk + (size_t)(2 * i + 1) * g1u, g1u, g2s.data() + (size_t)i * g2u,
+              pk_g2 + (size_t)i * g2u, g2u);
+  const uint8_t* after = new_challenge;
+  if (chunk_index == 0 && L.on >= 2) {
+    // element 0 must still be the generator; element 1 / alpha / beta must have moved by the proven scalars
+    std::vector<uint8_t> gen(g1u + g2u);
+    uint8_t* d_gen;
+    if ((rc = c.alloc((void**)&d_gen, g1u + g2u))) return rc;
+    if ((rc = ops->fill_generator(c, 0, GROUP_G1, 1, d_gen, 0, err, errcap))) return rc;
+    if ((rc = ops->fill_generator(c, 0, GROUP_G2, 1, d_gen + g1u, 0, err, errcap))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(gen.data(), d_gen, gen.size(), cudaMemcpyDeviceToHost, c.s[0]));
+    CUDA_TRY(cudaStreamSynchronize(c.s[0]));
+    if (memcmp(after + L.off_u[0], gen.data(), g1u) != 0) { set_err(err, errcap, "tau_g1[0] is not the G1 generator"); return SSO_E_VERIFY; }
+    if (memcmp(after + L.off_u[1], gen.data() + g1u, g2u) != 0) { set_err(err, errcap, "tau_g2[0] is not the G2 generator"); return SSO_E_VERIFY; }
+    add_check(checks, "before/after: tau_g1[1] vs tau proof", challenge + L.off_u[0] + g1u, after + L.off_u[0] + g1u, g1u,
+              g2s.data(), pk_g2, g2u);
+    add_check(checks, "before/after: alpha_g1[0] vs alpha proof", challenge + L.off_u[2], after + L.off_u[2], g1u,
+              g2s.data() + g2u, pk_g2 + g2u, g2u);
+    add_check(checks, "before/after: beta_g1[0] vs beta proof", challenge + L.off_u[3], after + L.off_u[3], g1u,
+              g2s.data() + 2 * g2u, pk_g2 + 2 * g2u, g2u);
+    add_check(checks, "before/after: beta_g2 vs beta_g1[0]", challenge + L.off_u[3], after + L.off_u[3], g1u,
+              challenge + L.off_u[4], after + L.off_u[4], g2u);
+  }
+  if (ratio_check && d_pairs[1]) {
+    // consecutive powers inside the chunk share one ratio: compare the G1 combinations with the G2 one
+    const uint8_t* g2p = pairs[1].data();
+    if (chunk_index == 0) g2p = after + L.off_u[1];           // (tau_g2[0], tau_g2[1]) exactly, as upstream
+    if (d_pairs[0]) add_check(checks, "power ratio: tau_g1", pairs[0].data(), pairs[0].data() + g1u, g1u, g2p, g2p + g2u, g2u);
+    if (d_pairs[2]) add_check(checks, "power ratio: alpha_g1", pairs[2].data(), pairs[2].data() + g1u, g1u, g2p, g2p + g2u, g2u);
+    if (d_pairs[3]) add_check(checks, "power ratio: beta_g1", pairs[3].data(), pairs[3].data() + g1u, g1u, g2p, g2p + g2u, g2u);
+    if (chunk_index == 0)
+      add_check(checks, "power ratio: tau_g2", after + L.off_u[0], after + L.off_u[0] + g1u, g1u, pairs[1].data(), pairs[1].data() + g2u, g2u);
+  }
+  return run_checks(c, ops, checks, err, errcap);
+}
+
+}  // namespace sso

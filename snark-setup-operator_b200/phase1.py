@@ -208,3 +208,53 @@ def same_ratio(curve, checks, device=0):
     verdicts = (ctypes.c_uint32 * max(1, len(checks)))()
     call("sso_same_ratio", curve_id(curve), buf, len(checks), verdicts, device)
     return [bool(v) for v in verdicts[:len(checks)]]
+
+
+SUBGROUP_AUTO, SUBGROUP_DIRECT, SUBGROUP_BATCHED, SUBGROUP_NO = 0, 1, 2, 3
+
+
+def keygen(curve, seed32: bytes, digest64: bytes, device=0):
+    """Phase1::key_generation -> ((tau, alpha, beta), serialized public key)."""
+    s = curve_sizes(curve)
+    sc = ctypes.create_string_buffer(3 * s["fr"])
+    pk = ctypes.create_string_buffer(6 * s["g1_u"] + 3 * s["g2_u"])
+    call("sso_p1_keygen", curve_id(curve), seed32, digest64, sc, len(sc), pk, len(pk), device)
+    fr = s["fr"]
+    return tuple(int.from_bytes(sc.raw[i * fr:(i + 1) * fr], "little") for i in range(3)), pk.raw
+
+
+def contribute_seeded_buf(params: Phase1Parameters, challenge, response, seed32: bytes, check=CHECK_NONZERO, device=0):
+    """phase1_cli::contribute on host buffers with the RNG given by its 32-byte seed."""
+    ch_ptr, ch_len, k1 = _host_ptr(challenge)
+    rs_ptr, rs_len, k2 = _host_ptr(response)
+    call("sso_p1_contribute_seeded_buf", ctypes.byref(params.c_struct()), ch_ptr, ch_len, rs_ptr, rs_len, seed32, check, device)
+    del k1, k2
+    return response
+
+
+def contribute(challenge_filename, challenge_hash_filename, response_filename, response_hash_filename, check_input, batch_exp_mode,
+               parameters: Phase1Parameters, seed32: bytes, device=0):
+    """phase1_cli::contribute, argument for argument (reference src/bin/contribute.rs:811-823); rng -> its seed."""
+    call("sso_p1_contribute_file", ctypes.byref(parameters.c_struct()), challenge_filename.encode(), challenge_hash_filename.encode(),
+         response_filename.encode(), response_hash_filename.encode(), check_input, batch_exp_mode, seed32, device)
+
+
+def verify_chunk_buf(params: Phase1Parameters, challenge, response, new_challenge, check_input=CHECK_NO, check_output=CHECK_FULL,
+                     subgroup_check_mode=SUBGROUP_AUTO, ratio_check=True, rlc_seed32=None, device=0):
+    """Phase1::verification of one chunk on host buffers; raises SsoError(code -4) on a rejected contribution."""
+    ch_ptr, ch_len, k1 = _host_ptr(challenge)
+    rs_ptr, rs_len, k2 = _host_ptr(response)
+    nc_ptr, nc_len, k3 = _host_ptr(new_challenge)
+    call("sso_p1_verify_chunk_buf", ctypes.byref(params.c_struct()), ch_ptr, ch_len, rs_ptr, rs_len, nc_ptr, nc_len, check_input,
+         check_output, subgroup_check_mode, int(ratio_check), rlc_seed32, device)
+    del k1, k2, k3
+    return new_challenge
+
+
+def transform_pok_and_correctness(challenge_filename, challenge_hash_filename, check_input, response_filename, response_hash_filename,
+                                  check_output, new_challenge_filename, new_challenge_hash_filename, subgroup_check_mode, ratio_check,
+                                  parameters: Phase1Parameters, device=0):
+    """phase1_cli::transform_pok_and_correctness, argument for argument (reference src/bin/contribute.rs:968-986)."""
+    call("sso_p1_verify_chunk_file", ctypes.byref(parameters.c_struct()), challenge_filename.encode(), challenge_hash_filename.encode(),
+         check_input, response_filename.encode(), response_hash_filename.encode(), check_output, new_challenge_filename.encode(),
+         new_challenge_hash_filename.encode(), subgroup_check_mode, int(ratio_check), device)

@@ -19,6 +19,7 @@
 #include "../../snark-setup-operator_b200/csrc/kernels.cuh"
 #include "../../snark-setup-operator_b200/csrc/msm.cuh"
 #include "../../snark-setup-operator_b200/csrc/pairing.cuh"
+#include "../../snark-setup-operator_b200/csrc/keygen.cuh"
 
 using namespace sso;
 
@@ -210,4 +211,14 @@ extern "C" int emul_same_ratio(uint32_t curve, const uint8_t* checks, uint32_t n
     case 3: same_ratio_emul<Mnt6_753_G1, Mnt6_753_G2, PAIR_mnt6_753>(checks, n, verdicts); return 0;
   }
   return -1;
+}
+
+// key generation pieces
+extern "C" int emul_keygen_g1(uint32_t curve, const uint32_t* seed, uint32_t nscalars, uint32_t* scalars_out, uint8_t* g1_out) {
+  return dispatch_group(curve, 0, [&](auto g) { body_keygen_g1<decltype(g)>(seed, nscalars, scalars_out, g1_out); });
+}
+extern "C" int emul_hash_to_g2(uint32_t curve, uint32_t n, const uint32_t* seeds, const uint32_t* scalars, uint8_t* g2_s, uint8_t* g2_sx) {
+  return dispatch_group(curve, 1, [&](auto g) {
+    for (uint32_t t = 0; t < n; t++) body_hash_to_g2<decltype(g)>(t, n, seeds, scalars, g2_s, g2_sx);
+  });
 }

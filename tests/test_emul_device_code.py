@@ -221,3 +221,35 @@ def test_same_ratio_pairing(emul, name):
     if name == "bls12_377":
         for (a, b), (cc, d), want in cases[:2]:
             assert pairing.same_ratio(c, (a, b), (cc, d)) == want
+
+
+@pytest.mark.parametrize("name", ["bls12_377", "mnt4_753"])
+def test_key_generation_matches_oracle(emul, name):
+    """Device samplers (ChaCha20 stream, Fr::rand, G::rand with cofactor clearing, hash_to_g2) reproduce
+    the oracle's Phase1::key_generation byte for byte."""
+    import hashlib
+    from oracle import phase1
+    from oracle.chacha import ChaChaRng
+    c = get_curve(name)
+    seed = synth.SEED_CONTRIB
+    digest = phase1.blank_hash()
+    pub, key = phase1.key_generation(c, ChaChaRng(seed), digest)
+    Lr = (c.Fr.bits + 31) // 32
+    g1u, g2u = ser.point_size(c.g1, False), ser.point_size(c.g2, False)
+    scal = (ctypes.c_uint32 * (3 * Lr))()
+    g1_out = ctypes.create_string_buffer(6 * g1u)
+    assert emul.emul_keygen_g1(c.cid, (ctypes.c_uint32 * 8).from_buffer_copy(seed), 3, scal, g1_out) == 0
+    got = [sum(scal[i * Lr + w] << (32 * w) for w in range(Lr)) for i in range(3)]
+    assert got == [key.tau, key.alpha, key.beta]
+    want_pk = pub.to_bytes(c)
+    assert g1_out.raw == want_pk[:6 * g1u]
+    seeds = b""
+    for i in range(3):
+        h = hashlib.blake2b(digest_size=64)
+        h.update(bytes([i])); h.update(digest); h.update(g1_out.raw[2 * i * g1u:(2 * i + 2) * g1u])
+        seeds += h.digest()[:32]
+    g2_s = ctypes.create_string_buffer(3 * g2u)
+    g2_sx = ctypes.create_string_buffer(3 * g2u)
+    assert emul.emul_hash_to_g2(c.cid, 3, (ctypes.c_uint32 * 24).from_buffer_copy(seeds), scal, g2_s, g2_sx) == 0
+    assert g2_sx.raw == want_pk[6 * g1u:]
+    assert g2_s.raw[:g2u] == ser.point_to_bytes(c.g2, phase1.compute_g2_s(c, digest, pub.tau_g1[0], pub.tau_g1[1], 0), False)

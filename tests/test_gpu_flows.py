@@ -1,0 +1,120 @@
+"""The file-level ceremony calls on the GPU through the C ABI: key generation from the seeded RNG, the full
+phase1_cli::contribute (hash chain + public key), chunk verification with real pairings (accept / reject
+verdicts against the oracle), and the file entry points with the reference's argument order."""
+import os
+
+import pytest
+
+import snark_setup_operator_b200 as sso
+from oracle import phase1, serialize as ser, synth
+from oracle.chacha import ChaChaRng
+from oracle.curves import CURVE_NAMES, get_curve
+from oracle.params import Phase1Params
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.mark.parametrize("name", CURVE_NAMES)
+def test_keygen_matches_oracle(name):
+    c = get_curve(name)
+    digest = phase1.calculate_hash(b"some challenge")
+    pub, key = phase1.key_generation(c, ChaChaRng(synth.SEED_CONTRIB), digest)
+    scalars, pk = sso.keygen(name, synth.SEED_CONTRIB, digest)
+    assert scalars == (key.tau, key.alpha, key.beta)
+    assert pk == pub.to_bytes(c)
+
+
+def _contribution(name, k, cs=4, power=3):
+    o = Phase1Params.new_chunk(name, k, cs, power, cs)
+    p = sso.Phase1Parameters.new_chunk(name, k, cs, power, cs)
+    ch = synth.synthetic_challenge(o)
+    resp = bytearray(o.contribution_size)
+    sso.contribute_seeded_buf(p, ch, resp, synth.SEED_CONTRIB)
+    return o, p, ch, bytes(resp)
+
+
+def test_full_contribute_matches_oracle():
+    o, p, ch, resp = _contribution("bls12_377", 1)
+    want, ch_hash, resp_hash = phase1.contribute(o, ch, ChaChaRng(synth.SEED_CONTRIB))
+    assert resp == want
+
+
+@pytest.mark.parametrize("name,k", [("bls12_377", 0), ("bls12_377", 1), ("bls12_377", 3), ("bw6_761", 1), ("mnt4_753", 0),
+                                    ("mnt6_753", 1)])
+def test_verify_accepts_honest_contribution(name, k):
+    o, p, ch, resp = _contribution(name, k)
+    new_ch = bytearray(o.accumulator_size)
+    sso.verify_chunk_buf(p, ch, resp, new_ch, rlc_seed32=bytes(range(32)))
+    assert bytes(new_ch) == phase1.decompress_response(o, resp)
+    if name == "bls12_377" and k == 1:
+        assert phase1.verify_chunk(o, ch, resp, rlc_seed32=bytes(range(32))) == bytes(new_ch)
+
+
+def test_verify_rejects_bad_contributions():
+    o, p, ch, resp = _contribution("bls12_377", 0)
+    c = o.curve
+    new_ch = bytearray(o.accumulator_size)
+    oc = o.offsets(True)
+
+    def rejected(bad, match, **kw):
+        with pytest.raises(sso.SsoError) as e:
+            sso.verify_chunk_buf(p, ch, bytes(bad), new_ch, **kw)
+        assert e.value.code == -4 and match in e.value.message, e.value.message
+
+    bad = bytearray(resp); bad[0] ^= 1
+    rejected(bad, "hash chain")
+    # a valid subgroup point with the wrong scalar in the middle of tau_g1: only the RLC power check sees it
+    bad = bytearray(resp); bad[oc[0] + 2 * 48: oc[0] + 3 * 48] = ser.point_to_bytes(c.g1, c.g1.mul(c.g1.gen, 12345), True)
+    rejected(bad, "power ratio: tau_g1")
+    with pytest.raises(phase1.VerificationError, match="power ratio: tau_g1"):
+        phase1.verify_chunk(o, ch, bytes(bad))
+    sso.verify_chunk_buf(p, ch, bytes(bad), new_ch, ratio_check=False)      # --skip-ratio-check lets it through
+    # alpha_g1[0] replaced: the before/after check against the alpha proof fails
+    bad = bytearray(resp); bad[oc[2]: oc[2] + 48] = ser.point_to_bytes(c.g1, c.g1.mul(c.g1.gen, 777), True)
+    rejected(bad, "alpha")
+    # a point outside the prime-order subgroup
+    from oracle.curves import _some_point
+    bad = bytearray(resp); bad[oc[3] + 48: oc[3] + 96] = ser.point_to_bytes(c.g1, _some_point(c.g1, 11), True)
+    rejected(bad, "subgroup")
+    # tampered public key: proof of knowledge fails
+    bad = bytearray(resp); pk0 = oc[5]
+    bad[pk0 + 96: pk0 + 192] = ser.point_to_bytes(c.g1, c.g1.mul(c.g1.gen, 99), False)
+    rejected(bad, "proof of knowledge: tau")
+    # point at infinity in the output
+    bad = bytearray(resp); bad[oc[0] + 48: oc[0] + 96] = ser.point_to_bytes(c.g1, None, True)
+    rejected(bad, "infinity")
+    # tau_g1[0] moved away from the generator
+    bad = bytearray(resp); bad[oc[0]: oc[0] + 48] = ser.point_to_bytes(c.g1, c.g1.mul(c.g1.gen, 2), True)
+    rejected(bad, "generator", ratio_check=False)
+
+
+def test_file_entry_points(tmp_path):
+    """contribute -> transform_pok_and_correctness through files, reference argument order; hash files hold the
+    raw 64 bytes (reference src/utils.rs:264-276); existing outputs are an error (create_new)."""
+    name = "bls12_377"
+    o = Phase1Params.new_chunk(name, 2, 4, 3, 4)
+    p = sso.Phase1Parameters.new_chunk(name, 2, 4, 3, 4)
+    f = {k: str(tmp_path / k) for k in ("challenge", "challenge.hash", "response", "response.hash", "new_challenge",
+                                         "new_challenge.hash", "challenge.verified.hash", "response.verified.hash")}
+    ch = synth.synthetic_challenge(o)
+    open(f["challenge"], "wb").write(ch)
+    sso.contribute(f["challenge"], f["challenge.hash"], f["response"], f["response.hash"], sso.CHECK_NONZERO, 0, p, synth.SEED_CONTRIB)
+    resp = open(f["response"], "rb").read()
+    want, ch_hash, resp_hash = phase1.contribute(o, ch, ChaChaRng(synth.SEED_CONTRIB))
+    assert resp == want
+    assert open(f["challenge.hash"], "rb").read() == ch_hash and open(f["response.hash"], "rb").read() == resp_hash
+    with pytest.raises(sso.SsoError) as e:                      # outputs already exist
+        sso.contribute(f["challenge"], f["challenge.hash"], f["response"], f["response.hash"], sso.CHECK_NONZERO, 0, p, synth.SEED_CONTRIB)
+    assert e.value.code == -5
+    sso.transform_pok_and_correctness(f["challenge"], f["challenge.verified.hash"], sso.CHECK_NO, f["response"], f["response.verified.hash"],
+                                      sso.CHECK_FULL, f["new_challenge"], f["new_challenge.hash"], 0, True, p)
+    new_ch = open(f["new_challenge"], "rb").read()
+    assert new_ch == phase1.decompress_response(o, resp)
+    assert open(f["new_challenge.hash"], "rb").read() == phase1.calculate_hash(new_ch)
+    assert open(f["response.verified.hash"], "rb").read() == resp_hash
+    # wrong-size input file: the reference asserts file lengths
+    open(f["challenge"], "ab").write(b"\0")
+    with pytest.raises(sso.SsoError) as e:
+        sso.contribute(f["challenge"], str(tmp_path / "x1"), str(tmp_path / "x2"), str(tmp_path / "x3"), 0, 0, p, synth.SEED_CONTRIB)
+    assert e.value.code == -1 and "size" in e.value.message
