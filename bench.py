@@ -37,22 +37,28 @@ def macs_per_fq_mul(limbs: int) -> int:
     return 2 * limbs * limbs + limbs            # CIOS on L 32-bit limbs
 
 
+GLV_KBITS = {"bls12_377": 129, "bw6_761": 191}      # csrc/constants.cuh GLV_*::KBITS (half-size scalars)
+
+
 def declared_fq_muls_per_point(curve: str, group: int) -> float:
-    """Closed-form field-multiplication count of k_batch_exp per point:
-    signed 4-bit windows, NW = ceil((bits+2)/4); table = 4 dbl + 3 madd; main loop = 4 (NW-1) dbl +
-    NW * 15/16 full additions; plus 4 multiplications to read the point into Montgomery form.
-    Fq2: mul = 3, sqr = 2 base multiplications; Fq3: mul = sqr = 6."""
+    """Closed-form field-multiplication count of k_batch_exp per point (kernels):
+    signed 4-bit windows; table 1P..8P = 4 dbl + 3 madd; 4 multiplications to read the point into Montgomery form.
+      plain ladder (MNT4/6):  NW = ceil((bits+2)/4) windows, 4 (NW-1) dbl + NW * 15/16 additions
+      GLV (BLS12-377, BW6):   NW = ceil((KBITS+2)/4) windows on the two half-size scalars,
+                              4 (NW-1) dbl + 2 NW * 15/16 additions + NW * 15/16 multiplications by beta
+    Fq2: mul = 3, sqr = 2 base multiplications; Fq3: mul = sqr = 6; squarings count as multiplications."""
     _, bits = CURVE_BITS[curve]
-    nw = (bits + 2 + 3) // 4
     deg = G2_DEG[curve] if group == 1 else 1
     M, S = {1: (1, 1), 2: (3, 2), 3: (6, 6)}[deg]
-    if A_ZERO[curve]:
-        dbl = 2 * M + 5 * S
-    else:
-        dbl = 1 * M + 8 * S                      # dbl-2007-bl: 1M + 8S (+ cheap mul_a)
+    dbl = 2 * M + 5 * S if A_ZERO[curve] else 1 * M + 8 * S
     madd = 7 * M + 4 * S
     add = 11 * M + 5 * S
-    return 4 * dbl + 3 * madd + 4 * (nw - 1) * dbl + nw * (15.0 / 16.0) * add + 4 * deg
+    table = 4 * dbl + 3 * madd + 4 * deg
+    if curve in GLV_KBITS:
+        nw = (GLV_KBITS[curve] + 2 + 3) // 4
+        return table + 4 * (nw - 1) * dbl + 2 * nw * (15.0 / 16.0) * add + nw * (15.0 / 16.0) * deg
+    nw = (bits + 2 + 3) // 4
+    return table + 4 * (nw - 1) * dbl + nw * (15.0 / 16.0) * add
 
 
 class ClockSampler(threading.Thread):
@@ -230,16 +236,21 @@ def main():
     step_dev = lambda: sso.contribute_dev(p, d_ch, d_resp, *mine, check=sso.CHECK_NONZERO, device=dev)
     step_e2e = lambda: sso.contribute_buf(p, h_ch, h_resp, *mine, pubkey=pubkey, check=sso.CHECK_NONZERO, device=dev)
 
-    # ---- device-resident timing (value) with per-kernel events for the roofline
+    # ---- device-resident timing (value)
     run_steps(step_dev, args.warmup, False)
     sso.profile_reset()
-    sso.profile_enable(not os.environ.get("SSO_BENCH_NOPROF"))
     sampler = ClockSampler(local_rank)
     if not os.environ.get("SSO_BENCH_NOSAMPLER"):
         sampler.start()
     barrier()
     ms_total = run_steps(step_dev, args.steps, True)
     barrier()
+    launches_total = sum(v["launches"] for v in sso.profile_read().values())
+    # ---- roofline pass: the same steps with every kernel timed by CUDA events on its launching stream and
+    # the two streams of a call serialised, so that each kernel's time is its time alone on the GPU
+    sso.profile_reset()
+    sso.profile_enable(2)
+    run_steps(step_dev, args.steps, True)
     sso.profile_enable(False)
     prof = sso.profile_read()
     # ---- end-to-end timing through the host-buffer entry point
@@ -250,6 +261,22 @@ def main():
     sampler.stop_flag = True
     if sampler.is_alive():
         sampler.join(timeout=2)
+    # ---- chunk verification (BASELINE metric, second half: "chunk verify s"): transform_pok_and_correctness on host
+    # buffers — hash chain, 3 proofs of knowledge, decompression + subgroup checks, RLC power-ratio MSMs, pairings
+    verify = None
+    if rank == 0 and not os.environ.get("SSO_BENCH_NOVERIFY"):
+        seed = bytes(range(32))
+        sso.contribute_seeded_buf(p, h_ch, h_resp, seed, check=sso.CHECK_NO, device=dev)
+        h_new = torch.empty(acc, dtype=torch.uint8).pin_memory()
+        vt = []
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            sso.verify_chunk_buf(p, h_ch, h_resp, h_new, ratio_check=True, device=dev)
+            vt.append(time.perf_counter() - t0)
+        verify = {"s_per_chunk": min(vt[1:]), "runs_s": [round(x, 4) for x in vt],
+                  "what": "sso_p1_verify_chunk_buf: hash chain, PoK pairings, decompress + direct subgroup checks of %d points, "
+                          "RLC power-ratio MSMs, same_ratio pairings; host buffers" % npts}
 
     t = torch.tensor([ms_total, ms_e2e_total], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -277,7 +304,7 @@ def main():
         k = prof[kind]
         kernels.append({"kernel": "k_" + kind, "launches": k["launches"], "ms_total": round(k["ms"], 3), "points": k["elems"]})
     dom = max((k for k in kernels if "frac" in k), key=lambda k: k["ms_total"], default={"kernel": None, "achieved_tmacs": None, "frac": None})
-    launches = sum(v["launches"] for v in prof.values()) // max(1, args.steps)
+    launches = launches_total // max(1, args.steps)
     line = {
         "metric": "phase1_contribute_points_per_s", "value": world * npts / (ms_step * 1e-3), "unit": "points/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -293,6 +320,7 @@ def main():
                      "macs_per_fq_mul": mac, "kernels": kernels},
         "clocks": sampler.summary(),
         "points_per_step": npts,
+        "verify": verify,
     }
     if not args.no_cpu_baseline:
         cb, _ = cpu_reference_run(args.curve, args.power, args.chunk_log, 1, 0, 12.0)

@@ -151,7 +151,8 @@ int32_t sso_p1_new_challenge_dev(const sso_p1_params_t* p, void* d_challenge, in
 
 /* Kernel accounting.  Launch counts are always kept; with profiling enabled every kernel launch is
  * bracketed by CUDA events on its own stream.  sso_profile_read fills (launches, nanoseconds, elements)
- * triples per kernel kind, in the order of SSO_PK_*, and returns the number of kinds. */
+ * triples per kernel kind, in the order of SSO_PK_*, and returns the number of kinds.  sso_profile_enable(2)
+ * additionally runs every call on a single stream, so that a kernel's event time is its time alone on the GPU. */
 enum { SSO_PK_TAU_TABLES = 0, SSO_PK_BATCH_EXP_G1, SSO_PK_BATCH_EXP_G2, SSO_PK_NORMALIZE_G1, SSO_PK_NORMALIZE_G2,
        SSO_PK_REENCODE_G1, SSO_PK_REENCODE_G2, SSO_PK_FILL, SSO_PK_MSM, SSO_PK_OTHER, SSO_PK_COUNT };
 int32_t sso_profile_enable(int32_t on);
@@ -193,6 +194,24 @@ int32_t sso_p1_verify_chunk_file(const sso_p1_params_t* p, const char* challenge
                                  const char* response_fn, const char* response_hash_fn, uint32_t check_output,
                                  const char* new_challenge_fn, const char* new_challenge_hash_fn, uint32_t subgroup_check_mode,
                                  uint32_t ratio_check, int device, char* err, size_t errcap);
+
+/* Sum of n uncompressed points (host buffers) -> one uncompressed point.  Used to combine the per-GPU partial
+ * results of a sharded power_pairs / merge_pairs after the NCCL all-gather. */
+int32_t sso_points_sum(uint32_t curve, uint32_t group, const uint8_t* points, uint64_t n, uint8_t* out, size_t out_len, int device,
+                       char* err, size_t errcap);
+
+/* phase2_cli::contribute core (reference src/bin/contribute.rs:827-838): multiply every
+ * point of a G1 query vector (h_query or l_query) by delta^-1.  Host buffers of n serialized G1 points. */
+int32_t sso_p2_scale_queries_buf(uint32_t curve, const uint8_t* in, size_t in_len, uint8_t* out, size_t out_len, uint64_t n,
+                                 const uint8_t* delta_inv, uint32_t in_compressed, uint32_t out_compressed, uint32_t check_input,
+                                 int device, char* err, size_t errcap);
+
+/* phase2_cli::verify core (reference src/bin/contribute.rs:990-1007; row a11): accepts iff
+ * same_ratio(merge_pairs(query_before, query_after), (delta_g2_after, delta_g2_before)); SSO_E_VERIFY otherwise. */
+int32_t sso_p2_verify_queries_buf(uint32_t curve, const uint8_t* before, size_t before_len, const uint8_t* after, size_t after_len,
+                                  uint64_t n, uint32_t before_compressed, uint32_t after_compressed, const uint8_t* delta_g2_before,
+                                  const uint8_t* delta_g2_after, uint32_t check, uint32_t subgroup_check, const uint8_t* rlc_seed32,
+                                  int device, char* err, size_t errcap);
 
 /* setup_utils::calculate_hash (reference src/utils.rs:618-623): Blake2b-512, unkeyed. Host only. */
 int32_t sso_blake2b_512(const uint8_t* data, size_t len, uint8_t out[64]);

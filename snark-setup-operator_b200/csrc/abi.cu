@@ -429,7 +429,7 @@ int32_t sso_p1_new_challenge_dev(const sso_p1_params_t* p, void* d_challenge, in
 }
 
 int32_t sso_profile_enable(int32_t on) {
-  g_prof_enabled.store(on ? 1 : 0);
+  g_prof_enabled.store(on == 2 ? 2 : (on ? 1 : 0));
   return SSO_OK;
 }
 
@@ -551,6 +551,87 @@ int32_t sso_p1_verify_chunk_file(const sso_p1_params_t* p, const char* challenge
   if ((rc = write_new_file(new_challenge_fn, new_challenge.data(), new_challenge.size(), err, errcap))) return rc;
   blake2b_512(new_challenge.data(), new_challenge.size(), h);
   return write_new_file(new_challenge_hash_fn, h, 64, err, errcap);
+}
+
+// sum of n uncompressed points on host buffers (combining all-gathered per-GPU partial MSM results)
+int32_t sso_points_sum(uint32_t curve, uint32_t group, const uint8_t* points, uint64_t n, uint8_t* out, size_t out_len, int device,
+                       char* err, size_t errcap) {
+  const CurveOps* ops = ops_for(curve);
+  CurveSizes cs;
+  if (!ops || group > 1 || !curve_sizes(curve, cs)) { set_err(err, errcap, "unknown curve/group %u/%u", curve, group); return SSO_E_ARG; }
+  uint64_t usz = group == GROUP_G1 ? cs.g1u : cs.g2u;
+  if (out_len != usz || n == 0 || n > 65536) { set_err(err, errcap, "points_sum: bad sizes"); return SSO_E_ARG; }
+  Ctx c(err, errcap);
+  int rc = c.init(device);
+  if (rc) return rc;
+  uint8_t *d_in, *d_out;
+  uint32_t* d_status;
+  if ((rc = status_buffer(c, &d_status, err, errcap))) return rc;
+  if ((rc = c.alloc((void**)&d_in, n * usz))) return rc;
+  if ((rc = c.alloc((void**)&d_out, usz))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(d_in, points, n * usz, cudaMemcpyHostToDevice, c.s[0]));
+  if ((rc = ops->points_sum(c, 0, group, d_in, (uint32_t)n, d_out, d_status, err, errcap))) return rc;
+  if ((rc = sync_all(c, err, errcap))) return rc;
+  if ((rc = check_status(c, d_status, "point", err, errcap))) return rc;
+  CUDA_TRY(cudaMemcpy(out, d_out, usz, cudaMemcpyDeviceToHost));
+  return SSO_OK;
+}
+
+// phase-2 batch_mul of a G1 query vector (h_query / l_query) by delta^-1 on host buffers (a10 core)
+int32_t sso_p2_scale_queries_buf(uint32_t curve, const uint8_t* in, size_t in_len, uint8_t* out, size_t out_len, uint64_t n,
+                                 const uint8_t* delta_inv, uint32_t in_compressed, uint32_t out_compressed, uint32_t check_input,
+                                 int device, char* err, size_t errcap) {
+  CurveSizes cs;
+  if (!curve_sizes(curve, cs) || !in || !out || !delta_inv) { set_err(err, errcap, "unknown curve %u or null argument", curve); return SSO_E_ARG; }
+  size_t isz = in_compressed ? cs.g1c : cs.g1u, osz = out_compressed ? cs.g1c : cs.g1u;
+  if (in_len != n * isz || out_len != n * osz) { set_err(err, errcap, "query buffers have the wrong size for %llu points", (unsigned long long)n); return SSO_E_ARG; }
+  if (n == 0) return SSO_OK;
+  Ctx c(err, errcap);
+  int rc = c.init(device);
+  if (rc) return rc;
+  uint8_t *d_in, *d_out;
+  if ((rc = c.alloc((void**)&d_in, in_len))) return rc;
+  if ((rc = c.alloc((void**)&d_out, out_len))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(d_in, in, in_len, cudaMemcpyHostToDevice, c.s[0]));
+  CUDA_TRY(cudaStreamSynchronize(c.s[0]));
+  if ((rc = sso_batch_mul_dev(curve, GROUP_G1, d_in, in_compressed, n, delta_inv, d_out, out_compressed, check_input, device, err, errcap))) return rc;
+  CUDA_TRY(cudaMemcpy(out, d_out, out_len, cudaMemcpyDeviceToHost));
+  return SSO_OK;
+}
+
+// phase-2 query check (a11 core): same_ratio(merge_pairs(before, after), (delta_g2_after, delta_g2_before))
+int32_t sso_p2_verify_queries_buf(uint32_t curve, const uint8_t* before, size_t before_len, const uint8_t* after, size_t after_len,
+                                  uint64_t n, uint32_t before_compressed, uint32_t after_compressed, const uint8_t* delta_g2_before,
+                                  const uint8_t* delta_g2_after, uint32_t check, uint32_t subgroup_check, const uint8_t* rlc_seed32,
+                                  int device, char* err, size_t errcap) {
+  const CurveOps* ops = ops_for(curve);
+  CurveSizes cs;
+  if (!ops || !curve_sizes(curve, cs) || !before || !after || !delta_g2_before || !delta_g2_after) { set_err(err, errcap, "unknown curve %u or null argument", curve); return SSO_E_ARG; }
+  size_t bsz = before_compressed ? cs.g1c : cs.g1u, asz = after_compressed ? cs.g1c : cs.g1u;
+  if (before_len != n * bsz || after_len != n * asz || n == 0) { set_err(err, errcap, "query buffers have the wrong size for %llu points", (unsigned long long)n); return SSO_E_ARG; }
+  Ctx c(err, errcap);
+  int rc = c.init(device);
+  if (rc) return rc;
+  uint8_t *d_b, *d_a, *d_pair;
+  uint32_t *d_status, *d_aff_b, *d_aff_a;
+  if ((rc = status_buffer(c, &d_status, err, errcap))) return rc;
+  if ((rc = c.alloc((void**)&d_b, before_len))) return rc;
+  if ((rc = c.alloc((void**)&d_a, after_len))) return rc;
+  if ((rc = c.alloc((void**)&d_aff_b, n * ops->aff_words[0] * 4))) return rc;
+  if ((rc = c.alloc((void**)&d_aff_a, n * ops->aff_words[0] * 4))) return rc;
+  if ((rc = c.alloc((void**)&d_pair, 2 * cs.g1u))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(d_b, before, before_len, cudaMemcpyHostToDevice, c.s[0]));
+  CUDA_TRY(cudaMemcpyAsync(d_a, after, after_len, cudaMemcpyHostToDevice, c.s[0]));
+  if ((rc = ops->reencode(c, 0, GROUP_G1, d_b, before_compressed, n, nullptr, 0, SSO_CHECK_NO, 0, d_aff_b, d_status, err, errcap))) return rc;
+  if ((rc = ops->reencode(c, 0, GROUP_G1, d_a, after_compressed, n, nullptr, 0, check, subgroup_check, d_aff_a, d_status, err, errcap))) return rc;
+  if ((rc = ops->msm_pairs(c, 0, GROUP_G1, d_aff_b, d_aff_a, n, rlc_seed32, d_pair, err, errcap))) return rc;
+  if ((rc = sync_all(c, err, errcap))) return rc;
+  if ((rc = check_status(c, d_status, "query", err, errcap))) return rc == SSO_E_INPUT ? SSO_E_VERIFY : rc;
+  std::vector<uint8_t> pair(2 * cs.g1u);
+  CUDA_TRY(cudaMemcpy(pair.data(), d_pair, pair.size(), cudaMemcpyDeviceToHost));
+  std::vector<RatioCheck> checks;
+  add_check(checks, "phase-2 query vs delta_g2", pair.data(), pair.data() + cs.g1u, cs.g1u, delta_g2_after, delta_g2_before, cs.g2u);
+  return run_checks(c, ops, checks, err, errcap);
 }
 
 int32_t sso_imad_peak(int device, int variant, double* macs_per_s, char* err, size_t errcap) {

@@ -38,6 +38,8 @@ struct CurveOps {
   int (*hash_to_g2)(Ctx& c, int si, uint32_t n, const uint32_t* d_seeds, const uint32_t* d_scalars, uint8_t* d_g2_s, uint8_t* d_g2_sx,
                     char* err, size_t errcap);
   uint32_t fr_words;
+  // sum of n uncompressed points -> one uncompressed point (combining per-GPU partial MSM results)
+  int (*points_sum)(Ctx& c, int si, uint32_t group, const uint8_t* d_points, uint32_t n, uint8_t* d_out, uint32_t* d_status, char* err, size_t errcap);
   // phase1_cli::new_challenge: n copies of the group generator, uncompressed or compressed
   int (*fill_generator)(Ctx& c, int si, uint32_t group, uint64_t n, uint8_t* d_out, uint32_t out_compressed, char* err, size_t errcap);
   uint32_t fr_bytes;
@@ -204,6 +206,29 @@ __global__ void k_hash_to_g2(uint32_t n, const uint32_t* seeds, const uint32_t* 
   if (threadIdx.x == 0) body_hash_to_g2<G2>(blockIdx.x, n, seeds, scalars, g2_s, g2_sx);
 }
 
+template <class G>
+__global__ void k_points_sum(const uint8_t* pts, uint32_t n, uint8_t* out, uint32_t* status) {
+  using C = SW<G>;
+  using F = typename G::F;
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  typename C::Jac acc = C::identity();
+  for (uint32_t i = 0; i < n; i++) {
+    typename C::Affine p;
+    uint32_t st = C::read_uncompressed(pts + (size_t)i * C::SIZE_U, p);
+    if (st != C::DESER_OK || !C::on_curve(p)) { report(status, st ? st : (uint32_t)ST_NOT_ON_CURVE, i); return; }
+    acc = C::madd(acc, p);
+  }
+  C::write_uncompressed(out, jac_to_affine<G>(acc));
+}
+template <class G>
+inline int run_points_sum(Ctx& c, int si, const uint8_t* d_points, uint32_t n, uint8_t* d_out, uint32_t* d_status, char* err, size_t errcap) {
+  c.begin(PK_OTHER, si, n);
+  k_points_sum<G><<<1, 32, 0, c.s[si]>>>(d_points, n, d_out, d_status);
+  c.end(si);
+  CUDA_TRY(cudaGetLastError());
+  return SSO_OK;
+}
+
 inline uint32_t msm_window_bits(uint64_t n) {
   uint32_t lg = 0;
   while ((2ull << lg) <= n) lg++;
@@ -321,6 +346,12 @@ template <class G1, class G2, class PP> struct CurveImpl {
     CUDA_TRY(cudaGetLastError());
     return SSO_OK;
   }
+  static int points_sum(Ctx& c, int si, uint32_t group, const uint8_t* d_points, uint32_t n, uint8_t* d_out, uint32_t* d_status, char* err, size_t errcap) {
+    if (group == GROUP_G1) return run_points_sum<G1>(c, si, d_points, n, d_out, d_status, err, errcap);
+    if (group == GROUP_G2) return run_points_sum<G2>(c, si, d_points, n, d_out, d_status, err, errcap);
+    set_err(err, errcap, "unknown group %u", group);
+    return SSO_E_ARG;
+  }
   static int fill_generator(Ctx& c, int si, uint32_t group, uint64_t n, uint8_t* d_out, uint32_t out_compressed, char* err, size_t errcap) {
     if (group == GROUP_G1) return run_fill_generator<G1>(c, si, n, d_out, out_compressed, err, errcap);
     if (group == GROUP_G2) return run_fill_generator<G2>(c, si, n, d_out, out_compressed, err, errcap);
@@ -328,7 +359,7 @@ template <class G1, class G2, class PP> struct CurveImpl {
     return SSO_E_ARG;
   }
   static const CurveOps* ops() {
-    static const CurveOps o = {&tau_tables, &batch_exp, &reencode, &msm_pairs, &same_ratio, (uint32_t)Pairing<G1, G2, PP>::CHECK_BYTES, &keygen_g1, &hash_to_g2, (uint32_t)G1::Fr::L, &fill_generator, (uint32_t)G1::Fr::NBYTES, {2u * G1::F::WORDS, 2u * G2::F::WORDS}};
+    static const CurveOps o = {&tau_tables, &batch_exp, &reencode, &msm_pairs, &same_ratio, (uint32_t)Pairing<G1, G2, PP>::CHECK_BYTES, &keygen_g1, &hash_to_g2, (uint32_t)G1::Fr::L, &points_sum, &fill_generator, (uint32_t)G1::Fr::NBYTES, {2u * G1::F::WORDS, 2u * G2::F::WORDS}};
     return &o;
   }
 };

@@ -102,6 +102,7 @@ extern std::atomic<int> g_prof_enabled;
 // RAII: device selection + streams + stream-ordered scratch; one per ABI call (re-entrant)
 struct Ctx {
   int dev = -1, prev = -1;
+  bool aliased = false;
   cudaStream_t s[2] = {nullptr, nullptr};
   std::vector<void*> allocs;
   std::vector<std::vector<uint32_t>> staging;     // host copies that must outlive async H2D
@@ -146,7 +147,11 @@ struct Ctx {
       }
       pool_configured.fetch_or(1ull << device);
     }
-    for (int i = 0; i < nstreams; i++) CUDA_TRY(cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking));
+    // profiling mode 2 serialises the call on ONE stream so that per-kernel event times are not inflated by
+    // kernels of the other stream sharing the SMs (used for the roofline pass of bench.py)
+    aliased = nstreams > 1 && g_prof_enabled.load(std::memory_order_relaxed) == 2;
+    for (int i = 0; i < (aliased ? 1 : nstreams); i++) CUDA_TRY(cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking));
+    if (aliased) s[1] = s[0];
     mark("init: device + streams");
     return SSO_OK;
   }
@@ -195,6 +200,7 @@ struct Ctx {
       resolve_timings();
       mark("dtor: streams drained");
       for (void* p : allocs) cudaFreeAsync(p, s[0]);
+      if (aliased) s[1] = nullptr;
       for (auto& st : s) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
       if (prev >= 0) cudaSetDevice(prev);
       mark("dtor: freed + destroyed");

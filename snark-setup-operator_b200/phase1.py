@@ -157,8 +157,9 @@ PROFILE_KINDS = ("tau_tables", "batch_exp_g1", "batch_exp_g2", "normalize_g1", "
                  "fill", "msm", "other")
 
 
-def profile_enable(on: bool = True):
-    _lib.lib().sso_profile_enable(1 if on else 0)
+def profile_enable(on=True):
+    """True/1: time every kernel with events; 2: also serialise each call on one stream (isolated kernel times)."""
+    _lib.lib().sso_profile_enable(int(on))
 
 
 def profile_reset():

@@ -118,3 +118,73 @@ def test_file_entry_points(tmp_path):
     with pytest.raises(sso.SsoError) as e:
         sso.contribute(f["challenge"], str(tmp_path / "x1"), str(tmp_path / "x2"), str(tmp_path / "x3"), 0, 0, p, synth.SEED_CONTRIB)
     assert e.value.code == -1 and "size" in e.value.message
+
+
+@pytest.mark.parametrize("name", ["mnt4_753", "mnt6_753", "bls12_377"])
+def test_phase2_delta_update_and_check(name):
+    """Config 4: H / L query scaling by delta^-1 is bit-exact with the oracle and passes the same-ratio check
+    against (delta_g2_after, delta_g2_before); a tampered element is rejected."""
+    import random
+    from oracle import phase2 as o2
+    from snark_setup_operator_b200 import phase2 as p2
+    c = get_curve(name)
+    rnd = random.Random(4)
+    n = 7
+    pts = [c.g1.mul(c.g1.gen, rnd.randrange(1, c.Fr.p)) for _ in range(n)]
+    before = ser.points_to_bytes(c.g1, pts, False)
+    delta = synth.scalars_from_seed(c, synth.SEED_CONTRIB, 4)[3]
+    dinv = pow(delta, -1, c.Fr.p)
+    after = p2.scale_queries(name, before, n, dinv)
+    assert after == o2.scale_queries(c, before, delta, False, False)
+    d2_before = c.g2.mul(c.g2.gen, 31337)
+    d2_after = c.g2.mul(d2_before, delta)
+    db, da = ser.point_to_bytes(c.g2, d2_before, False), ser.point_to_bytes(c.g2, d2_after, False)
+    p2.verify_queries(name, before, after, n, db, da, rlc_seed32=bytes(32))
+    bad = bytearray(after); sz = len(after) // n
+    bad[2 * sz:3 * sz] = ser.point_to_bytes(c.g1, c.g1.mul(c.g1.gen, 5), False)
+    with pytest.raises(sso.SsoError) as e:
+        p2.verify_queries(name, before, bytes(bad), n, db, da)
+    assert e.value.code == -4
+    # points_sum: combining partial results
+    tot = p2.points_sum(name, 0, before, n)
+    assert tot == ser.point_to_bytes(c.g1, c.g1.sum(pts), False)
+
+
+def test_combine_and_transform_ratios(tmp_path):
+    """A whole (tiny) ceremony round on the GPU: new_challenge per chunk, seeded contributions, combine, and the
+    full-accumulator ratio check (transform_ratios); a tampered element is rejected."""
+    import numpy as np
+    from snark_setup_operator_b200 import transcript
+    name, power, cs = "bls12_377", 3, 4
+    full = sso.Phase1Parameters.new_full(name, power, cs)
+    nchunks = sso.Phase1Parameters.new_chunk(name, 0, cs, power, cs).sizes()["num_chunks"]
+    files, cps = [], []
+    for k in range(nchunks):
+        p = sso.Phase1Parameters.new_chunk(name, k, cs, power, cs)
+        d_ch = torch.empty(p.accumulator_size, dtype=torch.uint8, device="cuda")
+        sso.new_challenge_dev(p, d_ch)
+        resp = bytearray(p.contribution_size)
+        sso.contribute_seeded_buf(p, d_ch.cpu().numpy(), resp, synth.SEED_CONTRIB)
+        fn = str(tmp_path / ("response_%d" % k))
+        open(fn, "wb").write(resp)
+        files.append(fn); cps.append(p)
+    combined = str(tmp_path / "combined")
+    transcript.combine(files, combined, cps, full)
+    assert os.path.getsize(combined) == full.accumulator_size
+    # the combined vectors are the powers of the contributor's tau on the generators
+    c = get_curve(name)
+    key = phase1.PrivateKey(*synth.scalars_from_seed(c, synth.SEED_CONTRIB))
+    o_full = Phase1Params.new_full(name, power, cs)
+    v = phase1.read_chunk(o_full, open(combined, "rb").read(), False)
+    r = c.Fr.p
+    assert all(c.g1.eq(P, c.g1.mul(c.g1.gen, pow(key.tau, i, r))) for i, P in enumerate(v.tau_g1))
+    assert all(c.g1.eq(P, c.g1.mul(c.g1.gen, key.beta * pow(key.tau, i, r) % r)) for i, P in enumerate(v.beta_g1))
+    assert transcript.transform_ratios(combined, sso.CHECK_FULL, full, rlc_seed32=bytes(range(32)), subgroup_check=True)
+    # tamper with tau_g1[5]
+    mm = np.memmap(combined, dtype=np.uint8, mode="r+")
+    off = 64 + 5 * 96
+    mm[off:off + 96] = np.frombuffer(ser.point_to_bytes(c.g1, c.g1.mul(c.g1.gen, 4242), False), dtype=np.uint8)
+    mm.flush(); del mm
+    with pytest.raises(sso.SsoError) as e:
+        transcript.transform_ratios(combined, sso.CHECK_NO, full)
+    assert e.value.code == -4 and "tau_g1" in e.value.message
