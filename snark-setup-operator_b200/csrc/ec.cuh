@@ -12,6 +12,10 @@
 #pragma once
 #include "ext.cuh"
 
+#ifndef SSO_POINT_BY_VALUE
+#define SSO_POINT_BY_VALUE 0
+#endif
+
 namespace sso {
 
 template <class Cfg> struct SW {
@@ -41,7 +45,20 @@ template <class Cfg> struct SW {
     return r;
   }
 
-  __device__ __noinline__ static Jac dbl(const Jac& p) {
+  // Point formulas: one out-of-line copy each.  For single-field-element coordinates of up to 12 limbs the
+  // arguments travel by value (registers); wider points go by reference.
+  static constexpr bool BY_VALUE = SSO_POINT_BY_VALUE && F::WORDS <= 12;
+  __device__ __noinline__ static Jac dbl_val(Jac p) { return dbl_body(p); }
+  __device__ __noinline__ static Jac dbl_ref(const Jac& p) { return dbl_body(p); }
+  __device__ __forceinline__ static Jac dbl(const Jac& p) { if constexpr (BY_VALUE) return dbl_val(p); else return dbl_ref(p); }
+  __device__ __noinline__ static Jac madd_val(Jac p, Affine q) { return madd_body(p, q); }
+  __device__ __noinline__ static Jac madd_ref(const Jac& p, const Affine& q) { return madd_body(p, q); }
+  __device__ __forceinline__ static Jac madd(const Jac& p, const Affine& q) { if constexpr (BY_VALUE) return madd_val(p, q); else return madd_ref(p, q); }
+  __device__ __noinline__ static Jac add_val(Jac p, Jac q) { return add_body(p, q); }
+  __device__ __noinline__ static Jac add_ref(const Jac& p, const Jac& q) { return add_body(p, q); }
+  __device__ __forceinline__ static Jac add(const Jac& p, const Jac& q) { if constexpr (BY_VALUE) return add_val(p, q); else return add_ref(p, q); }
+
+  __device__ __forceinline__ static Jac dbl_body(const Jac& p) {
     Jac r;
     if (Cfg::A_IS_ZERO) {
       FT A = F::sqr(p.X);
@@ -72,7 +89,7 @@ template <class Cfg> struct SW {
   }
 
   // p + q with q affine (q.inf handled)
-  __device__ __noinline__ static Jac madd(const Jac& p, const Affine& q) {
+  __device__ __forceinline__ static Jac madd_body(const Jac& p, const Affine& q) {
     if (q.inf) return p;
     if (is_identity(p)) return Jac{q.x, q.y, F::one()};
     FT Z1Z1 = F::sqr(p.Z);
@@ -96,7 +113,7 @@ template <class Cfg> struct SW {
     return r;
   }
 
-  __device__ __noinline__ static Jac add(const Jac& p, const Jac& q) {
+  __device__ __forceinline__ static Jac add_body(const Jac& p, const Jac& q) {
     if (is_identity(p)) return q;
     if (is_identity(q)) return p;
     FT Z1Z1 = F::sqr(p.Z);

@@ -36,7 +36,8 @@ template <class B_, class NR> struct Fp2 {
   template <int K> __device__ __forceinline__ static T mul_small(const T& a) {
     return T{B::template mul_small<K>(a.c0), B::template mul_small<K>(a.c1)};
   }
-  __device__ __noinline__ static T mul(const T& a, const T& b) {
+  // out of line, parameters and result by value (registers under the device ABI; see fp.cuh)
+  __device__ __noinline__ static T mul_val(T a, T b) {
     typename B::T v0 = B::mul(a.c0, b.c0);
     typename B::T v1 = B::mul(a.c1, b.c1);
     typename B::T s = B::mul(B::add(a.c0, a.c1), B::add(b.c0, b.c1));
@@ -45,7 +46,7 @@ template <class B_, class NR> struct Fp2 {
     r.c1 = B::sub(B::sub(s, v0), v1);
     return r;
   }
-  __device__ __noinline__ static T sqr(const T& a) {
+  __device__ __noinline__ static T sqr_val(T a) {
     // (a0 + a1)(a0 + nr a1) = a0^2 + nr a1^2 + (nr + 1) a0 a1
     typename B::T v = B::mul(a.c0, a.c1);
     typename B::T pr = B::mul(B::add(a.c0, a.c1), B::add(a.c0, NR::mul(a.c1)));
@@ -54,6 +55,8 @@ template <class B_, class NR> struct Fp2 {
     r.c1 = B::dbl(v);
     return r;
   }
+  __device__ __forceinline__ static T mul(const T& a, const T& b) { return mul_val(a, b); }
+  __device__ __forceinline__ static T sqr(const T& a) { return sqr_val(a); }
   __device__ __forceinline__ static T mul_base(const T& a, const typename B::T& k) { return T{B::mul(a.c0, k), B::mul(a.c1, k)}; }
   __device__ __noinline__ static T inv(const T& a) {
     typename B::T n = B::sub(B::sqr(a.c0), NR::mul(B::sqr(a.c1)));
