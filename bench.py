@@ -292,6 +292,16 @@ def main():
     mac = macs_per_fq_mul(limbs)
     peak = sso.imad_peak(0, dev)
     kernels = []
+    n_g1 = sz["g1_count"] + 2 * sz["other_count"]
+    n_g2 = sz["other_count"] + 1
+    fm1, fm2 = declared_fq_muls_per_point(args.curve, 0), declared_fq_muls_per_point(args.curve, 1)
+    k = prof["batch_exp_chunk"]
+    if k["launches"] and k["ms"] > 0:
+        macs = k["launches"] * (n_g1 * fm1 + n_g2 * fm2) * mac          # both groups run in the one launch
+        achieved = macs / (k["ms"] * 1e-3)
+        kernels.append({"kernel": "k_batch_exp_chunk", "launches": k["launches"], "ms_total": round(k["ms"], 3),
+                        "points": k["elems"], "fq_muls_per_point": {"g1": round(fm1, 1), "g2": round(fm2, 1)},
+                        "achieved_tmacs": achieved / 1e12, "frac": achieved / peak})
     for kind, grp in (("batch_exp_g1", 0), ("batch_exp_g2", 1)):
         k = prof[kind]
         if k["launches"] and k["ms"] > 0:
@@ -300,9 +310,10 @@ def main():
             kernels.append({"kernel": "k_" + kind, "launches": k["launches"], "ms_total": round(k["ms"], 3),
                             "points": k["elems"], "fq_muls_per_point": round(fm, 1), "achieved_tmacs": achieved / 1e12,
                             "frac": achieved / peak})
-    for kind in ("normalize_g1", "normalize_g2", "tau_tables"):
+    for kind in ("normalize_chunk", "normalize_g1", "normalize_g2", "tau_tables"):
         k = prof[kind]
-        kernels.append({"kernel": "k_" + kind, "launches": k["launches"], "ms_total": round(k["ms"], 3), "points": k["elems"]})
+        if k["launches"]:
+            kernels.append({"kernel": "k_" + kind, "launches": k["launches"], "ms_total": round(k["ms"], 3), "points": k["elems"]})
     dom = max((k for k in kernels if "frac" in k), key=lambda k: k["ms_total"], default={"kernel": None, "achieved_tmacs": None, "frac": None})
     launches = launches_total // max(1, args.steps)
     line = {

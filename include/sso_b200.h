@@ -154,7 +154,8 @@ int32_t sso_p1_new_challenge_dev(const sso_p1_params_t* p, void* d_challenge, in
  * triples per kernel kind, in the order of SSO_PK_*, and returns the number of kinds.  sso_profile_enable(2)
  * additionally runs every call on a single stream, so that a kernel's event time is its time alone on the GPU. */
 enum { SSO_PK_TAU_TABLES = 0, SSO_PK_BATCH_EXP_G1, SSO_PK_BATCH_EXP_G2, SSO_PK_NORMALIZE_G1, SSO_PK_NORMALIZE_G2,
-       SSO_PK_REENCODE_G1, SSO_PK_REENCODE_G2, SSO_PK_FILL, SSO_PK_MSM, SSO_PK_OTHER, SSO_PK_COUNT };
+       SSO_PK_REENCODE_G1, SSO_PK_REENCODE_G2, SSO_PK_FILL, SSO_PK_MSM, SSO_PK_OTHER, SSO_PK_BATCH_EXP_CHUNK,
+       SSO_PK_NORMALIZE_CHUNK, SSO_PK_COUNT };
 int32_t sso_profile_enable(int32_t on);
 int32_t sso_profile_reset(void);
 int32_t sso_profile_read(uint64_t* out, size_t cap);

@@ -126,8 +126,8 @@ inline VecBatch batch_of(std::initializer_list<VecSeg> segs) {
   return b;
 }
 
-// Phase1::computation on the five vectors of one chunk: ONE tau-table launch, ONE launch pair for the
-// three G1 vectors (stream 0) and ONE for tauG2 + betaG2 (stream 1).  Coefficient slots: 0 = 1, 1 = alpha, 2 = beta.
+// Phase1::computation on the five vectors of one chunk: ONE tau-table launch, ONE batch_exp launch and ONE
+// normalisation launch covering the three G1 vectors and tauG2 + betaG2.  Coefficient slots: 0 = 1, 1 = alpha, 2 = beta.
 int p1_contribute_streams(Ctx& c, const CurveOps* ops, const P1Layout& L, const uint8_t* d_ch, uint8_t* d_resp,
                           const uint8_t* tau, const uint8_t* alpha, const uint8_t* beta, uint32_t check, uint32_t* d_status,
                           char* err, size_t errcap) {
@@ -135,15 +135,13 @@ int p1_contribute_streams(Ctx& c, const CurveOps* ops, const P1Layout& L, const 
   const uint8_t* coeffs[TAU_COEFF_SLOTS] = {nullptr, alpha, beta};
   uint32_t* d_table;
   if ((rc = ops->tau_tables(c, 0, L.start, tau, coeffs, &d_table, err, errcap))) return rc;
-  if ((rc = c.fork(0, 1))) return rc;
   VecBatch g2 = batch_of({seg(d_ch + L.off_u[1], d_resp + L.off_c[1], L.on, 0, 0, 0),
                           seg(d_ch + L.off_u[4], d_resp + L.off_c[4], 1, 2, 1, 1)});
   VecBatch g1 = batch_of({seg(d_ch + L.off_u[0], d_resp + L.off_c[0], L.g1n, 0, 0, 0),
                           seg(d_ch + L.off_u[2], d_resp + L.off_c[2], L.on, 1, 1, 0),
                           seg(d_ch + L.off_u[3], d_resp + L.off_c[3], L.on, 2, 1, 0)});
-  // the G2 launch holds the longest-running threads: enqueue it first
-  if ((rc = ops->batch_exp(c, 1, GROUP_G2, g2, 0, d_table, 1, check, d_status, err, errcap))) return rc;
-  return ops->batch_exp(c, 0, GROUP_G1, g1, 0, d_table, 1, check, d_status, err, errcap);
+  // one launch for both groups: G2 blocks (longest-running) first, G1 blocks fill the tail
+  return ops->batch_exp_chunk(c, 0, g1, g2, 0, d_table, 1, check, d_status, err, errcap);
 }
 
 // one vector, one scalar rule

@@ -19,6 +19,9 @@ struct CurveOps {
   // K2-K4 on up to four vectors of one group in one launch pair
   int (*batch_exp)(Ctx& c, int si, uint32_t group, const VecBatch& batch, uint32_t in_compressed, const uint32_t* d_table,
                    uint32_t out_compressed, uint32_t check, uint32_t* d_status, char* err, size_t errcap);
+  // K2-K4 for the G1 and G2 vectors of a chunk in one launch pair (tail filling across the groups)
+  int (*batch_exp_chunk)(Ctx& c, int si, const VecBatch& b1, const VecBatch& b2, uint32_t in_compressed, const uint32_t* d_table,
+                         uint32_t out_compressed, uint32_t check, uint32_t* d_status, char* err, size_t errcap);
   // K3 (+K6) alone
   int (*reencode)(Ctx& c, int si, uint32_t group, const uint8_t* d_in, uint32_t in_compressed, uint64_t n, uint8_t* d_out,
                   uint32_t out_compressed, uint32_t check, uint32_t subgroup, uint32_t* d_aff, uint32_t* d_status, char* err,
@@ -52,8 +55,11 @@ __global__ void k_tau_tables(const uint32_t* tau_canon, const uint32_t* coeff_ca
   if (tid < (uint32_t)TAU_TABLE_ELEMS) body_tau_tables<Fr>(tid, tau_canon, coeff_canon, first_index, table);
 }
 
+#ifndef SSO_EXP_MIN_BLOCKS
+#define SSO_EXP_MIN_BLOCKS 1
+#endif
 template <class G>
-__global__ void __launch_bounds__(128) k_batch_exp(const __grid_constant__ VecBatch batch, uint32_t in_compressed,
+__global__ void __launch_bounds__(128, SSO_EXP_MIN_BLOCKS) k_batch_exp(const __grid_constant__ VecBatch batch, uint32_t in_compressed,
                                                     const uint32_t* table, uint32_t check, uint32_t* jac_out, uint32_t* status) {
   uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   body_batch_exp<G>(tid, batch, in_compressed, table, check, jac_out, status);
@@ -72,6 +78,50 @@ __global__ void __launch_bounds__(128) k_reencode(uint32_t n, const uint8_t* in,
                                                    uint32_t* status) {
   uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   body_reencode<G>(tid, n, in, in_compressed, out, out_compressed, check, subgroup, aff_out, status);
+}
+
+// Both groups of a chunk in ONE launch: blocks [0, nb2) take G2 points (the long-running ones, scheduled first),
+// the rest take G1 points.  All blocks have the same register footprint, so G1 blocks fill the SMs that the last,
+// partial wave of G2 blocks leaves idle (two separate launches lose ~13 % each to wave quantisation).
+template <class G1, class G2>
+__global__ void __launch_bounds__(128) k_batch_exp_chunk(const __grid_constant__ VecBatch b1, const __grid_constant__ VecBatch b2,
+                                                          uint32_t nb2, uint32_t in_compressed, const uint32_t* table, uint32_t check,
+                                                          uint32_t* jac1, uint32_t* jac2, uint32_t* status) {
+  if (blockIdx.x < nb2) {
+    body_batch_exp<G2>(blockIdx.x * blockDim.x + threadIdx.x, b2, in_compressed, table, check, jac2, status);
+  } else {
+    body_batch_exp<G1>((blockIdx.x - nb2) * blockDim.x + threadIdx.x, b1, in_compressed, table, check, jac1, status);
+  }
+}
+template <class G1, class G2>
+__global__ void __launch_bounds__(128) k_normalize_chunk(const __grid_constant__ VecBatch b1, const __grid_constant__ VecBatch b2,
+                                                          uint32_t nb2, const uint32_t* jac1, const uint32_t* jac2, uint32_t out_compressed) {
+  if (blockIdx.x < nb2) body_normalize_write<G2>(blockIdx.x * blockDim.x + threadIdx.x, b2, jac2, out_compressed);
+  else body_normalize_write<G1>((blockIdx.x - nb2) * blockDim.x + threadIdx.x, b1, jac1, out_compressed);
+}
+
+template <class G1, class G2>
+inline int run_batch_exp_chunk(Ctx& c, int si, const VecBatch& b1, const VecBatch& b2, uint32_t in_compressed, const uint32_t* d_table,
+                               uint32_t out_compressed, uint32_t check, uint32_t* d_status, char* err, size_t errcap) {
+  uint64_t n1 = b1.total, n2 = b2.total;
+  if (n1 + n2 == 0) return SSO_OK;
+  for (uint32_t i = 0; i < b1.nseg; i++) if (b1.seg[i].n > (1u << 24)) { set_err(err, errcap, "vector longer than 2^24 elements: split the call"); return SSO_E_ARG; }
+  for (uint32_t i = 0; i < b2.nseg; i++) if (b2.seg[i].n > (1u << 24)) { set_err(err, errcap, "vector longer than 2^24 elements: split the call"); return SSO_E_ARG; }
+  cudaStream_t st = c.s[si];
+  uint32_t *d_jac1 = nullptr, *d_jac2 = nullptr;
+  int rc;
+  if ((rc = c.alloc((void**)&d_jac1, (size_t)n1 * 3 * G1::F::WORDS * 4, si))) return rc;
+  if ((rc = c.alloc((void**)&d_jac2, (size_t)n2 * 3 * G2::F::WORDS * 4, si))) return rc;
+  uint32_t nb2 = div_up(n2, 128), nb1 = div_up(n1, 128);
+  c.begin(PK_BATCH_EXP_CHUNK, si, n1 + n2);
+  k_batch_exp_chunk<G1, G2><<<nb1 + nb2, 128, 0, st>>>(b1, b2, nb2, in_compressed, d_table, check, d_jac1, d_jac2, d_status);
+  c.end(si);
+  uint32_t mb2 = div_up(div_up(n2, NORM_BATCH), 128), mb1 = div_up(div_up(n1, NORM_BATCH), 128);
+  c.begin(PK_NORMALIZE_CHUNK, si, n1 + n2);
+  k_normalize_chunk<G1, G2><<<mb1 + mb2, 128, 0, st>>>(b1, b2, mb2, d_jac1, d_jac2, out_compressed);
+  c.end(si);
+  CUDA_TRY(cudaGetLastError());
+  return SSO_OK;
 }
 
 // tau tables for one call: powers of tau from first_index plus up to three coefficient slots
@@ -314,6 +364,10 @@ template <class G1, class G2, class PP> struct CurveImpl {
     set_err(err, errcap, "unknown group %u", group);
     return SSO_E_ARG;
   }
+  static int batch_exp_chunk(Ctx& c, int si, const VecBatch& b1, const VecBatch& b2, uint32_t in_compressed, const uint32_t* d_table,
+                             uint32_t out_compressed, uint32_t check, uint32_t* d_status, char* err, size_t errcap) {
+    return run_batch_exp_chunk<G1, G2>(c, si, b1, b2, in_compressed, d_table, out_compressed, check, d_status, err, errcap);
+  }
   static int reencode(Ctx& c, int si, uint32_t group, const uint8_t* d_in, uint32_t in_compressed, uint64_t n, uint8_t* d_out,
                       uint32_t out_compressed, uint32_t check, uint32_t subgroup, uint32_t* d_aff, uint32_t* d_status, char* err,
                       size_t errcap) {
@@ -359,7 +413,7 @@ template <class G1, class G2, class PP> struct CurveImpl {
     return SSO_E_ARG;
   }
   static const CurveOps* ops() {
-    static const CurveOps o = {&tau_tables, &batch_exp, &reencode, &msm_pairs, &same_ratio, (uint32_t)Pairing<G1, G2, PP>::CHECK_BYTES, &keygen_g1, &hash_to_g2, (uint32_t)G1::Fr::L, &points_sum, &fill_generator, (uint32_t)G1::Fr::NBYTES, {2u * G1::F::WORDS, 2u * G2::F::WORDS}};
+    static const CurveOps o = {&tau_tables, &batch_exp, &batch_exp_chunk, &reencode, &msm_pairs, &same_ratio, (uint32_t)Pairing<G1, G2, PP>::CHECK_BYTES, &keygen_g1, &hash_to_g2, (uint32_t)G1::Fr::L, &points_sum, &fill_generator, (uint32_t)G1::Fr::NBYTES, {2u * G1::F::WORDS, 2u * G2::F::WORDS}};
     return &o;
   }
 };

@@ -37,10 +37,20 @@ template <class B_, class NR> struct Fp2 {
     return T{B::template mul_small<K>(a.c0), B::template mul_small<K>(a.c1)};
   }
   // out of line, parameters and result by value (registers under the device ABI; see fp.cuh)
+#ifndef SSO_FQ2_INLINE_BASE_MUL
+#define SSO_FQ2_INLINE_BASE_MUL 0
+#endif
+  __device__ __forceinline__ static typename B::T bmul(const typename B::T& x, const typename B::T& y) {
+#if SSO_FQ2_INLINE_BASE_MUL
+    return B::mul_inl(x, y);
+#else
+    return B::mul(x, y);
+#endif
+  }
   __device__ __noinline__ static T mul_val(T a, T b) {
-    typename B::T v0 = B::mul(a.c0, b.c0);
-    typename B::T v1 = B::mul(a.c1, b.c1);
-    typename B::T s = B::mul(B::add(a.c0, a.c1), B::add(b.c0, b.c1));
+    typename B::T v0 = bmul(a.c0, b.c0);
+    typename B::T v1 = bmul(a.c1, b.c1);
+    typename B::T s = bmul(B::add(a.c0, a.c1), B::add(b.c0, b.c1));
     T r;
     r.c0 = B::add(v0, NR::mul(v1));
     r.c1 = B::sub(B::sub(s, v0), v1);
@@ -48,8 +58,8 @@ template <class B_, class NR> struct Fp2 {
   }
   __device__ __noinline__ static T sqr_val(T a) {
     // (a0 + a1)(a0 + nr a1) = a0^2 + nr a1^2 + (nr + 1) a0 a1
-    typename B::T v = B::mul(a.c0, a.c1);
-    typename B::T pr = B::mul(B::add(a.c0, a.c1), B::add(a.c0, NR::mul(a.c1)));
+    typename B::T v = bmul(a.c0, a.c1);
+    typename B::T pr = bmul(B::add(a.c0, a.c1), B::add(a.c0, NR::mul(a.c1)));
     T r;
     r.c0 = B::sub(B::sub(pr, v), NR::mul(v));
     r.c1 = B::dbl(v);

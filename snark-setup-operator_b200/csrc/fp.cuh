@@ -35,6 +35,7 @@ __device__ __forceinline__ uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r
 __device__ __forceinline__ uint32_t subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 __device__ __forceinline__ uint32_t mul_lo(uint32_t a, uint32_t b) { uint32_t r; asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 __device__ __forceinline__ uint32_t mul_hi(uint32_t a, uint32_t b) { uint32_t r; asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint64_t mul_wide(uint32_t a, uint32_t b) { uint64_t r; asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b)); return r; }
 __device__ __forceinline__ uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 __device__ __forceinline__ uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 __device__ __forceinline__ uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
@@ -53,6 +54,7 @@ static inline uint32_t subc_cc(uint32_t a, uint32_t b) { return emu_sub(a, b, g_
 static inline uint32_t subc(uint32_t a, uint32_t b) { return emu_sub(a, b, g_cf, false); }
 static inline uint32_t mul_lo(uint32_t a, uint32_t b) { return (uint32_t)((uint64_t)a * b); }
 static inline uint32_t mul_hi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+static inline uint64_t mul_wide(uint32_t a, uint32_t b) { return (uint64_t)a * b; }
 static inline uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return emu_add(mul_lo(a, b), c, 0, true); }
 static inline uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return emu_add(mul_lo(a, b), c, g_cf, true); }
 static inline uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return emu_add(mul_hi(a, b), c, g_cf, true); }
@@ -106,8 +108,9 @@ template <int N> __device__ __forceinline__ uint32_t limbs_sub(uint32_t* r, cons
 template <int n> __device__ __forceinline__ void mul_n(uint32_t* acc, const uint32_t* a, uint32_t bi) {
 #pragma unroll
   for (int j = 0; j < n; j += 2) {
-    acc[j] = mul_lo(a[j], bi);
-    acc[j + 1] = mul_hi(a[j], bi);
+    uint64_t t = mul_wide(a[j], bi);               // one IMAD.WIDE instead of an IMAD + IMAD.HI pair
+    acc[j] = (uint32_t)t;
+    acc[j + 1] = (uint32_t)(t >> 32);
   }
 }
 // acc += sum_{j even} a[j] * bi * 2^(32 j); carry-out left in CC.CF
@@ -131,11 +134,19 @@ template <int n> __device__ __forceinline__ void madc_n_rshift(uint32_t* acc, co
   acc[n - 1] = madc_hi(a[n - 2], bi, 0);
 }
 
+// Note on instruction selection (measured, tools/mulbench): ptxas turns the a * b_i products of each row into
+// single IMAD.WIDE.U32.X instructions but always splits the m * p products of the reduction into IMAD.X +
+// IMAD.HI.U32.X pairs, whether the modulus sits in the constant bank, in uniform registers or in vector registers.
+template <class P> __device__ __forceinline__ void load_modulus(uint32_t* mod) {
+#pragma unroll
+  for (int i = 0; i < P::L; i++) mod[i] = P::p()[i];
+}
+
 // One CIOS step: T <- (T + a * bi + m * p) / 2^32 with T held as E (aligned at limb 0) plus
 // O (aligned at limb 1).  After the step the roles of E and O are exchanged (caller swaps).
-template <class P> __device__ __forceinline__ void mad_n_redc(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi, bool first) {
+template <class P> __device__ __forceinline__ void mad_n_redc(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi, bool first,
+                                                              const uint32_t* MOD) {
   constexpr int n = P::L;
-  const uint32_t* MOD = P::p();
   if (first) {
     mul_n<n>(O, a + 1, bi);
     mul_n<n>(E, a, bi);
@@ -154,11 +165,12 @@ template <class P> __device__ __forceinline__ void mad_n_redc(uint32_t* E, uint3
 // r = a * b * R^-1 mod p, inputs and output fully reduced
 template <class P> __device__ __forceinline__ void mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
   constexpr int n = P::L;
-  uint32_t even[n], odd[n];
+  uint32_t even[n], odd[n], mod[n];
+  load_modulus<P>(mod);
 #pragma unroll
   for (int i = 0; i < n; i += 2) {
-    mad_n_redc<P>(even, odd, a, b[i], i == 0);
-    mad_n_redc<P>(odd, even, a, b[i + 1], false);
+    mad_n_redc<P>(even, odd, a, b[i], i == 0, mod);
+    mad_n_redc<P>(odd, even, a, b[i + 1], false, mod);
   }
   // merge: result[k] = even[k] + odd[k+1]
   even[0] = add_cc(even[0], odd[1]);
@@ -167,7 +179,7 @@ template <class P> __device__ __forceinline__ void mont_mul(uint32_t* r, const u
   even[n - 1] = addc(even[n - 1], 0);
   // final subtraction: result < 2p
   uint32_t t[n];
-  uint32_t borrow = limbs_sub<n>(t, even, P::p());
+  uint32_t borrow = limbs_sub<n>(t, even, mod);
 #pragma unroll
   for (int k = 0; k < n; k++) r[k] = borrow ? even[k] : t[k];
 }
@@ -228,6 +240,8 @@ template <class P_> struct Fp {
     if constexpr (L > SSO_INLINE_MUL_MAX_L) { return mul_outlined(a, b); } else { T r; mont_mul<P>(r.v, a.v, b.v); return r; }
   }
   __device__ __forceinline__ static T sqr(const T& a) { return mul(a, a); }
+  // always-inlined multiplication, for callers that want independent multiplications interleaved by the scheduler
+  __device__ __forceinline__ static T mul_inl(const T& a, const T& b) { T r; mont_mul<P>(r.v, a.v, b.v); return r; }
   // multiply by a small non-negative integer constant
   template <int K> __device__ __forceinline__ static T mul_small(const T& a) {
     static_assert(K >= 0 && K < 64, "small constant");

@@ -94,7 +94,7 @@ inline const char* status_text(uint32_t code) {
 // Per-kernel launch accounting (always on) and optional CUDA-event timing on the launching stream
 // (sso_profile_enable) — the source of bench.py's roofline.achieved and gpu_launches.
 enum ProfKind { PK_TAU_TABLES = 0, PK_BATCH_EXP_G1, PK_BATCH_EXP_G2, PK_NORMALIZE_G1, PK_NORMALIZE_G2, PK_REENCODE_G1,
-                PK_REENCODE_G2, PK_FILL, PK_MSM, PK_OTHER, PK_COUNT };
+                PK_REENCODE_G2, PK_FILL, PK_MSM, PK_OTHER, PK_BATCH_EXP_CHUNK, PK_NORMALIZE_CHUNK, PK_COUNT };
 struct ProfSlot { std::atomic<uint64_t> launches{0}; std::atomic<uint64_t> ns{0}; std::atomic<uint64_t> elems{0}; };
 extern ProfSlot g_prof[PK_COUNT];
 extern std::atomic<int> g_prof_enabled;

@@ -154,7 +154,7 @@ def new_challenge_dev(params: Phase1Parameters, d_challenge, device=0):
 
 
 PROFILE_KINDS = ("tau_tables", "batch_exp_g1", "batch_exp_g2", "normalize_g1", "normalize_g2", "reencode_g1", "reencode_g2",
-                 "fill", "msm", "other")
+                 "fill", "msm", "other", "batch_exp_chunk", "normalize_chunk")
 
 
 def profile_enable(on=True):
