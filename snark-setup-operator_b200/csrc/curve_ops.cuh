@@ -61,8 +61,8 @@ __global__ void k_tau_tables(const uint32_t* tau_canon, const uint32_t* coeff_ca
 template <class G>
 __global__ void __launch_bounds__(128, SSO_EXP_MIN_BLOCKS) k_batch_exp(const __grid_constant__ VecBatch batch, uint32_t in_compressed,
                                                     const uint32_t* table, uint32_t check, uint32_t* jac_out, uint32_t* status) {
-  uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-  body_batch_exp<G>(tid, batch, in_compressed, table, check, jac_out, status);
+  extern __shared__ __align__(16) unsigned char tree_raw[];          // 2 * EXP_BLOCK field elements (dynamic: up to 72 KB)
+  block_batch_exp<G>(blockIdx.x, batch, in_compressed, table, check, jac_out, status, reinterpret_cast<typename G::F::T*>(tree_raw));
 }
 
 template <class G>
@@ -87,10 +87,12 @@ template <class G1, class G2>
 __global__ void __launch_bounds__(128) k_batch_exp_chunk(const __grid_constant__ VecBatch b1, const __grid_constant__ VecBatch b2,
                                                           uint32_t nb2, uint32_t in_compressed, const uint32_t* table, uint32_t check,
                                                           uint32_t* jac1, uint32_t* jac2, uint32_t* status) {
+  // one dynamic shared buffer, sized by the host for the wider of the two coordinate fields (2 * EXP_BLOCK elements)
+  extern __shared__ __align__(16) unsigned char tree_raw[];
   if (blockIdx.x < nb2) {
-    body_batch_exp<G2>(blockIdx.x * blockDim.x + threadIdx.x, b2, in_compressed, table, check, jac2, status);
+    block_batch_exp<G2>(blockIdx.x, b2, in_compressed, table, check, jac2, status, reinterpret_cast<typename G2::F::T*>(tree_raw));
   } else {
-    body_batch_exp<G1>((blockIdx.x - nb2) * blockDim.x + threadIdx.x, b1, in_compressed, table, check, jac1, status);
+    block_batch_exp<G1>(blockIdx.x - nb2, b1, in_compressed, table, check, jac1, status, reinterpret_cast<typename G1::F::T*>(tree_raw));
   }
 }
 template <class G1, class G2>
@@ -112,9 +114,14 @@ inline int run_batch_exp_chunk(Ctx& c, int si, const VecBatch& b1, const VecBatc
   int rc;
   if ((rc = c.alloc((void**)&d_jac1, (size_t)n1 * 3 * G1::F::WORDS * 4, si))) return rc;
   if ((rc = c.alloc((void**)&d_jac2, (size_t)n2 * 3 * G2::F::WORDS * 4, si))) return rc;
-  uint32_t nb2 = div_up(n2, 128), nb1 = div_up(n1, 128);
+  uint32_t nb2 = div_up(n2, EXP_BLOCK), nb1 = div_up(n1, EXP_BLOCK);
+  constexpr size_t TREE_BYTES = 2 * EXP_BLOCK * (sizeof(typename G1::F::T) > sizeof(typename G2::F::T) ? sizeof(typename G1::F::T)
+                                                                                                        : sizeof(typename G2::F::T));
+  static std::atomic<int> smem_set{0};
+  if (TREE_BYTES > 48 * 1024 && !smem_set.exchange(1))
+    CUDA_TRY(cudaFuncSetAttribute(k_batch_exp_chunk<G1, G2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TREE_BYTES));
   c.begin(PK_BATCH_EXP_CHUNK, si, n1 + n2);
-  k_batch_exp_chunk<G1, G2><<<nb1 + nb2, 128, 0, st>>>(b1, b2, nb2, in_compressed, d_table, check, d_jac1, d_jac2, d_status);
+  k_batch_exp_chunk<G1, G2><<<nb1 + nb2, EXP_BLOCK, TREE_BYTES, st>>>(b1, b2, nb2, in_compressed, d_table, check, d_jac1, d_jac2, d_status);
   c.end(si);
   uint32_t mb2 = div_up(div_up(n2, NORM_BATCH), 128), mb1 = div_up(div_up(n1, NORM_BATCH), 128);
   c.begin(PK_NORMALIZE_CHUNK, si, n1 + n2);
@@ -161,8 +168,12 @@ inline int run_batch_exp(Ctx& c, int si, const VecBatch& batch, uint32_t in_comp
   int rc;
   if ((rc = c.alloc((void**)&d_jac, (size_t)n * 3 * F::WORDS * 4, si))) return rc;
   constexpr bool IS_G1 = G::GROUP == 0;
+  constexpr size_t TREE_BYTES = 2 * EXP_BLOCK * sizeof(typename F::T);
+  static std::atomic<int> smem_set{0};
+  if (TREE_BYTES > 48 * 1024 && !smem_set.exchange(1))
+    CUDA_TRY(cudaFuncSetAttribute(k_batch_exp<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TREE_BYTES));
   c.begin(IS_G1 ? PK_BATCH_EXP_G1 : PK_BATCH_EXP_G2, si, n);
-  k_batch_exp<G><<<div_up(n, 128), 128, 0, st>>>(batch, in_compressed, d_table, check, d_jac, d_status);
+  k_batch_exp<G><<<div_up(n, EXP_BLOCK), EXP_BLOCK, TREE_BYTES, st>>>(batch, in_compressed, d_table, check, d_jac, d_status);
   c.end(si);
   c.begin(IS_G1 ? PK_NORMALIZE_G1 : PK_NORMALIZE_G2, si, n);
   k_normalize_write<G><<<div_up(div_up(n, NORM_BATCH), 128), 128, 0, st>>>(batch, d_jac, out_compressed);

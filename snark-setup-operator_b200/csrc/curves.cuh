@@ -30,6 +30,7 @@ using Fq6x3 = Fp3<Fq6, SmallNR<Fq6, 11, false>>;          // u^3 = 11
   static constexpr int COFACTOR_WORDS = COFACTOR_WORDS_##NAME;
 
 struct Bls12_377_G1 {
+  static constexpr bool AFFINE_TABLE = true;
   static constexpr bool HAS_GLV = true;
   using Glv = GLV_bls12_377_g1;
   static constexpr uint32_t GROUP = 0;
@@ -39,6 +40,7 @@ struct Bls12_377_G1 {
   __device__ __forceinline__ static bool field_sqrt(const F::T& a, F::T& o) { return F::sqrt(a, o); }
 };
 struct Bls12_377_G2 {
+  static constexpr bool AFFINE_TABLE = true;
   static constexpr bool HAS_GLV = true;
   using Glv = GLV_bls12_377_g2;
   static constexpr uint32_t GROUP = 1;
@@ -48,6 +50,7 @@ struct Bls12_377_G2 {
   __device__ __forceinline__ static bool field_sqrt(const F::T& a, F::T& o) { return F::sqrt(a, o); }
 };
 struct Bw6_761_G1 {
+  static constexpr bool AFFINE_TABLE = true;
   static constexpr bool HAS_GLV = true;
   using Glv = GLV_bw6_761_g1;
   static constexpr uint32_t GROUP = 0;
@@ -57,6 +60,7 @@ struct Bw6_761_G1 {
   __device__ __forceinline__ static bool field_sqrt(const F::T& a, F::T& o) { return F::sqrt(a, o); }
 };
 struct Bw6_761_G2 {
+  static constexpr bool AFFINE_TABLE = true;
   static constexpr bool HAS_GLV = true;
   using Glv = GLV_bw6_761_g2;
   static constexpr uint32_t GROUP = 1;
@@ -66,6 +70,7 @@ struct Bw6_761_G2 {
   __device__ __forceinline__ static bool field_sqrt(const F::T& a, F::T& o) { return F::sqrt(a, o); }
 };
 struct Mnt4_753_G1 {
+  static constexpr bool AFFINE_TABLE = true;
   static constexpr bool HAS_GLV = false;
   static constexpr uint32_t GROUP = 0;                                         // a = 2
   SSO_GROUP_COMMON(mnt4_753_g1, Fq4, Fq6)
@@ -74,6 +79,7 @@ struct Mnt4_753_G1 {
   __device__ __forceinline__ static bool field_sqrt(const F::T& a, F::T& o) { return F::sqrt(a, o); }
 };
 struct Mnt4_753_G2 {
+  static constexpr bool AFFINE_TABLE = true;
   static constexpr bool HAS_GLV = false;
   static constexpr uint32_t GROUP = 1;                                         // a' = (26, 0)
   SSO_GROUP_COMMON(mnt4_753_g2, Fq4x2, Fq6)
@@ -82,6 +88,7 @@ struct Mnt4_753_G2 {
   __device__ __forceinline__ static bool field_sqrt(const F::T& a, F::T& o) { return F::sqrt(a, o); }
 };
 struct Mnt6_753_G1 {
+  static constexpr bool AFFINE_TABLE = true;
   static constexpr bool HAS_GLV = false;
   static constexpr uint32_t GROUP = 0;                                         // a = 11
   SSO_GROUP_COMMON(mnt6_753_g1, Fq6, Fq4)
@@ -90,6 +97,7 @@ struct Mnt6_753_G1 {
   __device__ __forceinline__ static bool field_sqrt(const F::T& a, F::T& o) { return F::sqrt(a, o); }
 };
 struct Mnt6_753_G2 {
+  static constexpr bool AFFINE_TABLE = false;   // measured: the 72 KB Fq3 inversion tree costs more than mixed additions save
   static constexpr bool HAS_GLV = false;
   static constexpr uint32_t GROUP = 1;                                         // a' = (0, 0, 11) = 11 u^2, u^3 = 11
   SSO_GROUP_COMMON(mnt6_753_g2, Fq6x3, Fq4)

@@ -167,6 +167,7 @@ template <class B_, class NR> struct Fp3 {
     return r;
   }
   __device__ __noinline__ static T sqr(const T& a) { return mul(a, a); }
+  __device__ __forceinline__ static T mul_base(const T& a, const typename B::T& k) { return T{B::mul(a.c0, k), B::mul(a.c1, k), B::mul(a.c2, k)}; }
   __device__ __noinline__ static T inv(const T& a) {
     typename B::T t0 = B::sub(B::sqr(a.c0), NR::mul(B::mul(a.c1, a.c2)));
     typename B::T t1 = B::sub(NR::mul(B::sqr(a.c2)), B::mul(a.c0, a.c1));

@@ -273,7 +273,58 @@ template <class P_> struct Fp {
     }
     return r;
   }
-  __device__ __forceinline__ static T inv(const T& a) { return pow_const(a, P::pm2()); }
+  // Fermat inversion a^(p-2): ~1.5 * bits multiplications (kept for cross-checking the binary algorithm)
+  __device__ __forceinline__ static T inv_fermat(const T& a) { return pow_const(a, P::pm2()); }
+
+  // Modular inversion by the binary extended Euclidean algorithm on the raw residue (no multiplications:
+  // shifts, subtractions and comparisons only — ~5x fewer instructions than Fermat, which matters where ONE
+  // thread inverts for a whole block).  Input/output in Montgomery form; inv(0) = 0.
+  //   raw = a R  ->  raw^-1 = a^-1 R^-1 ; two multiplications by R^2 give a^-1 R.
+  __device__ __noinline__ static T inv(const T& a) {
+    if (is_zero(a)) return a;
+    uint32_t u[L], v[L], x1[L], x2[L], t[L];
+#pragma unroll
+    for (int i = 0; i < L; i++) { u[i] = a.v[i]; v[i] = P::p()[i]; x1[i] = i == 0 ? 1u : 0u; x2[i] = 0u; }
+    // halve x modulo p: x even -> x/2, x odd -> (x + p)/2   (x + p < 2^(32 L): p has spare top bits)
+    auto halve_mod = [&](uint32_t* x) {
+      if (x[0] & 1u) limbs_add<L>(x, x, P::p());
+#pragma unroll
+      for (int i = 0; i < L - 1; i++) x[i] = (x[i] >> 1) | (x[i + 1] << 31);
+      x[L - 1] >>= 1;
+    };
+    auto shr1 = [&](uint32_t* x) {
+#pragma unroll
+      for (int i = 0; i < L - 1; i++) x[i] = (x[i] >> 1) | (x[i + 1] << 31);
+      x[L - 1] >>= 1;
+    };
+    auto is_one = [&](const uint32_t* x) {
+      uint32_t o = x[0] ^ 1u;
+#pragma unroll
+      for (int i = 1; i < L; i++) o |= x[i];
+      return o == 0;
+    };
+    while (!is_one(u) && !is_one(v)) {
+      while ((u[0] & 1u) == 0) { shr1(u); halve_mod(x1); }
+      while ((v[0] & 1u) == 0) { shr1(v); halve_mod(x2); }
+      // u, v odd
+      if (limbs_sub<L>(t, u, v) == 0) {             // u >= v
+#pragma unroll
+        for (int i = 0; i < L; i++) u[i] = t[i];
+        if (limbs_sub<L>(x1, x1, x2) != 0) limbs_add<L>(x1, x1, P::p());
+      } else {
+        limbs_sub<L>(v, v, u);
+        if (limbs_sub<L>(x2, x2, x1) != 0) limbs_add<L>(x2, x2, P::p());
+      }
+    }
+    T r;
+    bool use1 = is_one(u);
+#pragma unroll
+    for (int i = 0; i < L; i++) r.v[i] = use1 ? x1[i] : x2[i];
+    T r2;
+#pragma unroll
+    for (int i = 0; i < L; i++) r2.v[i] = P::r2()[i];
+    return mul(mul(r, r2), r2);
+  }
 
   // canonical-order comparison "a > -a" used by the serialisation sign flag
   __device__ __forceinline__ static bool is_neg_canonical(const T& canon) { return limbs_gt<L>(canon.v, P::half()); }

@@ -103,24 +103,75 @@ __device__ __forceinline__ void scalar_for_index(const uint32_t* table, uint32_t
 }
 
 // ---------------------------------------------------------------------------------------------
+// One field inversion per thread block: product tree over the block's leaves in shared memory.
+//   tree : 2 * BS field elements; the leaf of thread t sits at tree[BS + t] and is replaced by its inverse.
+// Leaves must be non-zero.  tree_up / tree_down are the per-thread steps (also driven by tests/emul).
+// ---------------------------------------------------------------------------------------------
+static constexpr int EXP_BLOCK = 128;
+
+template <class F> __device__ __forceinline__ void tree_up(typename F::T* tree, int n, int t) {
+  if (t < n) tree[n + t] = F::mul(tree[2 * (n + t)], tree[2 * (n + t) + 1]);
+}
+template <class F> __device__ __forceinline__ void tree_down(typename F::T* tree, int n, int t) {
+  if (t < n) {
+    int k = n + t;
+    typename F::T l = tree[2 * k], r = tree[2 * k + 1], pinv = tree[k];
+    tree[2 * k] = F::mul(pinv, r);
+    tree[2 * k + 1] = F::mul(pinv, l);
+  }
+}
+#ifndef SSO_HOST_EMUL
+template <class F> __device__ __forceinline__ void block_batch_inverse(typename F::T* tree, int t) {
+  for (int n = EXP_BLOCK / 2; n >= 1; n >>= 1) { __syncthreads(); tree_up<F>(tree, n, t); }
+  __syncthreads();
+  if (t == 0) tree[1] = F::inv(tree[1]);
+  for (int n = 1; n < EXP_BLOCK; n <<= 1) { __syncthreads(); tree_down<F>(tree, n, t); }
+  __syncthreads();
+}
+#else
+template <class F> inline void block_batch_inverse_all(typename F::T* tree) {
+  for (int n = EXP_BLOCK / 2; n >= 1; n >>= 1) for (int t = 0; t < n; t++) tree_up<F>(tree, n, t);
+  tree[1] = F::inv(tree[1]);
+  for (int n = 1; n < EXP_BLOCK; n <<= 1) for (int t = 0; t < n; t++) tree_down<F>(tree, n, t);
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------
 // K3 + K2: read one point, validate, multiply by its scalar, leave the Jacobian result in HBM.
 //   jac_out : total * 3 * F::WORDS words, [flat point index][X|Y|Z][limb]
 //   status  : [0] first failure code, [1] element index inside its vector, [2] vector (segment) index
+// Three stages around the per-block inversion (ec.cuh "staged scalar multiplication"):
+//   exp_stage_a  per thread : decode + checks, scalar from the tau tables, recoding, Jacobian window table
+//   (block)                  : block_batch_inverse over the threads' Z products
+//   exp_stage_c  per thread : affine table, window loop with mixed additions, store
 // ---------------------------------------------------------------------------------------------
+template <class G> struct ExpTypes {
+  using C = SW<G>;
+  using Fr = typename G::Fr;
+  static constexpr bool GLV = G::HAS_GLV;
+  static constexpr int KBITS = [] { if constexpr (G::HAS_GLV) return (int)G::Glv::KBITS; else return (int)G::Fr::P::BITS; }();
+  static constexpr int KW = [] { if constexpr (G::HAS_GLV) return (int)G::Glv::KW; else return (int)G::Fr::L; }();
+  static constexpr int NW = (KBITS + 2 + 3) / 4;
+  using State = typename C::template Staged<GLV, KW, NW>;
+};
+
 template <class G>
-__device__ __forceinline__ void body_batch_exp(uint32_t tid, const VecBatch& b, uint32_t in_compressed, const uint32_t* table,
-                                               uint32_t check, uint32_t* jac_out, uint32_t* status) {
+__device__ __forceinline__ typename G::F::T exp_stage_a(uint32_t tid, const VecBatch& b, uint32_t in_compressed, const uint32_t* table,
+                                                        uint32_t check, uint32_t* status, typename ExpTypes<G>::State& st) {
   using C = SW<G>;
   using F = typename G::F;
   using Fr = typename G::Fr;
+  using ET = ExpTypes<G>;
   uint32_t sidx, j;
-  if (!locate(b, tid, sidx, j)) return;
+  st.active = false;
+  st.affine = false;
+  if (!locate(b, tid, sidx, j)) return F::one();
   const VecSeg& sg = b.seg[sidx];
   typename C::Affine p;
-  uint32_t st = in_compressed ? C::read_compressed(sg.in + (size_t)j * C::SIZE_C, p)
-                              : C::read_uncompressed(sg.in + (size_t)j * C::SIZE_U, p);
-  if (st != C::DESER_OK) { report(status, st, j, sidx); p.inf = true; }
-  if (check != CHECK_NO && st == C::DESER_OK) {
+  uint32_t dst = in_compressed ? C::read_compressed(sg.in + (size_t)j * C::SIZE_C, p)
+                               : C::read_uncompressed(sg.in + (size_t)j * C::SIZE_U, p);
+  if (dst != C::DESER_OK) { report(status, dst, j, sidx); p.inf = true; }
+  if (check != CHECK_NO && dst == C::DESER_OK) {
     if (p.inf) report(status, ST_ZERO_POINT, j, sidx);
     else if (check == CHECK_FULL && !in_compressed && !C::on_curve(p)) { report(status, ST_NOT_ON_CURVE, j, sidx); p.inf = true; }
   }
@@ -132,14 +183,63 @@ __device__ __forceinline__ void body_batch_exp(uint32_t tid, const VecBatch& b, 
 #pragma unroll
     for (int i = 0; i < Fr::L; i++) k[i] = s.v[i];
   }
-  typename C::Jac r;
-  if constexpr (G::HAS_GLV) r = C::template scalar_mul_glv<typename G::Glv, Fr::L>(p, k);
-  else r = C::template scalar_mul<Fr::L, Fr::P::BITS>(p, k);
+  if constexpr (ET::GLV) {
+    uint32_t k1[ET::KW], k2[ET::KW];
+    C::template glv_split<typename G::Glv, Fr::L>(k, k1, k2, st.neg1, st.neg2);
+    C::template bias_scalar<ET::KW, ET::NW>(k1, st.kb1);
+    C::template bias_scalar<ET::KW, ET::NW>(k2, st.kb2);
+  } else {
+    st.neg1 = st.neg2 = false;
+    C::template bias_scalar<Fr::L, ET::NW>(k, st.kb1);
+  }
+  return C::staged_table(st, p);
+}
+
+template <class G>
+__device__ __forceinline__ void exp_stage_c(uint32_t tid, const VecBatch& b, typename ExpTypes<G>::State& st,
+                                            const typename G::F::T& zinv, uint32_t* jac_out) {
+  using C = SW<G>;
+  using F = typename G::F;
+  if (tid >= b.total) return;
+  C::staged_normalise(st, zinv);
+  const uint32_t* beta = nullptr;
+  if constexpr (ExpTypes<G>::GLV) beta = G::Glv::beta();
+  typename C::Jac r = C::staged_loop(st, beta);
   uint32_t* o = jac_out + (size_t)tid * 3 * F::WORDS;
   F::store(o, 1, r.X);
   F::store(o + F::WORDS, 1, r.Y);
   F::store(o + 2 * F::WORDS, 1, r.Z);
 }
+
+#ifndef SSO_HOST_EMUL
+// whole block: `tree` is shared memory for 2 * EXP_BLOCK field elements
+template <class G>
+__device__ __forceinline__ void block_batch_exp(uint32_t block, const VecBatch& b, uint32_t in_compressed, const uint32_t* table,
+                                                uint32_t check, uint32_t* jac_out, uint32_t* status, typename G::F::T* tree) {
+  typename ExpTypes<G>::State st;
+  uint32_t tid = block * EXP_BLOCK + threadIdx.x;
+  typename G::F::T leaf = exp_stage_a<G>(tid, b, in_compressed, table, check, status, st);
+  if constexpr (G::AFFINE_TABLE) {
+    tree[EXP_BLOCK + threadIdx.x] = leaf;
+    block_batch_inverse<typename G::F>(tree, threadIdx.x);
+    leaf = tree[EXP_BLOCK + threadIdx.x];
+  }
+  exp_stage_c<G>(tid, b, st, leaf, jac_out);
+}
+#else
+// emulation: one block at a time, stages run for all of its threads in turn
+template <class G>
+inline void block_batch_exp_all(uint32_t block, const VecBatch& b, uint32_t in_compressed, const uint32_t* table, uint32_t check,
+                                uint32_t* jac_out, uint32_t* status) {
+  using F = typename G::F;
+  std::vector<typename ExpTypes<G>::State> st(EXP_BLOCK);
+  std::vector<typename F::T> tree(2 * EXP_BLOCK);
+  for (int t = 0; t < EXP_BLOCK; t++)
+    tree[EXP_BLOCK + t] = exp_stage_a<G>(block * EXP_BLOCK + t, b, in_compressed, table, check, status, st[t]);
+  block_batch_inverse_all<F>(tree.data());
+  for (int t = 0; t < EXP_BLOCK; t++) exp_stage_c<G>(block * EXP_BLOCK + t, b, st[t], tree[EXP_BLOCK + t], jac_out);
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // K4: batch normalisation (Montgomery's trick over NB consecutive points per thread: one field

@@ -98,7 +98,7 @@ extern "C" int emul_batch_exp(uint32_t curve, uint32_t group, const uint8_t* in,
     // second segment continues the index range: emulate by a second table start -> instead run it as its own batch
     b.total = n0;
     std::vector<uint32_t> jac((size_t)n * 3 * F::WORDS);
-    for (uint32_t t = 0; t < n0; t++) body_batch_exp<G>(t, b, in_compressed, table.data(), check, jac.data(), status);
+    for (uint32_t blk = 0; blk * EXP_BLOCK < n0; blk++) block_batch_exp_all<G>(blk, b, in_compressed, table.data(), check, jac.data(), status);
     for (uint32_t t = 0; t * NORM_BATCH < n0; t++) body_normalize_write<G>(t, b, jac.data(), out_compressed);
     // remaining elements: a batch of two segments (n1 - 1 elements + 1 element) starting at index first + n0
     std::vector<uint32_t> table2((size_t)TAU_TABLE_ELEMS * Fr::L);
@@ -110,7 +110,7 @@ extern "C" int emul_batch_exp(uint32_t curve, uint32_t group, const uint8_t* in,
       memset(&b2, 0, sizeof b2);
       b2.seg[0] = VecSeg{in + n0 * isz, out + n0 * osz, n1, 2, coeff_canon != nullptr, mode};
       b2.nseg = 1; b2.total = n1;
-      for (uint32_t t = 0; t < n1; t++) body_batch_exp<G>(t, b2, in_compressed, table2.data(), check, jac.data(), st2);
+      for (uint32_t blk = 0; blk * EXP_BLOCK < n1; blk++) block_batch_exp_all<G>(blk, b2, in_compressed, table2.data(), check, jac.data(), st2);
       for (uint32_t t = 0; t * NORM_BATCH < n1; t++) body_normalize_write<G>(t, b2, jac.data(), out_compressed);
       if (status[0] == 0 && st2[0] != 0) { status[0] = st2[0]; status[1] = st2[1] + n0; }
     }
@@ -138,7 +138,7 @@ extern "C" int emul_batch_exp2(uint32_t curve, uint32_t group, const uint8_t* in
     b.seg[1] = VecSeg{in1, out1, n1, 2, 1, 1};      // shared scalar coeff2
     b.nseg = 2; b.total = n0 + n1;
     std::vector<uint32_t> jac((size_t)b.total * 3 * F::WORDS);
-    for (uint32_t t = 0; t < b.total; t++) body_batch_exp<G>(t, b, 0, table.data(), 1, jac.data(), status);
+    for (uint32_t blk = 0; blk * EXP_BLOCK < b.total; blk++) block_batch_exp_all<G>(blk, b, 0, table.data(), 1, jac.data(), status);
     for (uint32_t t = 0; t * NORM_BATCH < b.total; t++) body_normalize_write<G>(t, b, jac.data(), 1);
   });
 }

@@ -253,3 +253,22 @@ def test_key_generation_matches_oracle(emul, name):
     assert emul.emul_hash_to_g2(c.cid, 3, (ctypes.c_uint32 * 24).from_buffer_copy(seeds), scal, g2_s, g2_sx) == 0
     assert g2_sx.raw == want_pk[6 * g1u:]
     assert g2_s.raw[:g2u] == ser.point_to_bytes(c.g2, phase1.compute_g2_s(c, digest, pub.tau_g1[0], pub.tau_g1[1], 0), False)
+
+
+def test_small_order_base_point(emul):
+    """A base point whose multiples hit the identity (order 2: (-1, 0) on y^2 = x^3 + 1) makes table entries with
+    Z = 0; the affine-table path must fall back to the Jacobian table for that thread only, and the other threads of
+    the block (sharing the batched inversion) must be unaffected."""
+    c = get_curve("bls12_377")
+    G = c.g1
+    p2 = (c.Fq.p - 1, 0)
+    assert G.on_curve(p2) and G.add(p2, p2) is None
+    Lr = (c.Fr.bits + 31) // 32
+    pts = [G.mul(G.gen, 5), p2, G.mul(G.gen, 7), None]
+    buf = ser.points_to_bytes(G, pts, False)
+    st = (ctypes.c_uint32 * 3)()
+    for k in (1, 2, 12345, 12346):
+        want = ser.points_to_bytes(G, [G.mul(P, k) for P in pts], True)
+        out = ctypes.create_string_buffer(len(want))
+        assert emul.emul_batch_exp(c.cid, 0, buf, 0, len(pts), words(1, Lr), words(k, Lr), ctypes.c_uint64(0), 1, 0, out, 1, st) == 0
+        assert out.raw == want, k
