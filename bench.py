@@ -41,24 +41,32 @@ GLV_KBITS = {"bls12_377": 129, "bw6_761": 191}      # csrc/constants.cuh GLV_*::
 
 
 def declared_fq_muls_per_point(curve: str, group: int) -> float:
-    """Closed-form field-multiplication count of k_batch_exp per point (kernels):
-    signed 4-bit windows; table 1P..8P = 4 dbl + 3 madd; 4 multiplications to read the point into Montgomery form.
-      plain ladder (MNT4/6):  NW = ceil((bits+2)/4) windows, 4 (NW-1) dbl + NW * 15/16 additions
-      GLV (BLS12-377, BW6):   NW = ceil((KBITS+2)/4) windows on the two half-size scalars,
-                              4 (NW-1) dbl + 2 NW * 15/16 additions + NW * 15/16 multiplications by beta
-    Fq2: mul = 3, sqr = 2 base multiplications; Fq3: mul = sqr = 6; squarings count as multiplications."""
+    """Closed-form field-multiplication count of the batch_exp kernel per point, S = M:
+      read the point into Montgomery form            2 deg
+      window table 1P..8P                            4 dbl + 3 madd
+      affine table (all groups but MNT6 G2)          6 F-mul (Z products) + 13 F-mul + 7 (1 S + 3 M) (normalisation)
+                                                     + 3 F-mul (share of the per-block inversion tree)
+      window loop, signed 4-bit digits               4 (NW - 1) dbl + additions on 15/16 of the windows:
+         plain ladder (MNT4/6)   NW = ceil((bits+2)/4)   one addition per window
+         GLV (BLS12-377, BW6)    NW = ceil((KBITS+2)/4)  two additions per window + one multiplication by beta (deg Fq-muls)
+      additions are mixed (madd) with the affine table, full Jacobian additions otherwise.
+    Fq2: mul = 3, sqr = 2 base multiplications; Fq3: mul = sqr = 6."""
     _, bits = CURVE_BITS[curve]
     deg = G2_DEG[curve] if group == 1 else 1
     M, S = {1: (1, 1), 2: (3, 2), 3: (6, 6)}[deg]
     dbl = 2 * M + 5 * S if A_ZERO[curve] else 1 * M + 8 * S
     madd = 7 * M + 4 * S
     add = 11 * M + 5 * S
-    table = 4 * dbl + 3 * madd + 4 * deg
+    affine = not (curve == "mnt6_753" and group == 1)
+    work = 2 * deg + 4 * dbl + 3 * madd
+    if affine:
+        work += (6 + 13 + 21 + 3) * M + 7 * S
+    step = madd if affine else add
     if curve in GLV_KBITS:
         nw = (GLV_KBITS[curve] + 2 + 3) // 4
-        return table + 4 * (nw - 1) * dbl + 2 * nw * (15.0 / 16.0) * add + nw * (15.0 / 16.0) * deg
+        return work + 4 * (nw - 1) * dbl + 2 * nw * (15.0 / 16.0) * step + nw * (15.0 / 16.0) * deg
     nw = (bits + 2 + 3) // 4
-    return table + 4 * (nw - 1) * dbl + nw * (15.0 / 16.0) * add
+    return work + 4 * (nw - 1) * dbl + nw * (15.0 / 16.0) * step
 
 
 class ClockSampler(threading.Thread):

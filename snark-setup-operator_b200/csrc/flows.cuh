@@ -129,11 +129,8 @@ inline int verify_chunk_host(Ctx& c, const CurveOps* ops, const P1Layout& L, uin
                              uint32_t subgroup_mode, uint32_t ratio_check, const uint8_t* rlc_seed32, char* err, size_t errcap) {
   int rc;
   const size_t g1u = L.cs.g1u, g2u = L.cs.g2u;
-  // 1. hash chain: the response must continue the challenge it claims to be based on
-  uint8_t ch_hash[64];
-  blake2b_512(challenge, L.acc_size, ch_hash);
-  if (memcmp(ch_hash, response, 64) != 0) { set_err(err, errcap, "hash chain broken: response does not continue the challenge"); return SSO_E_VERIFY; }
-  // 2. decode + check the response vectors on the device, producing the new challenge image
+  // 1. decode + check the response vectors on the device, producing the new challenge image; the GPU starts
+  //    first so that the two sequential Blake2b passes on the host (challenge, response) overlap with it
   uint8_t *d_resp, *d_new;
   uint32_t* d_status;
   if ((rc = c.alloc((void**)&d_resp, L.contrib_size))) return rc;
@@ -165,6 +162,10 @@ inline int verify_chunk_host(Ctx& c, const CurveOps* ops, const P1Layout& L, uin
     if ((rc = ops->msm_pairs(c, si, groups[v], d_aff[v], d_aff[v] + ops->aff_words[groups[v]], counts[v] - 1, rlc_seed32, d_pairs[v],
                              err, errcap))) return rc;
   }
+  // 3b. hash chain (host, overlapped with the GPU work above): the response must continue the challenge
+  uint8_t ch_hash[64];
+  blake2b_512(challenge, L.acc_size, ch_hash);
+  if (memcmp(ch_hash, response, 64) != 0) { set_err(err, errcap, "hash chain broken: response does not continue the challenge"); return SSO_E_VERIFY; }
   // 4. proof-of-knowledge seeds while the GPU works: g2_s = hash_to_g2(Blake2b(pers || digest || g1_s || g1_s_x))
   const uint8_t* pk = response + L.off_c[5];
   std::vector<uint8_t> seeds2(3 * 32);
