@@ -46,7 +46,6 @@ def combine(response_list, combined_filename: str, chunk_params, full_params: p1
     file (uncompressed here), decoding on the GPU.  `chunk_params[i]` describes response_list[i]."""
     import torch
     offs_f, counts_f, sizes_f = full_layout(full_params, False)
-    out = np.lib.format.open_memmap if False else None
     total = offs_f[5]
     mm = np.memmap(combined_filename, dtype=np.uint8, mode="w+", shape=(total,))
     cursor = list(offs_f[:5])

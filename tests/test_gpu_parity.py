@@ -213,3 +213,51 @@ def test_same_ratio_verdicts(name):
     with pytest.raises(sso.SsoError) as e:
         sso.same_ratio(name, [(bytes(bad),) + checks[0][1:]])
     assert e.value.code == -3
+
+
+@pytest.mark.parametrize("name,power,clog,k", [("bls12_377", 20, 16, 1),      # BASELINE config 2: one full chunk
+                                               ("bw6_761", 12, 10, 0),        # BASELINE config 1: first chunk
+                                               ("bw6_761", 12, 10, 7)])       # BASELINE config 1: G1-only tail chunk
+def test_named_configs_at_full_size(name, power, clog, k):
+    """The configurations BASELINE.json names, at their real sizes: composition of two contributions equals the
+    contribution with the product key (byte for byte), the verifier accepts the result, and sampled elements match
+    the oracle's scalar multiplication."""
+    c = get_curve(name)
+    cs = 1 << clog
+    p = sso.Phase1Parameters.new_chunk(name, k, cs, power, cs)
+    o = Phase1Params.new_chunk(name, k, cs, power, cs)
+    d_gen = torch.empty(o.accumulator_size, dtype=torch.uint8, device="cuda")
+    sso.new_challenge_dev(p, d_gen)
+    r = c.Fr.p
+    k1 = phase1.PrivateKey(*synth.scalars_from_seed(c, synth.SEED_PREV))
+    k2 = synth.contributor_key(c)
+    k12 = phase1.PrivateKey(k1.tau * k2.tau % r, k1.alpha * k2.alpha % r, k1.beta * k2.beta % r)
+    d_r1 = torch.zeros(o.contribution_size, dtype=torch.uint8, device="cuda")
+    sso.contribute_dev(p, d_gen, d_r1, k1.tau, k1.alpha, k1.beta)
+    d_c1 = _decompress_response(p, d_r1)
+    d_r2 = torch.zeros(o.contribution_size, dtype=torch.uint8, device="cuda")
+    sso.contribute_dev(p, d_c1, d_r2, k2.tau, k2.alpha, k2.beta)
+    d_r12 = torch.zeros(o.contribution_size, dtype=torch.uint8, device="cuda")
+    sso.contribute_dev(p, d_gen, d_r12, k12.tau, k12.alpha, k12.beta)
+    end = o.offsets(True)[5]
+    assert torch.equal(d_r2[64:end], d_r12[64:end])
+    resp = host_bytes(d_r1)
+    oc = o.offsets(True)
+    g1c, g2c = o.sizes(True)
+    rnd = random.Random(k)
+    for vec, G, size, coeff, cnt in ((0, c.g1, g1c, 1, o.g1_count), (1, c.g2, g2c, 1, o.other_count),
+                                     (2, c.g1, g1c, k1.alpha, o.other_count), (3, c.g1, g1c, k1.beta, o.other_count)):
+        if cnt == 0:
+            continue
+        for j in {0, cnt - 1, rnd.randrange(cnt)}:
+            want = G.mul(G.gen, coeff * pow(k1.tau, o.start + j, r) % r)
+            assert resp[oc[vec] + j * size: oc[vec] + (j + 1) * size] == ser.point_to_bytes(G, want, True)
+    # a full seeded contribution of the same chunk is accepted by the verifier (hash chain, PoK, ratio checks)
+    ch = host_bytes(d_c1)
+    h_ch = bytearray(ch)
+    h_ch[:64] = phase1.blank_hash()
+    resp2 = bytearray(o.contribution_size)
+    sso.contribute_seeded_buf(p, bytes(h_ch), resp2, synth.SEED_CONTRIB)
+    new_ch = bytearray(o.accumulator_size)
+    sso.verify_chunk_buf(p, bytes(h_ch), bytes(resp2), new_ch)
+    assert bytes(new_ch[:64]) == phase1.calculate_hash(bytes(resp2))
