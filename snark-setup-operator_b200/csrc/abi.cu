@@ -392,9 +392,9 @@ int32_t sso_p1_contribute_buf(const sso_p1_params_t* p, const uint8_t* challenge
   if ((rc = c.alloc((void**)&d_resp, L.contrib_size))) return rc;
   if ((rc = status_buffer(c, &d_status, err, errcap))) return rc;
   c.mark("scratch allocated");
+  // stream-ordered: the kernels below are enqueued behind the copy, and the host goes straight on to hashing
   CUDA_TRY(cudaMemcpyAsync(d_ch, challenge, L.acc_size, cudaMemcpyHostToDevice, c.s[0]));
-  CUDA_TRY(cudaStreamSynchronize(c.s[0]));
-  c.mark("challenge H2D");
+  c.mark("challenge H2D enqueued");
   if ((rc = p1_contribute_streams(c, ops, L, d_ch, d_resp, tau, alpha, beta, check_input, d_status, err, errcap))) return rc;
   c.mark("kernels enqueued");
   // the hash-chain link is computed on the host while the GPU works

