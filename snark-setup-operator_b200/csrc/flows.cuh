@@ -152,6 +152,7 @@ inline int verify_chunk_host(Ctx& c, const CurveOps* ops, const P1Layout& L, uin
     if ((rc = ops->reencode(c, si, groups[v], d_resp + L.off_c[v], 1, counts[v], d_new + L.off_u[v], 0, check_output, subgroup,
                             d_aff[v], d_status, err, errcap))) return rc;
   }
+  c.mark("verify: decode launches enqueued");
   // 3. random-linear-combination pairs for the power-ratio checks
   uint8_t* d_pairs[4] = {nullptr, nullptr, nullptr, nullptr};
   for (int v = 0; v < 4; v++) {
@@ -162,10 +163,12 @@ inline int verify_chunk_host(Ctx& c, const CurveOps* ops, const P1Layout& L, uin
     if ((rc = ops->msm_pairs(c, si, groups[v], d_aff[v], d_aff[v] + ops->aff_words[groups[v]], counts[v] - 1, rlc_seed32, d_pairs[v],
                              err, errcap))) return rc;
   }
+  c.mark("verify: msm launches enqueued");
   // 3b. hash chain (host, overlapped with the GPU work above): the response must continue the challenge
   uint8_t ch_hash[64];
   blake2b_512(challenge, L.acc_size, ch_hash);
   if (memcmp(ch_hash, response, 64) != 0) { set_err(err, errcap, "hash chain broken: response does not continue the challenge"); return SSO_E_VERIFY; }
+  c.mark("verify: blake2b(challenge)");
   // 4. proof-of-knowledge seeds while the GPU works: g2_s = hash_to_g2(Blake2b(pers || digest || g1_s || g1_s_x))
   const uint8_t* pk = response + L.off_c[5];
   std::vector<uint8_t> seeds2(3 * 32);
@@ -186,6 +189,7 @@ inline int verify_chunk_host(Ctx& c, const CurveOps* ops, const P1Layout& L, uin
   if ((rc = ops->hash_to_g2(c, 0, 3, d_seeds2, nullptr, d_g2s, nullptr, err, errcap))) return rc;
   // the new challenge's hash slot chains the response
   blake2b_512(response, L.contrib_size, new_challenge);
+  c.mark("verify: blake2b(response)");
   if ((rc = sync_all(c, err, errcap))) return rc;
   if ((rc = check_status(c, d_status, "response", err, errcap))) return rc == SSO_E_INPUT ? SSO_E_VERIFY : rc;
   CUDA_TRY(cudaMemcpy(new_challenge + 64, d_new + 64, L.acc_size - 64, cudaMemcpyDeviceToHost));
@@ -197,6 +201,7 @@ inline int verify_chunk_host(Ctx& c, const CurveOps* ops, const P1Layout& L, uin
     pairs[v].resize(2 * (groups[v] == GROUP_G1 ? g1u : g2u));
     CUDA_TRY(cudaMemcpy(pairs[v].data(), d_pairs[v], pairs[v].size(), cudaMemcpyDeviceToHost));
   }
+  c.mark("verify: results D2H");
   // 5. collect the same_ratio checks
   std::vector<RatioCheck> checks;
   const uint8_t* pk_g2 = pk + 6 * g1u;                       // tau_g2, alpha_g2, beta_g2 (= g2_s_x)
@@ -235,7 +240,9 @@ inline int verify_chunk_host(Ctx& c, const CurveOps* ops, const P1Layout& L, uin
     if (chunk_index == 0)
       add_check(checks, "power ratio: tau_g2", after + L.off_u[0], after + L.off_u[0] + g1u, g1u, pairs[1].data(), pairs[1].data() + g2u, g2u);
   }
-  return run_checks(c, ops, checks, err, errcap);
+  rc = run_checks(c, ops, checks, err, errcap);
+  c.mark("verify: pairings");
+  return rc;
 }
 
 }  // namespace sso

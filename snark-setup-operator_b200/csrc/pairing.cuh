@@ -27,7 +27,7 @@ template <class G1, class G2, class PP> struct Pairing {
   using C1 = SW<G1>;
   using C2 = SW<G2>;
   static constexpr int K = PP::K;
-  struct Ws { FT f[K], g[K], xq[K], yq[K], ln[K], u[K], v[K]; };
+  struct Ws { FT f[K], g[K], xq[K], yq[K], ln[K], u[K], v[K], part[3 * K]; };
 
   __device__ __forceinline__ static FT mul_nu(const FT& x) {
     FT t = Fq::template mul_small<PP::NU_ABS>(x);
@@ -50,9 +50,15 @@ template <class G1, class G2, class PP> struct Pairing {
 #endif
   }
 
-  // out = a * b in Fq[w]/(w^K - nu)
-  __device__ __noinline__ static void kmul(int lane, FT* out, const FT* a, const FT* b) {
-    coop(lane, out, [&](int l) {
+  // out = a * b in Fq[w]/(w^K - nu).  The K^2 limb products are spread over all lanes: lane l = part * K + c
+  // (part < PARTS = 32 / K) sums the products a[i] * b[c - i] for i = part (mod PARTS); the partial sums meet in
+  // ws_part (shared memory) and lane c (part 0) adds them.  K = 12: 6 multiplications per lane instead of 12.
+  static constexpr int PARTS = (32 / K) < 1 ? 1 : (32 / K > 4 ? 4 : 32 / K);
+  __device__ __noinline__ static void kmul(int lane, FT* out, const FT* a, const FT* b, FT* part_buf) {
+#ifdef SSO_HOST_EMUL
+    (void)lane; (void)part_buf;
+    FT tmp[K];
+    for (int l = 0; l < K; l++) {
       FT lo = Fq::zero(), hi = Fq::zero();
       for (int i = 0; i < K; i++) {
         int j = l - i;
@@ -61,9 +67,34 @@ template <class G1, class G2, class PP> struct Pairing {
         FT pr = Fq::mul(a[i], b[j]);
         if (wrap) hi = Fq::add(hi, pr); else lo = Fq::add(lo, pr);
       }
-      return Fq::add(lo, mul_nu(hi));
-    });
+      tmp[l] = Fq::add(lo, mul_nu(hi));
+    }
+    for (int l = 0; l < K; l++) out[l] = tmp[l];
+#else
+    int part = lane / K, c = lane - part * K;
+    FT val = Fq::zero();
+    if (part < PARTS) {
+      FT lo = Fq::zero(), hi = Fq::zero();
+      for (int i = part; i < K; i += PARTS) {
+        int j = c - i;
+        bool wrap = j < 0;
+        if (wrap) j += K;
+        FT pr = Fq::mul(a[i], b[j]);
+        if (wrap) hi = Fq::add(hi, pr); else lo = Fq::add(lo, pr);
+      }
+      val = Fq::add(lo, mul_nu(hi));
+      if (part > 0) part_buf[(part - 1) * K + c] = val;
+    }
+    __syncwarp();
+    if (part == 0) {
+      for (int p = 1; p < PARTS; p++) val = Fq::add(val, part_buf[(p - 1) * K + c]);
+    }
+    __syncwarp();
+    if (part == 0) out[c] = val;
+    __syncwarp();
+#endif
   }
+  __device__ __forceinline__ static void kmul(int lane, Ws& ws, FT* out, const FT* a, const FT* b) { kmul(lane, out, a, b, ws.part); }
   // conjugation at `stride`: negate coefficients at odd multiples of stride
   __device__ __forceinline__ static void kconj(int lane, FT* out, const FT* a, int stride) {
     coop(lane, out, [&](int l) { return ((l / stride) & 1) ? Fq::neg(a[l]) : a[l]; });
@@ -86,8 +117,8 @@ template <class G1, class G2, class PP> struct Pairing {
     int stride = 1;
     while (((K / stride) & 1) == 0) {
       kconj(lane, tmp, cur, stride);
-      kmul(lane, acc, acc, tmp);
-      kmul(lane, cur, cur, tmp);
+      kmul(lane, ws, acc, acc, tmp);
+      kmul(lane, ws, cur, cur, tmp);
       stride *= 2;
     }
     int n = K / stride;
@@ -108,7 +139,7 @@ template <class G1, class G2, class PP> struct Pairing {
         return Fq::zero();
       });
     }
-    kmul(lane, out, acc, cur);
+    kmul(lane, ws, out, acc, cur);
   }
 
   // psi(Q): xq = embed(x') w^(2s), yq = embed(y') w^(3s)
@@ -129,8 +160,8 @@ template <class G1, class G2, class PP> struct Pairing {
     });
   }
 
-  // ws.f = t(P, Q) reduced Tate pairing; P, Q affine (Montgomery); identity inputs give 1
-  __device__ __noinline__ static void tate(int lane, Ws& ws, const typename C1::Affine& P, const typename C2::Affine& Q) {
+  // ws.f = f_{r,P}(psi(Q)) (Miller function, vertical lines dropped); P, Q affine (Montgomery); identity inputs give 1
+  __device__ __noinline__ static void miller(int lane, Ws& ws, const typename C1::Affine& P, const typename C2::Affine& Q) {
     kone(lane, ws.f);
     if (P.inf || Q.inf) return;
     untwist_coord(lane, ws.xq, Q.x, 2 * PP::TWIST_SIGN);
@@ -152,8 +183,8 @@ template <class G1, class G2, class PP> struct Pairing {
           return l == 0 ? Fq::add(v, Cc) : v;
         });
       }
-      kmul(lane, ws.f, ws.f, ws.f);
-      kmul(lane, ws.f, ws.f, ws.ln);
+      kmul(lane, ws, ws.f, ws.f, ws.f);
+      kmul(lane, ws, ws.f, ws.f, ws.ln);
       T = C1::dbl(T);
       if ((r[bit >> 5] >> (bit & 31)) & 1) {
         FT ZZ = Fq::sqr(T.Z);
@@ -167,31 +198,42 @@ template <class G1, class G2, class PP> struct Pairing {
             FT v = Fq::add(Fq::mul(N, ws.yq[l]), Fq::mul(B, ws.xq[l]));
             return l == 0 ? Fq::add(v, Cc) : v;
           });
-          kmul(lane, ws.f, ws.f, ws.ln);
+          kmul(lane, ws, ws.f, ws.f, ws.ln);
         }
         T = C1::madd(T, P);
       }
     }
-    // final exponentiation: (q^(k/2) - 1) then (q^(k/2) + 1) / r
+  }
+
+  // ws.f <- ws.f ^ ((q^k - 1) / r): (q^(k/2) - 1) by conjugation and one inversion, then (q^(k/2) + 1) / r
+  __device__ __noinline__ static void final_exp(int lane, Ws& ws) {
     kinv(lane, ws, ws.g, ws.f);                       // g = f^-1
     kconj(lane, ws.u, ws.f, 1);                       // u = f^(q^(k/2))
-    kmul(lane, ws.g, ws.g, ws.u);                     // g = f^(q^(k/2) - 1)
+    kmul(lane, ws, ws.g, ws.g, ws.u);                     // g = f^(q^(k/2) - 1)
     kone(lane, ws.f);
     const uint32_t* e = PP::hard();
     bool started = false;
     for (int i = PP::HARD_WORDS * 32 - 1; i >= 0; i--) {
-      if (started) kmul(lane, ws.f, ws.f, ws.f);
+      if (started) kmul(lane, ws, ws.f, ws.f, ws.f);
       if ((e[i >> 5] >> (i & 31)) & 1) {
-        if (started) kmul(lane, ws.f, ws.f, ws.g); else kcopy(lane, ws.f, ws.g);
+        if (started) kmul(lane, ws, ws.f, ws.f, ws.g); else kcopy(lane, ws.f, ws.g);
         started = true;
       }
     }
   }
 
+  // reduced Tate pairing t(P, Q)
+  __device__ __forceinline__ static void tate(int lane, Ws& ws, const typename C1::Affine& P, const typename C2::Affine& Q) {
+    miller(lane, ws, P, Q);
+    final_exp(lane, ws);
+  }
+
   // bytes of one check: a | b (G1 uncompressed) | c | d (G2 uncompressed)
   static constexpr int CHECK_BYTES = 2 * C1::SIZE_U + 2 * C2::SIZE_U;
 
-  // side 0 computes e(a, d), side 1 computes e(b, c).  Returns a deserialisation status (0 ok).
+  // same_ratio as ONE final exponentiation: e(a, d) == e(b, c)  <=>  (f_a(d) * f_{-b}(c)) ^ ((q^k-1)/r) == 1.
+  // side 0 leaves the Miller value f_{r,a}(d) in ws.f, side 1 leaves f_{r,-b}(c).  Returns a deserialisation
+  // status (0 ok).
   __device__ __forceinline__ static uint32_t run_side(int lane, Ws& ws, const uint8_t* check, int side) {
     typename C1::Affine P;
     typename C2::Affine Q;
@@ -199,8 +241,22 @@ template <class G1, class G2, class PP> struct Pairing {
     uint32_t s2 = C2::read_uncompressed(check + 2 * C1::SIZE_U + (side == 0 ? C2::SIZE_U : 0), Q);
     if (s1 != 0 || s2 != 0) return s1 ? s1 : s2;
     if (!C1::on_curve(P) || !C2::on_curve(Q)) return 3;
-    tate(lane, ws, P, Q);
+    if (side == 1 && !P.inf) P.y = Fq::neg(P.y);
+    miller(lane, ws, P, Q);
     return 0;
+  }
+  // after both sides: ws0.f <- (ws0.f * ws1.f)^((q^k-1)/r); true iff the result is 1
+  __device__ __forceinline__ static bool combine_and_check(int lane, Ws& ws0, const Ws& ws1) {
+    kmul(lane, ws0, ws0.f, ws0.f, ws1.f);
+    final_exp(lane, ws0);
+    bool ok = true;
+#ifdef SSO_HOST_EMUL
+    for (int l = 0; l < K; l++) ok = ok && Fq::eq(ws0.f[l], l == 0 ? Fq::one() : Fq::zero());
+#else
+    if (lane < K) ok = Fq::eq(ws0.f[lane], lane == 0 ? Fq::one() : Fq::zero());
+    ok = __all_sync(0xffffffffu, ok);
+#endif
+    return ok;
   }
 };
 

@@ -198,9 +198,7 @@ template <class G1, class G2, class PP> static void same_ratio_emul(const uint8_
     uint32_t s0 = PR::run_side(0, w0, checks + (size_t)i * PR::CHECK_BYTES, 0);
     uint32_t s1 = PR::run_side(0, w1, checks + (size_t)i * PR::CHECK_BYTES, 1);
     if (s0 || s1) { verdicts[i] = 0x100 + (s0 ? s0 : s1); continue; }
-    bool eq = true;
-    for (int l = 0; l < PR::K; l++) eq = eq && Fq::eq(w0.f[l], w1.f[l]);
-    verdicts[i] = eq ? 1 : 0;
+    verdicts[i] = PR::combine_and_check(0, w0, w1) ? 1 : 0;
   }
 }
 extern "C" int emul_same_ratio(uint32_t curve, const uint8_t* checks, uint32_t n, uint32_t* verdicts) {
