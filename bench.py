@@ -37,7 +37,11 @@ def macs_per_fq_mul(limbs: int) -> int:
     return 2 * limbs * limbs + limbs            # CIOS on L 32-bit limbs
 
 
-GLV_KBITS = {"bls12_377": 129, "bw6_761": 191}      # csrc/constants.cuh GLV_*::KBITS (half-size scalars)
+GLV_KBITS = {"bls12_377": 129, "bw6_761": 191}
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_batch_exp_chunk launch on the bench workload, from the committed
+# `ncu --set full` capture (profiles/r1_ncu_batch_exp_chunk_summary.csv): window tables and spills in local memory;
+# the algorithmic bytes are 31.5 MB in + 15.7 MB out + 38 MB of Jacobian intermediates
+NCU_DRAM_BYTES_PER_LAUNCH = {"bls12_377": 1.26e9}      # csrc/constants.cuh GLV_*::KBITS (half-size scalars)
 
 
 def declared_fq_muls_per_point(curve: str, group: int) -> float:
@@ -298,7 +302,8 @@ def main():
 
     limbs, _ = CURVE_BITS[args.curve]
     mac = macs_per_fq_mul(limbs)
-    peak = sso.imad_peak(0, dev)
+    peak = sso.imad_peak(0, dev)                 # independent mad.wide.u32 chains: the integer-MAC ceiling of the chip
+    peak_chain = sso.imad_peak(1, dev)           # mad.lo.cc/madc.hi.cc carry chains: what carry-propagating limbs can reach
     kernels = []
     n_g1 = sz["g1_count"] + 2 * sz["other_count"]
     n_g2 = sz["other_count"] + 1
@@ -334,8 +339,10 @@ def main():
         "gpu_launches": launches,
         "roofline": {"bound": "imad",
                      "kernel": dom["kernel"], "achieved": dom["achieved_tmacs"], "peak": peak / 1e12, "unit": "TMAC/s",
-                     "frac": dom["frac"], "traffic": None,
+                     "frac": dom["frac"], "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(args.curve),
                      "peak_source": "measured live: mad.wide.u32 probe kernel (sso_imad_peak variant 0)",
+                     "peak_carry_chain": peak_chain / 1e12, "frac_of_carry_chain_peak": (dom["frac"] * peak / peak_chain) if dom["frac"] else None,
+                     "traffic_source": "profiles/r1_ncu_batch_exp_chunk_summary.csv (dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
                      "macs_per_fq_mul": mac, "kernels": kernels},
         "clocks": sampler.summary(),
         "points_per_step": npts,

@@ -134,9 +134,11 @@ template <int n> __device__ __forceinline__ void madc_n_rshift(uint32_t* acc, co
   acc[n - 1] = madc_hi(a[n - 2], bi, 0);
 }
 
-// Note on instruction selection (measured, tools/mulbench): ptxas turns the a * b_i products of each row into
-// single IMAD.WIDE.U32.X instructions but always splits the m * p products of the reduction into IMAD.X +
-// IMAD.HI.U32.X pairs, whether the modulus sits in the constant bank, in uniform registers or in vector registers.
+// Note on instruction selection (measured, tools/mulbench + SASS): the Montgomery factor m = t * (-p^-1 mod 2^32)
+// must be computed with the constant read at RUN TIME (P::inv_rt(), constant bank).  For p = 1 (mod 2^32) — the
+// 377-bit and 253-bit primes — the compile-time constant is 0xffffffff; ptxas then rewrites m as a negation and
+// emits every m * p product of the reduction as an IMAD.X + IMAD.HI.U32.X pair instead of one IMAD.WIDE.U32.X
+// (+120 integer-pipe instructions per 12-limb multiplication).
 template <class P> __device__ __forceinline__ void load_modulus(uint32_t* mod) {
 #pragma unroll
   for (int i = 0; i < P::L; i++) mod[i] = P::p()[i];
@@ -156,7 +158,7 @@ template <class P> __device__ __forceinline__ void mad_n_redc(uint32_t* E, uint3
     cmad_n<n>(E, a, bi);
     O[n - 1] = addc(O[n - 1], 0);
   }
-  uint32_t mi = E[0] * P::INV;
+  uint32_t mi = E[0] * P::inv_rt();
   cmad_n<n>(O, MOD + 1, mi);
   cmad_n<n>(E, MOD, mi);
   O[n - 1] = addc(O[n - 1], 0);
