@@ -8,8 +8,9 @@ single B200: BLS12-377, 2^20 powers, chunk size 2^16 (262 145 points: 196 608 G1
 synthetic accumulator (a previous contribution applied to the all-generator accumulator).
 
   value      points/s with the chunk already resident in HBM (sso_p1_contribute_dev), CUDA events
-  e2e        points/s through the reference-facing host-buffer call (sso_p1_contribute_buf): H2D of
-             the 31 MB challenge, compute, Blake2b hash-chain link, D2H of the 15 MB response
+  e2e        points/s through the reference-facing host-buffer call with K chunks in flight
+             (sso_p1_contribute_many_buf): per chunk H2D of the 31 MB challenge, compute, Blake2b hash-chain
+             link, D2H of the 15 MB response; e2e.single_call = one chunk per call (sso_p1_contribute_buf)
   roofline   integer-pipe roofline of the dominant kernel (declared multiply-accumulates / event time
              / measured mad.wide.u32 peak), plus the per-kernel breakdown
   cpu_baseline  the oracle's C++ restatement of the reference algorithm on the host cores (bounded sample)
@@ -266,10 +267,34 @@ def main():
     sso.profile_enable(False)
     prof = sso.profile_read()
     # ---- end-to-end timing through the host-buffer entry point
+    # (a) one chunk per call: the latency of a single reference-facing call (hash of the 31 MB challenge on one core inside)
     run_steps(step_e2e, 1, False)
     barrier()
-    ms_e2e_total = run_steps(step_e2e, args.steps, True)
+    ms_e2e_single_total = run_steps(step_e2e, args.steps, True)
     barrier()
+    # (b) the headline: the same K steps with several chunks in flight (sso_p1_contribute_many_buf, the reference's
+    # Process lane): every step still copies its own challenge from pinned host memory and reads its own response back
+    n_resp = min(args.steps, 64)
+    h_resps = [torch.empty(contrib, dtype=torch.uint8).pin_memory() for _ in range(n_resp)]
+
+    def many(n):
+        done = 0
+        while done < n:
+            k = min(n_resp, n - done)
+            sso.contribute_many_buf([p] * k, [h_ch] * k, h_resps[:k], *mine, pubkey=pubkey, check=sso.CHECK_NONZERO, device=dev)
+            done += k
+
+    many(min(3, args.steps))
+    flush.zero_()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    many(args.steps)
+    e1.record()
+    e1.synchronize()
+    ms_e2e_total = e0.elapsed_time(e1)
+    barrier()
+    e2e_same = all(torch.equal(h_resps[i], h_resp) for i in range(n_resp))
     sampler.stop_flag = True
     if sampler.is_alive():
         sampler.join(timeout=2)
@@ -290,11 +315,12 @@ def main():
                   "what": "sso_p1_verify_chunk_buf: hash chain, PoK pairings, decompress + direct subgroup checks of %d points, "
                           "RLC power-ratio MSMs, same_ratio pairings; host buffers" % npts}
 
-    t = torch.tensor([ms_total, ms_e2e_total], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms_total, ms_e2e_total, ms_e2e_single_total], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = t[0].item() / args.steps
     ms_e2e = t[1].item() / args.steps
+    ms_e2e_single = t[2].item() / args.steps
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -335,7 +361,11 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (Montgomery, integer pipe)", "data": "synthetic",
         "config": config,
         "e2e": {"value": world * npts / (ms_e2e * 1e-3), "unit": "points/s", "h2d_bytes_per_step": acc,
-                "d2h_bytes_per_step": contrib - 64 - sz["public_key_size"], "ms_per_step": ms_e2e},
+                "d2h_bytes_per_step": contrib - 64 - sz["public_key_size"], "ms_per_step": ms_e2e,
+                "call": "sso_p1_contribute_many_buf: K chunks from pinned host buffers, 3 host workers, each chunk = H2D + kernels + "
+                        "Blake2b(challenge) + D2H; responses identical to the single-chunk call: %s" % e2e_same,
+                "single_call": {"value": world * npts / (ms_e2e_single * 1e-3), "ms_per_step": ms_e2e_single,
+                                "call": "sso_p1_contribute_buf, one chunk per call (Blake2b of the challenge on one host core is the floor)"}},
         "gpu_launches": launches,
         "roofline": {"bound": "imad",
                      "kernel": dom["kernel"], "achieved": dom["achieved_tmacs"], "peak": peak / 1e12, "unit": "TMAC/s",

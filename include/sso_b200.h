@@ -142,6 +142,18 @@ int32_t sso_p1_contribute_buf(const sso_p1_params_t* p, const uint8_t* challenge
                               const uint8_t* beta, const uint8_t* pubkey, size_t pubkey_len, uint32_t check_input,
                               int device, char* err, size_t errcap);
 
+/* sso_p1_contribute_buf over several chunks in flight, as the reference's Process lane holds several chunks
+ * (src/bin/contribute.rs:64-71, 158-163: --max-in-process-lane; chunks are independent, :1132-1139).
+ * params[i], challenges[i], responses[i] describe chunk i; the same scalars and public key are applied to all.
+ * host_threads workers (0 = default 3) each run one chunk at a time on their own CUDA streams: the sequential
+ * Blake2b of one chunk overlaps the copies and kernels of the others.  Results are byte-identical to n_chunks
+ * separate sso_p1_contribute_buf calls.  On failure the first error is returned and no further chunks start. */
+int32_t sso_p1_contribute_many_buf(const sso_p1_params_t* params, size_t n_chunks, const uint8_t* const* challenges,
+                                   const size_t* challenge_lens, uint8_t* const* responses, const size_t* response_lens,
+                                   const uint8_t* tau, const uint8_t* alpha, const uint8_t* beta, const uint8_t* pubkey,
+                                   size_t pubkey_len, uint32_t check_input, uint32_t host_threads, int device, char* err,
+                                   size_t errcap);
+
 /* phase1_cli::new_challenge (reference src/bin/new_setup.rs:105-109, src/bin/verify_transcript.rs:322-326):
  * the initial accumulator — every element is the group generator, hash slot = Blake2b-512 of the empty
  * string.  d_challenge: accumulator_size bytes on the device.  NOTE: for MNT4-753 / MNT6-753 G2 the

@@ -40,6 +40,7 @@ __device__ __forceinline__ uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c
 __device__ __forceinline__ uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 __device__ __forceinline__ uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 __device__ __forceinline__ uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ uint32_t shl1_from(uint32_t lo, uint32_t hi) { return __funnelshift_l(lo, hi, 1); }   // (hi:lo << 1) >> 32
 #else
 // TEST-ONLY instruction-level emulation of the PTX carry flag so that the device algorithms can be
 // exercised by g++ in this GPU-less container (tests/emul/).  Never part of the product library.
@@ -59,6 +60,7 @@ static inline uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return em
 static inline uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return emu_add(mul_lo(a, b), c, g_cf, true); }
 static inline uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return emu_add(mul_hi(a, b), c, g_cf, true); }
 static inline uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return emu_add(mul_hi(a, b), c, g_cf, false); }
+static inline uint32_t shl1_from(uint32_t lo, uint32_t hi) { return (hi << 1) | (lo >> 31); }
 #endif
 
 // ---------------------------------------------------------------------------------------------
@@ -187,6 +189,95 @@ template <class P> __device__ __forceinline__ void mont_mul(uint32_t* r, const u
 }
 
 // ---------------------------------------------------------------------------------------------
+// Dedicated squaring: the n(n-1)/2 off-diagonal products once, doubled by a funnel shift, plus the n squares on
+// the diagonal, then a Montgomery reduction of the 2n-limb result: n(n+1)/2 + n^2 + n multiply-accumulates
+// instead of 2n^2 + n (234 / 300 for 12 limbs, 900 / 1176 for 24).
+// ---------------------------------------------------------------------------------------------
+// one row of off-diagonal products a[i] * a[j], j = j0, j0+2, ... accumulated at limb positions i+j (lo), i+j+1 (hi)
+// of acc; the pairs of one row are contiguous, so the carry rides the chain and is deposited in the limb above the
+// row (which no product of this or an earlier row has reached: it holds at most earlier deposits)
+template <int n, int i, int j0> __device__ __forceinline__ void sqr_row(uint32_t* acc, const uint32_t* a) {
+  if constexpr (j0 < n) {
+    acc[i + j0] = mad_lo_cc(a[i], a[j0], acc[i + j0]);
+    acc[i + j0 + 1] = madc_hi_cc(a[i], a[j0], acc[i + j0 + 1]);
+    constexpr int last = j0 + 2 * ((n - 1 - j0) / 2);
+#pragma unroll
+    for (int j = j0 + 2; j < n; j += 2) {
+      acc[i + j] = madc_lo_cc(a[i], a[j], acc[i + j]);
+      acc[i + j + 1] = madc_hi_cc(a[i], a[j], acc[i + j + 1]);
+    }
+    acc[i + last + 2] = addc(acc[i + last + 2], 0);
+  }
+}
+template <int n, int i> __device__ __forceinline__ void sqr_rows(uint32_t* ev, uint32_t* od, const uint32_t* a) {
+  if constexpr (i < n - 1) {
+    sqr_row<n, i, i + 1>(od, a);                    // i + j odd: register pairs (odd, even) of od
+    sqr_row<n, i, i + 2>(ev, a);                    // i + j even: register pairs (even, odd) of ev
+    sqr_rows<n, i + 1>(ev, od, a);
+  }
+}
+// w[0..2n) = a^2
+template <int n> __device__ __forceinline__ void sqr_wide(uint32_t* w, const uint32_t* a) {
+  uint32_t ev[2 * n], od[2 * n];
+#pragma unroll
+  for (int k = 0; k < 2 * n; k++) { ev[k] = 0; od[k] = 0; }
+  sqr_rows<n, 0>(ev, od, a);
+  // s = ev + od (limb 0 is empty: the lowest off-diagonal product sits at limb 1)
+  ev[1] = add_cc(ev[1], od[1]);
+#pragma unroll
+  for (int k = 2; k < 2 * n - 1; k++) ev[k] = addc_cc(ev[k], od[k]);
+  ev[2 * n - 1] = addc(ev[2 * n - 1], od[2 * n - 1]);
+  // w = 2 s + sum a[i]^2 2^(64 i)
+  w[0] = mad_lo_cc(a[0], a[0], 0);
+  w[1] = madc_hi_cc(a[0], a[0], ev[1] << 1);
+#pragma unroll
+  for (int i = 1; i < n; i++) {
+    w[2 * i] = madc_lo_cc(a[i], a[i], shl1_from(ev[2 * i - 1], ev[2 * i]));
+    w[2 * i + 1] = i == n - 1 ? madc_hi(a[i], a[i], shl1_from(ev[2 * i], ev[2 * i + 1]))
+                              : madc_hi_cc(a[i], a[i], shl1_from(ev[2 * i], ev[2 * i + 1]));
+  }
+}
+// One reduction step: T <- (T + m p) / 2^32 with m = -T p^-1 mod 2^32, T = E + O 2^32 as in mad_n_redc
+template <class P> __device__ __forceinline__ void redc_step(uint32_t* E, uint32_t* O, bool first, const uint32_t* MOD) {
+  constexpr int n = P::L;
+  if (first) {
+    uint32_t mi = E[0] * P::inv_rt();
+    mul_n<n>(O, MOD + 1, mi);
+    cmad_n<n>(E, MOD, mi);
+    O[n - 1] = addc(O[n - 1], 0);
+  } else {
+    uint32_t mi = (E[0] + O[1]) * P::inv_rt();
+    E[0] = add_cc(E[0], O[1]);
+    madc_n_rshift<n>(O, MOD + 1, mi);
+    cmad_n<n>(E, MOD, mi);
+    O[n - 1] = addc(O[n - 1], 0);
+  }
+}
+// r = a^2 R^-1 mod p, input and output fully reduced
+template <class P> __device__ __forceinline__ void mont_sqr(uint32_t* r, const uint32_t* a) {
+  constexpr int n = P::L;
+  uint32_t w[2 * n], odd[n], mod[n];
+  sqr_wide<n>(w, a);
+  load_modulus<P>(mod);
+  uint32_t* even = w;                                // the low half is the window the reduction works on
+#pragma unroll
+  for (int i = 0; i < n; i += 2) {
+    redc_step<P>(even, odd, i == 0, mod);
+    redc_step<P>(odd, even, false, mod);
+  }
+  even[0] = add_cc(even[0], odd[1]);
+#pragma unroll
+  for (int k = 1; k < n - 1; k++) even[k] = addc_cc(even[k], odd[k + 1]);
+  even[n - 1] = addc(even[n - 1], 0);
+  // + the untouched high half of a^2: (a^2 + M p) / R = REDC(low half) + high half < 2p
+  limbs_add<n>(even, even, w + n);
+  uint32_t t[n];
+  uint32_t borrow = limbs_sub<n>(t, even, mod);
+#pragma unroll
+  for (int k = 0; k < n; k++) r[k] = borrow ? even[k] : t[k];
+}
+
+// ---------------------------------------------------------------------------------------------
 // Field wrapper: elements are structs of L limbs in Montgomery form
 // ---------------------------------------------------------------------------------------------
 template <class P_> struct Fp {
@@ -241,7 +332,14 @@ template <class P_> struct Fp {
   __device__ __forceinline__ static T mul(const T& a, const T& b) {
     if constexpr (L > SSO_INLINE_MUL_MAX_L) { return mul_outlined(a, b); } else { T r; mont_mul<P>(r.v, a.v, b.v); return r; }
   }
+#ifndef SSO_NO_DEDICATED_SQR
+  __device__ __noinline__ static T sqr_outlined(T a) { T r; mont_sqr<P>(r.v, a.v); return r; }
+  __device__ __forceinline__ static T sqr(const T& a) {
+    if constexpr (L > SSO_INLINE_MUL_MAX_L) { return sqr_outlined(a); } else { T r; mont_sqr<P>(r.v, a.v); return r; }
+  }
+#else
   __device__ __forceinline__ static T sqr(const T& a) { return mul(a, a); }
+#endif
   // always-inlined multiplication, for callers that want independent multiplications interleaved by the scheduler
   __device__ __forceinline__ static T mul_inl(const T& a, const T& b) { T r; mont_mul<P>(r.v, a.v, b.v); return r; }
   // multiply by a small non-negative integer constant

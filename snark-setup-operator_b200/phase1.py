@@ -147,6 +147,39 @@ def contribute_buf(params: Phase1Parameters, challenge, response, tau: int, alph
     return response
 
 
+def contribute_many_buf(params_list, challenges, responses, tau: int, alpha: int, beta: int, pubkey: bytes | None = None,
+                        check=CHECK_NONZERO, host_threads=0, device=0):
+    """contribute_buf over several chunks in flight (the reference's Process lane, src/bin/contribute.rs:64-71,158-163):
+    `host_threads` workers (0 = library default) each run one chunk at a time, so one chunk's Blake2b overlaps the
+    copies and kernels of the others.  params_list[i] / challenges[i] / responses[i] describe chunk i."""
+    n = len(params_list)
+    if not (len(challenges) == len(responses) == n):
+        raise SsoError(-1, "params, challenges and responses must have the same length")
+    if n == 0:
+        return responses
+    c = params_list[0].curve
+    P = (_lib.P1Params * n)(*[p.c_struct() for p in params_list])
+    keep, ch, rs = [], [], []
+    for a, b in zip(challenges, responses):
+        pa, la, ka = _host_ptr(a)
+        pb, lb, kb = _host_ptr(b)
+        keep += [ka, kb]
+        ch.append((pa, la))
+        rs.append((pb, lb))
+
+    def addr(x):
+        return x if isinstance(x, int) else ctypes.cast(x, ctypes.c_void_p).value
+
+    ch_p = (ctypes.c_void_p * n)(*[addr(x[0]) for x in ch])
+    ch_l = (ctypes.c_size_t * n)(*[x[1] for x in ch])
+    rs_p = (ctypes.c_void_p * n)(*[addr(x[0]) for x in rs])
+    rs_l = (ctypes.c_size_t * n)(*[x[1] for x in rs])
+    call("sso_p1_contribute_many_buf", P, n, ch_p, ch_l, rs_p, rs_l, scalar_bytes(c, tau), scalar_bytes(c, alpha),
+         scalar_bytes(c, beta), pubkey, 0 if pubkey is None else len(pubkey), check, host_threads, device)
+    del keep
+    return responses
+
+
 def new_challenge_dev(params: Phase1Parameters, d_challenge, device=0):
     """phase1_cli::new_challenge on a device buffer (all-generator accumulator, blank hash)."""
     assert d_challenge.numel() == params.accumulator_size

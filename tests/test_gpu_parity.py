@@ -89,6 +89,27 @@ def test_contribute_matches_golden_chunks(name, k, golden_dir):
     assert bytes(resp) == want                          # includes the Blake2b hash-chain link in [0, 64)
 
 
+def test_contribute_many_chunks_in_flight_matches_golden(golden_dir):
+    """sso_p1_contribute_many_buf (several chunks in flight on host worker threads) = the single-chunk call per chunk."""
+    name = "bls12_377"
+    key = synth.contributor_key(get_curve(name))
+    order = [0, 3, 3, 0, 3, 0, 0]
+    params = [sso.Phase1Parameters.new_chunk(name, k, 4, 3, 4) for k in order]
+    chs = [open(os.path.join(golden_dir, "p1_%s_c%d.challenge.bin" % (name, k)), "rb").read() for k in order]
+    wants = [open(os.path.join(golden_dir, "p1_%s_c%d.response.bin" % (name, k)), "rb").read() for k in order]
+    resps = [bytearray(p.contribution_size) for p in params]
+    sso.contribute_many_buf(params, chs, resps, key.tau, key.alpha, key.beta, pubkey=bytes(params[0].sizes()["public_key_size"]),
+                            check=sso.CHECK_NONZERO, host_threads=3)
+    assert [bytes(r) for r in resps] == wants
+    # an invalid chunk in the batch surfaces as that chunk's error
+    bad = chs[2][:-1]                                    # wrong length
+    with pytest.raises(sso.SsoError) as e:
+        sso.contribute_many_buf(params, chs[:2] + [bytes(bad)] + chs[3:], resps, key.tau, key.alpha, key.beta,
+                                pubkey=bytes(params[0].sizes()["public_key_size"]), check=sso.CHECK_NONZERO, host_threads=2)
+    assert "chunk 2 of the batch" in str(e.value)
+    sso.contribute_many_buf([], [], [], 1, 2, 3)
+
+
 def test_reencode_rejects_bad_points():
     c = get_curve("bls12_377")
     G = c.g1
