@@ -45,33 +45,62 @@ GLV_KBITS = {"bls12_377": 129, "bw6_761": 191}
 NCU_DRAM_BYTES_PER_LAUNCH = {"bls12_377": 1.26e9}      # csrc/constants.cuh GLV_*::KBITS (half-size scalars)
 
 
-def declared_fq_muls_per_point(curve: str, group: int) -> float:
-    """Closed-form field-multiplication count of the batch_exp kernel per point, S = M:
+def declared_work_per_point(curve: str, group: int):
+    """Closed-form count of base-field multiplications and squarings (m, s) of the batch_exp kernel per point:
       read the point into Montgomery form            2 deg
       window table 1P..8P                            4 dbl + 3 madd
       affine table (all groups but MNT6 G2)          6 F-mul (Z products) + 13 F-mul + 7 (1 S + 3 M) (normalisation)
                                                      + 3 F-mul (share of the per-block inversion tree)
       window loop, signed 4-bit digits               4 (NW - 1) dbl + additions on 15/16 of the windows:
          plain ladder (MNT4/6)   NW = ceil((bits+2)/4)   one addition per window
-         GLV (BLS12-377, BW6)    NW = ceil((KBITS+2)/4)  two additions per window + one multiplication by beta (deg Fq-muls)
+         GLV (BLS12-377 G1, BW6) NW = ceil((KBITS+2)/4)  two additions per window + one multiplication by beta (deg Fq-muls)
+         4-way psi decomposition (BLS12-377 G2)  NW = 17  four additions per window + (4 + 2 + 2) Fq-muls for psi, psi^2, psi^3
       additions are mixed (madd) with the affine table, full Jacobian additions otherwise.
-    Fq2: mul = 3, sqr = 2 base multiplications; Fq3: mul = sqr = 6."""
+    Base-field cost of an extension operation: Fq2 mul = 3 M, Fq2 sqr = 2 M (complex squaring); Fq3 mul = sqr = 6 M;
+    only prime-field squarings use the dedicated squaring (fewer multiply-accumulates, macs_per_fq_sqr)."""
     _, bits = CURVE_BITS[curve]
     deg = G2_DEG[curve] if group == 1 else 1
-    M, S = {1: (1, 1), 2: (3, 2), 3: (6, 6)}[deg]
-    dbl = 2 * M + 5 * S if A_ZERO[curve] else 1 * M + 8 * S
-    madd = 7 * M + 4 * S
-    add = 11 * M + 5 * S
+    M, S = {1: ((1, 0), (0, 1)), 2: ((3, 0), (2, 0)), 3: ((6, 0), (6, 0))}[deg]
+
+    def comb(*terms):
+        m = sum(k * t[0] for k, t in terms)
+        sq = sum(k * t[1] for k, t in terms)
+        return (m, sq)
+
+    dbl = comb((2, M), (5, S)) if A_ZERO[curve] else comb((1, M), (8, S))
+    madd = comb((7, M), (4, S))
+    add = comb((11, M), (5, S))
+    base = (1, 0)
     affine = not (curve == "mnt6_753" and group == 1)
-    work = 2 * deg + 4 * dbl + 3 * madd
+    terms = [(2 * deg, base), (4, dbl), (3, madd)]
     if affine:
-        work += (6 + 13 + 21 + 3) * M + 7 * S
+        terms += [(6 + 13 + 21 + 3, M), (7, S)]
     step = madd if affine else add
-    if curve in GLV_KBITS:
+    if curve == "bls12_377" and group == 1:
+        nw = 17
+        terms += [(4 * (nw - 1), dbl), (4 * nw * 15.0 / 16.0, step), (nw * (15.0 / 16.0) * 8, base)]
+    elif curve in GLV_KBITS:
         nw = (GLV_KBITS[curve] + 2 + 3) // 4
-        return work + 4 * (nw - 1) * dbl + 2 * nw * (15.0 / 16.0) * step + nw * (15.0 / 16.0) * deg
-    nw = (bits + 2 + 3) // 4
-    return work + 4 * (nw - 1) * dbl + nw * (15.0 / 16.0) * step
+        terms += [(4 * (nw - 1), dbl), (2 * nw * 15.0 / 16.0, step), (nw * (15.0 / 16.0) * deg, base)]
+    else:
+        nw = (bits + 2 + 3) // 4
+        terms += [(4 * (nw - 1), dbl), (nw * 15.0 / 16.0, step)]
+    return comb(*terms)
+
+
+def macs_per_fq_sqr(limbs: int) -> int:
+    return limbs * (limbs + 1) // 2 + limbs * limbs + limbs      # csrc/fp.cuh::mont_sqr
+
+
+def declared_fq_muls_per_point(curve: str, group: int) -> float:
+    m, sq = declared_work_per_point(curve, group)
+    return m + sq
+
+
+def declared_macs_per_point(curve: str, group: int) -> float:
+    limbs, _ = CURVE_BITS[curve]
+    m, sq = declared_work_per_point(curve, group)
+    return m * macs_per_fq_mul(limbs) + sq * macs_per_fq_sqr(limbs)
 
 
 class ClockSampler(threading.Thread):
@@ -336,7 +365,7 @@ def main():
     fm1, fm2 = declared_fq_muls_per_point(args.curve, 0), declared_fq_muls_per_point(args.curve, 1)
     k = prof["batch_exp_chunk"]
     if k["launches"] and k["ms"] > 0:
-        macs = k["launches"] * (n_g1 * fm1 + n_g2 * fm2) * mac          # both groups run in the one launch
+        macs = k["launches"] * (n_g1 * declared_macs_per_point(args.curve, 0) + n_g2 * declared_macs_per_point(args.curve, 1))   # both groups run in the one launch
         achieved = macs / (k["ms"] * 1e-3)
         kernels.append({"kernel": "k_batch_exp_chunk", "launches": k["launches"], "ms_total": round(k["ms"], 3),
                         "points": k["elems"], "fq_muls_per_point": {"g1": round(fm1, 1), "g2": round(fm2, 1)},
@@ -345,7 +374,7 @@ def main():
         k = prof[kind]
         if k["launches"] and k["ms"] > 0:
             fm = declared_fq_muls_per_point(args.curve, grp)
-            achieved = k["elems"] * fm * mac / (k["ms"] * 1e-3)
+            achieved = k["elems"] * declared_macs_per_point(args.curve, grp) / (k["ms"] * 1e-3)
             kernels.append({"kernel": "k_" + kind, "launches": k["launches"], "ms_total": round(k["ms"], 3),
                             "points": k["elems"], "fq_muls_per_point": round(fm, 1), "achieved_tmacs": achieved / 1e12,
                             "frac": achieved / peak})
@@ -373,7 +402,7 @@ def main():
                      "peak_source": "measured live: mad.wide.u32 probe kernel (sso_imad_peak variant 0)",
                      "peak_carry_chain": peak_chain / 1e12, "frac_of_carry_chain_peak": (dom["frac"] * peak / peak_chain) if dom["frac"] else None,
                      "traffic_source": "profiles/r1_ncu_batch_exp_chunk_summary.csv (dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
-                     "macs_per_fq_mul": mac, "kernels": kernels},
+                     "macs_per_fq_mul": mac, "macs_per_fq_sqr": macs_per_fq_sqr(limbs), "kernels": kernels},
         "clocks": sampler.summary(),
         "points_per_step": npts,
         "verify": verify,

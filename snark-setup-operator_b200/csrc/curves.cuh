@@ -33,6 +33,9 @@ struct Bls12_377_G1 {
   static constexpr bool AFFINE_TABLE = true;
   static constexpr bool HAS_GLV = true;
   using Glv = GLV_bls12_377_g1;
+  static constexpr int ENDO_SUBGROUP_TEST = 1;          // phi(P) = [-x^2]P  (ec.cuh::in_subgroup)
+  static constexpr bool HAS_GLS4 = false;
+  using Endo = ENDO_bls12_377;
   static constexpr uint32_t GROUP = 0;
   SSO_GROUP_COMMON(bls12_377_g1, Fq377, Fr253)
   static constexpr bool A_IS_ZERO = true;
@@ -43,6 +46,9 @@ struct Bls12_377_G2 {
   static constexpr bool AFFINE_TABLE = true;
   static constexpr bool HAS_GLV = true;
   using Glv = GLV_bls12_377_g2;
+  static constexpr int ENDO_SUBGROUP_TEST = 2;          // psi(P) = [x]P
+  static constexpr bool HAS_GLS4 = true;                // batch_exp: k = k0 + k1 x + k2 x^2 + k3 x^3 with psi (ec.cuh)
+  using Endo = ENDO_bls12_377;
   static constexpr uint32_t GROUP = 1;
   SSO_GROUP_COMMON(bls12_377_g2, Fq377x2, Fr253)
   static constexpr bool A_IS_ZERO = true;
@@ -53,6 +59,8 @@ struct Bw6_761_G1 {
   static constexpr bool AFFINE_TABLE = true;
   static constexpr bool HAS_GLV = true;
   using Glv = GLV_bw6_761_g1;
+  static constexpr int ENDO_SUBGROUP_TEST = 0;
+  static constexpr bool HAS_GLS4 = false;
   static constexpr uint32_t GROUP = 0;
   SSO_GROUP_COMMON(bw6_761_g1, Fq761, Fq377)
   static constexpr bool A_IS_ZERO = true;
@@ -63,6 +71,8 @@ struct Bw6_761_G2 {
   static constexpr bool AFFINE_TABLE = true;
   static constexpr bool HAS_GLV = true;
   using Glv = GLV_bw6_761_g2;
+  static constexpr int ENDO_SUBGROUP_TEST = 0;
+  static constexpr bool HAS_GLS4 = false;
   static constexpr uint32_t GROUP = 1;
   SSO_GROUP_COMMON(bw6_761_g2, Fq761, Fq377)
   static constexpr bool A_IS_ZERO = true;
@@ -72,6 +82,8 @@ struct Bw6_761_G2 {
 struct Mnt4_753_G1 {
   static constexpr bool AFFINE_TABLE = true;
   static constexpr bool HAS_GLV = false;
+  static constexpr int ENDO_SUBGROUP_TEST = 0;
+  static constexpr bool HAS_GLS4 = false;
   static constexpr uint32_t GROUP = 0;                                         // a = 2
   SSO_GROUP_COMMON(mnt4_753_g1, Fq4, Fq6)
   static constexpr bool A_IS_ZERO = false;
@@ -81,6 +93,8 @@ struct Mnt4_753_G1 {
 struct Mnt4_753_G2 {
   static constexpr bool AFFINE_TABLE = true;
   static constexpr bool HAS_GLV = false;
+  static constexpr int ENDO_SUBGROUP_TEST = 0;
+  static constexpr bool HAS_GLS4 = false;
   static constexpr uint32_t GROUP = 1;                                         // a' = (26, 0)
   SSO_GROUP_COMMON(mnt4_753_g2, Fq4x2, Fq6)
   static constexpr bool A_IS_ZERO = false;
@@ -90,6 +104,8 @@ struct Mnt4_753_G2 {
 struct Mnt6_753_G1 {
   static constexpr bool AFFINE_TABLE = true;
   static constexpr bool HAS_GLV = false;
+  static constexpr int ENDO_SUBGROUP_TEST = 0;
+  static constexpr bool HAS_GLS4 = false;
   static constexpr uint32_t GROUP = 0;                                         // a = 11
   SSO_GROUP_COMMON(mnt6_753_g1, Fq6, Fq4)
   static constexpr bool A_IS_ZERO = false;
@@ -99,6 +115,8 @@ struct Mnt6_753_G1 {
 struct Mnt6_753_G2 {
   static constexpr bool AFFINE_TABLE = false;   // measured: the 72 KB Fq3 inversion tree costs more than mixed additions save
   static constexpr bool HAS_GLV = false;
+  static constexpr int ENDO_SUBGROUP_TEST = 0;
+  static constexpr bool HAS_GLS4 = false;
   static constexpr uint32_t GROUP = 1;                                         // a' = (0, 0, 11) = 11 u^2, u^3 = 11
   SSO_GROUP_COMMON(mnt6_753_g2, Fq6x3, Fq4)
   static constexpr bool A_IS_ZERO = false;

@@ -375,6 +375,83 @@ template <class Cfg> struct SW {
     return acc;
   }
 
+  // ---- 4-way decomposition on BLS12 G2 (Galbraith-Scott): psi = twist^-1 . Frobenius . twist acts on G2 as
+  // multiplication by the curve parameter x (64 bits; r = x^4 - x^2 + 1 < x^4), so with k = k0 + k1 x + k2 x^2 + k3 x^3
+  // (plain base-x digits, 0 <= ki < x)   [k]P = [k0]P + [k1]psi(P) + [k2]psi^2(P) + [k3]psi^3(P):
+  // a quarter of the doublings of the plain ladder, half of the 2-way GLV's.  The images of the table entries
+  // are formed at addition time: psi costs 4 Fq multiplications, psi^2 and psi^3 two each
+  // (constants and their identities: tools/gen_constants.py::bls12_endo_block).
+  template <int NW_> struct Staged4 {
+    static constexpr int NW = NW_;
+    static constexpr int BL = (4 * NW + 31) / 32;
+    Jac tab[8];
+    uint32_t kb[4][BL];
+    bool active, affine;
+  };
+  // base-x digits of a canonical scalar of KL words (KL <= 8), each as two 32-bit words
+  template <int KL>
+  __device__ __forceinline__ static void gls4_split(const uint32_t* k, uint32_t kd[4][2]) {
+    constexpr unsigned long long X = Cfg::Endo::X;
+    unsigned long long n[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) n[i] = (2 * i < KL ? (unsigned long long)k[2 * i] : 0ull) | (2 * i + 1 < KL ? (unsigned long long)k[2 * i + 1] << 32 : 0ull);
+#pragma unroll 1
+    for (int d = 0; d < 4; d++) {
+      unsigned long long rem = 0;
+#pragma unroll 1
+      for (int i = 3; i >= 0; i--) {              // n = n / X, rem = n mod X   (rem < X: every partial quotient fits 64 bits)
+        unsigned __int128 cur = ((unsigned __int128)rem << 64) | n[i];
+        n[i] = (unsigned long long)(cur / X);
+        rem = (unsigned long long)(cur % X);
+      }
+      kd[d][0] = (uint32_t)rem;
+      kd[d][1] = (uint32_t)(rem >> 32);
+    }
+  }
+  // acc + sign * psi^j(table entry)
+  template <class ST>
+  __device__ __forceinline__ static Jac staged_add4(const ST& st, const Jac& acc, int dgt, int j) {
+    using B = typename F::Base;
+    using E = typename Cfg::Endo;
+    int idx = (dgt < 0 ? -dgt : dgt) - 1;
+    bool flip = dgt < 0;
+    Jac q = st.tab[idx];
+    if (j == 1) {
+      q.X = F::mul_base(F::conj(q.X), B::from_const(E::psi_cx()));
+      q.Y = F::mul_base(F::conj(q.Y), B::from_const(E::psi_cy()));
+      q.Z = F::conj(q.Z);
+    } else if (j == 2) {
+      q.X = F::mul_base(q.X, B::from_const(E::psi_omega()));
+      flip = !flip;
+    } else if (j == 3) {
+      q.X = F::neg(F::conj(q.X));
+      q.Y = F::mul_base(F::conj(q.Y), B::from_const(E::psi_cy()));
+      q.Z = F::conj(q.Z);
+      flip = !flip;
+    }
+    if (flip) q.Y = F::neg(q.Y);
+    if (st.affine) return madd(acc, Affine{q.X, q.Y, false});
+    return add(acc, q);
+  }
+  template <class ST>
+  __device__ __forceinline__ static Jac staged_loop4(const ST& st) {
+    Jac acc = identity();
+    if (!st.active) return acc;
+#pragma unroll 1
+    for (int w = ST::NW - 1; w >= 0; w--) {
+      if (w != ST::NW - 1) {
+#pragma unroll 1
+        for (int d = 0; d < 4; d++) acc = dbl(acc);
+      }
+#pragma unroll 1
+      for (int j = 0; j < 4; j++) {
+        int dg = digit(st.kb[j], w);
+        if (dg != 0) acc = staged_add4(st, acc, dg, j);
+      }
+    }
+    return acc;
+  }
+
   // plain MSB-first double-and-add for a constant-memory exponent (subgroup checks, cofactors)
   __device__ __noinline__ static Jac mul_const(const Affine& base, const uint32_t* e, int nwords) {
     Jac acc = identity();
@@ -383,6 +460,36 @@ template <class Cfg> struct SW {
       if ((e[i >> 5] >> (i & 31)) & 1) acc = madd(acc, base);
     }
     return acc;
+  }
+
+  // q == t for a Jacobian q and an affine t != O
+  __device__ __forceinline__ static bool jac_eq_affine(const Jac& q, const Affine& t) {
+    if (is_identity(q)) return false;
+    FT z2 = F::sqr(q.Z);
+    if (!F::eq(q.X, F::mul(t.x, z2))) return false;
+    return F::eq(q.Y, F::mul(t.y, F::mul(z2, q.Z)));
+  }
+  // Is the on-curve affine point p != O in the subgroup of order r?  Reference: `[r]P == O` per point
+  // (SubgroupCheckMode::Direct).  BLS12-377 uses the equivalent endomorphism tests (proofs of equivalence and the
+  // numerical checks of their hypotheses: tools/gen_constants.py::bls12_endo_block):
+  //   G1: phi(P) = [-x^2]P  <=>  [x^2]P = (beta X, -Y)      127-bit instead of 253-bit multiplication
+  //   G2: psi(P) = [x]P     <=>  [x]P = (conj(X) cx, conj(Y) cy)    64-bit instead of 253-bit
+  __device__ __forceinline__ static bool in_subgroup(const Affine& p) {
+    if constexpr (Cfg::ENDO_SUBGROUP_TEST == 1) {
+      using E = typename Cfg::Endo;
+      Jac q = mul_const(p, E::x2(), 4);
+      Affine t{F::mul(p.x, F::from_const(E::beta())), F::neg(p.y), false};
+      return jac_eq_affine(q, t);
+    } else if constexpr (Cfg::ENDO_SUBGROUP_TEST == 2) {
+      using E = typename Cfg::Endo;
+      using B = typename F::Base;
+      Jac q = mul_const(p, E::x(), 2);
+      Affine t{F::mul_base(F::conj(p.x), B::from_const(E::psi_cx())), F::mul_base(F::conj(p.y), B::from_const(E::psi_cy())), false};
+      return jac_eq_affine(q, t);
+    } else {
+      Jac q = mul_const(p, Cfg::order(), (Cfg::Fr::P::BITS + 31) / 32);
+      return is_identity(q);
+    }
   }
 
   // Jacobian -> affine given zinv = 1/Z

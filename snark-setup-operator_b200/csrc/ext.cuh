@@ -68,6 +68,7 @@ template <class B_, class NR> struct Fp2 {
   __device__ __forceinline__ static T mul(const T& a, const T& b) { return mul_val(a, b); }
   __device__ __forceinline__ static T sqr(const T& a) { return sqr_val(a); }
   __device__ __forceinline__ static T mul_base(const T& a, const typename B::T& k) { return T{B::mul(a.c0, k), B::mul(a.c1, k)}; }
+  __device__ __forceinline__ static T conj(const T& a) { return T{a.c0, B::neg(a.c1)}; }           // Frobenius of Fq2
   __device__ __noinline__ static T inv(const T& a) {
     typename B::T n = B::sub(B::sqr(a.c0), NR::mul(B::sqr(a.c1)));
     typename B::T ni = B::inv(n);

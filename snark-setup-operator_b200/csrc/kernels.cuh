@@ -9,6 +9,7 @@
 // The bodies take an explicit thread id so that tests/emul can run the very same code under an
 // instruction-level emulation of the PTX carry flag in this GPU-less container.
 #pragma once
+#include <type_traits>
 #include "curves.cuh"
 
 namespace sso {
@@ -148,11 +149,12 @@ template <class F> inline void block_batch_inverse_all(typename F::T* tree) {
 template <class G> struct ExpTypes {
   using C = SW<G>;
   using Fr = typename G::Fr;
-  static constexpr bool GLV = G::HAS_GLV;
-  static constexpr int KBITS = [] { if constexpr (G::HAS_GLV) return (int)G::Glv::KBITS; else return (int)G::Fr::P::BITS; }();
-  static constexpr int KW = [] { if constexpr (G::HAS_GLV) return (int)G::Glv::KW; else return (int)G::Fr::L; }();
+  static constexpr bool GLS4 = G::HAS_GLS4;            // 4-way psi decomposition (takes precedence over 2-way GLV)
+  static constexpr bool GLV = G::HAS_GLV && !GLS4;
+  static constexpr int KBITS = [] { if constexpr (G::HAS_GLS4) return 64; else if constexpr (G::HAS_GLV) return (int)G::Glv::KBITS; else return (int)G::Fr::P::BITS; }();
+  static constexpr int KW = [] { if constexpr (G::HAS_GLS4) return 2; else if constexpr (G::HAS_GLV) return (int)G::Glv::KW; else return (int)G::Fr::L; }();
   static constexpr int NW = (KBITS + 2 + 3) / 4;
-  using State = typename C::template Staged<GLV, KW, NW>;
+  using State = std::conditional_t<GLS4, typename C::template Staged4<NW>, typename C::template Staged<GLV, KW, NW>>;
 };
 
 template <class G>
@@ -183,7 +185,12 @@ __device__ __forceinline__ typename G::F::T exp_stage_a(uint32_t tid, const VecB
 #pragma unroll
     for (int i = 0; i < Fr::L; i++) k[i] = s.v[i];
   }
-  if constexpr (ET::GLV) {
+  if constexpr (ET::GLS4) {
+    uint32_t kd[4][2];
+    C::template gls4_split<Fr::L>(k, kd);
+#pragma unroll
+    for (int d = 0; d < 4; d++) C::template bias_scalar<2, ET::NW>(kd[d], st.kb[d]);
+  } else if constexpr (ET::GLV) {
     uint32_t k1[ET::KW], k2[ET::KW];
     C::template glv_split<typename G::Glv, Fr::L>(k, k1, k2, st.neg1, st.neg2);
     C::template bias_scalar<ET::KW, ET::NW>(k1, st.kb1);
@@ -202,9 +209,13 @@ __device__ __forceinline__ void exp_stage_c(uint32_t tid, const VecBatch& b, typ
   using F = typename G::F;
   if (tid >= b.total) return;
   C::staged_normalise(st, zinv);
-  const uint32_t* beta = nullptr;
-  if constexpr (ExpTypes<G>::GLV) beta = G::Glv::beta();
-  typename C::Jac r = C::staged_loop(st, beta);
+  typename C::Jac r;
+  if constexpr (ExpTypes<G>::GLS4) r = C::staged_loop4(st);
+  else {
+    const uint32_t* beta = nullptr;
+    if constexpr (ExpTypes<G>::GLV) beta = G::Glv::beta();
+    r = C::staged_loop(st, beta);
+  }
   uint32_t* o = jac_out + (size_t)tid * 3 * F::WORDS;
   F::store(o, 1, r.X);
   F::store(o + F::WORDS, 1, r.Y);
@@ -286,7 +297,7 @@ __device__ __forceinline__ void body_normalize_write(uint32_t tid, const VecBatc
 // ---------------------------------------------------------------------------------------------
 // K3 alone: re-encode points (compressed -> uncompressed and so on) with validation — the
 // decompression half of transform_pok_and_correctness / combine.
-//   subgroup != 0 : additionally require [r]P = O
+//   subgroup != 0 : additionally require [r]P = O (SW::in_subgroup: endomorphism form where the curve has one)
 // Optionally leaves the affine Montgomery coordinates in `aff_out` ([point][x|y] words, inf -> all-zero)
 // for the MSM that follows.
 // ---------------------------------------------------------------------------------------------
@@ -305,10 +316,7 @@ __device__ __forceinline__ void body_reencode(uint32_t tid, uint32_t n, const ui
     if (p.inf) report(status, ST_ZERO_POINT, tid);
     else if (check == CHECK_FULL) {
       if (!in_compressed && !C::on_curve(p)) report(status, ST_NOT_ON_CURVE, tid);
-      else if (subgroup) {
-        typename C::Jac q = C::mul_const(p, G::order(), (G::Fr::P::BITS + 31) / 32);
-        if (!C::is_identity(q)) report(status, ST_NOT_IN_SUBGROUP, tid);
-      }
+      else if (subgroup && !C::in_subgroup(p)) report(status, ST_NOT_IN_SUBGROUP, tid);
     }
   }
   if (out) {

@@ -54,6 +54,13 @@ def test_field_ops(emul, fid):
     cases = [(relem(), relem()) for _ in range(6)]
     top = F.p - 1 if F.deg == 1 else (F.p - 1,) * F.deg
     cases += [(F.zero, relem()), (top, top), (F.one, top)]
+    if F.deg == 1:
+        # carry-heavy residues for the dedicated squaring: runs of 0xffffffff / 0x00000000 limbs, single bits, p - small
+        bits = F.p.bit_length()
+        patt = [(1 << (bits - 1)) - 1, (1 << (bits - 2)) + 1, int("ffffffff00000000" * 12, 16) % F.p, int("00000000ffffffff" * 12, 16) % F.p,
+                (1 << 32) - 1, 1 << 32, F.p - 2, F.p // 2, F.p // 2 + 1, (1 << (32 * (bits // 32))) - 1]
+        patt += [rnd.randrange(F.p) | int("ffffffff" * (bits // 64), 16) for _ in range(6)]
+        cases += [(x % F.p, relem()) for x in patt]
     for a, b in cases:
         ab, bb = ser.field_to_bytes(F, a), ser.field_to_bytes(F, b)
         for op, fn in ops.items():
@@ -100,6 +107,56 @@ def test_batch_exp_and_reencode(emul, name, gi):
     assert emul.emul_reencode(c.cid, gi, want, 1, n - 1, out3, 0, 2, 1, st) == 0
     assert out3.raw[:len(buf) - ser.point_size(G, False)] == ser.points_to_bytes(G, want_pts[:-1], False)
     assert list(st)[:2] == [0, 0]
+
+
+def test_bls12_g2_four_way_decomposition_edge_scalars(emul):
+    """The G2 ladder of BLS12-377 splits the scalar into base-x digits (x = curve parameter) and uses psi, psi^2, psi^3:
+    scalars on the digit boundaries, and a small-order base point (Jacobian-table path), must still match [k]P."""
+    c = get_curve("bls12_377")
+    G = c.g2
+    x = 0x8508c00000000001
+    r = c.Fr.p
+    Lr = (c.Fr.bits + 31) // 32
+    pts = [G.mul(G.gen, 0x1234567), G.mul(G.gen, r - 5)]
+    buf = ser.points_to_bytes(G, pts, False)
+    st = (ctypes.c_uint32 * 3)()
+    ks = [1, 2, 8, 9, 15, 16, x - 1, x, x + 1, x * x - 1, x * x, x ** 3 - 1, x ** 3, x ** 3 + x * x + x + 1, r - 1, r - 2,
+          (x - 1) * (1 + x + x * x), 0x8888888888888888, (x - 1) + (x - 1) * x + (x - 1) * x * x + ((r - 1) // x ** 3) * x ** 3]
+    for k in ks:
+        k %= r
+        if k == 0:
+            continue
+        want = ser.points_to_bytes(G, [G.mul(P, k) for P in pts], False)
+        out = ctypes.create_string_buffer(len(want))
+        assert emul.emul_batch_exp(c.cid, 1, buf, 0, 2, words(1, Lr), words(k, Lr), ctypes.c_uint64(0), 1, 0, out, 0, st) == 0
+        assert out.raw == want, hex(k)
+
+
+@pytest.mark.parametrize("gi", [0, 1])
+def test_endomorphism_subgroup_tests_agree_with_order_check(emul, gi):
+    """BLS12-377 membership is tested on the device as phi(P) = [-x^2]P (G1) / psi(P) = [x]P (G2); the verdict must be
+    the reference's [r]P == O on every kind of on-curve point: random curve points, pure cofactor-torsion points
+    [r]P, and subgroup points plus a cofactor-torsion component."""
+    c = get_curve("bls12_377")
+    G = c.g1 if gi == 0 else c.g2
+    from oracle.curves import _some_point
+    rogue = [_some_point(G, s) for s in (11, 12, 13)]
+    torsion = [G.mul(P, G.r) for P in rogue[:2]]                      # order divides the cofactor
+    small = [G.mul(rogue[0], (G.cofactor * G.r) // ell) for ell in (2, 3, 7) if G.cofactor % ell == 0]   # tiny orders
+    mixed = [G.add(G.mul(G.gen, 77), torsion[0])]
+    good = [G.mul(G.gen, k) for k in (1, 2, 0x123456789abcdef, G.r - 1)]
+    cases = [(P, False) for P in rogue + torsion + mixed + small] + [(P, True) for P in good]
+    st = (ctypes.c_uint32 * 3)()
+    sz = ser.point_size(G, False)
+    out = ctypes.create_string_buffer(sz)
+    for P, want_ok in cases:
+        if P is None:
+            continue
+        assert G.on_curve(P) and G.in_subgroup(P) == want_ok
+        emul.emul_reencode(c.cid, gi, ser.point_to_bytes(G, P, False), 0, 1, out, 0, 2, 1, st)
+        assert (st[0] == 0) == want_ok, (gi, want_ok, st[0])
+        if not want_ok:
+            assert st[0] == 5
 
 
 def test_reencode_rejects_bad_points(emul):

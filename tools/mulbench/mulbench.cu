@@ -52,7 +52,7 @@ __device__ __forceinline__ void rr_mul(uint32_t* r, const uint32_t* a, const uin
 template <int VARIANT, int ILP>
 __global__ void __launch_bounds__(128) k_mulbench(uint32_t iters, uint32_t seed, uint32_t* out) {
   uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (VARIANT == 0) {
+  if (VARIANT == 0 || VARIANT == 3) {
     using F = Fp<P_q377>;
     typename F::T x[ILP], y[ILP];
 #pragma unroll
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(128) k_mulbench(uint32_t iters, uint32_t seed,
       for (int i = 0; i < 12; i++) { x[k].v[i] = seed * (i + 1) + tid + k; y[k].v[i] = seed * 7 + i * tid + k; x[k].v[11] &= 0xffffff; y[k].v[11] &= 0xffffff; }
     for (uint32_t it = 0; it < iters; it++) {
 #pragma unroll
-      for (int k = 0; k < ILP; k++) x[k] = F::mul(x[k], y[k]);
+      for (int k = 0; k < ILP; k++) x[k] = VARIANT == 3 ? F::add(F::sqr(x[k]), y[k]) : F::mul(x[k], y[k]);
     }
     uint32_t s = 0;
 #pragma unroll
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(128) k_mulbench(uint32_t iters, uint32_t seed,
 }
 
 // variant 2: the 24-limb (761-bit) multiplication as the kernels call it (out of line, by value)
-template <int ILP>
+template <int ILP, bool SQR>
 __global__ void __launch_bounds__(128) k_mulbench24(uint32_t iters, uint32_t seed, uint32_t* out) {
   using F = Fp<P_q761>;
   uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(128) k_mulbench24(uint32_t iters, uint32_t see
     for (int i = 0; i < 24; i++) { x[k].v[i] = seed * (i + 1) + tid + k; y[k].v[i] = seed * 7 + i * tid + k; x[k].v[23] &= 0xffffff; y[k].v[23] &= 0xffffff; }
   for (uint32_t it = 0; it < iters; it++) {
 #pragma unroll
-    for (int k = 0; k < ILP; k++) x[k] = F::mul(x[k], y[k]);
+    for (int k = 0; k < ILP; k++) x[k] = SQR ? F::add(F::sqr(x[k]), y[k]) : F::mul(x[k], y[k]);
   }
   uint32_t s = 0;
 #pragma unroll
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(128) k_mulbench24(uint32_t iters, uint32_t see
     for (int i = 0; i < 24; i++) s ^= x[k].v[i];
   out[tid] = s;
 }
-template <int ILP> void run24(int blocks_per_sm) {
+template <int ILP, bool SQR> void run24(int blocks_per_sm) {
   int dev = 0; cudaDeviceProp prop; cudaGetDeviceProperties(&prop, dev);
   uint32_t blocks = prop.multiProcessorCount * blocks_per_sm, threads = 128, iters = 1000;
   uint32_t* d_out; cudaMalloc(&d_out, (size_t)blocks * threads * 4);
@@ -122,14 +122,14 @@ template <int ILP> void run24(int blocks_per_sm) {
   float best = 1e9;
   for (int rep = 0; rep < 4; rep++) {
     cudaEventRecord(e0);
-    k_mulbench24<ILP><<<blocks, threads>>>(iters, 12345 + rep, d_out);
+    k_mulbench24<ILP, SQR><<<blocks, threads>>>(iters, 12345 + rep, d_out);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     if (rep && ms < best) best = ms;
   }
-  cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, k_mulbench24<ILP>);
+  cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, k_mulbench24<ILP, SQR>);
   double muls = (double)blocks * threads * iters * ILP;
-  printf("%-28s ilp=%d blocks/SM=%d regs=%d  %.3f ms  %.2f Gmul/s = %.2f TMAC/s (err=%s)\n", "cios32 24-limb (q761)", ILP, blocks_per_sm, fa.numRegs, best,
+  printf("%-28s ilp=%d blocks/SM=%d regs=%d  %.3f ms  %.2f Gmul/s = %.2f TMAC/s (err=%s)\n", SQR ? "sqr+add 24-limb (q761)" : "cios32 24-limb (q761)", ILP, blocks_per_sm, fa.numRegs, best,
          muls / best / 1e6, muls / best / 1e6 * 1176 / 1e3, cudaGetErrorString(cudaGetLastError()));
   cudaFree(d_out);
 }
@@ -170,10 +170,11 @@ int main() {
   uint32_t x = 1; for (int i = 0; i < 6; i++) x *= 2 - limbs[0] * x;
   uint32_t inv = (0u - x) & MASK;
   cudaMemcpyToSymbol(c_p28, limbs, sizeof limbs); cudaMemcpyToSymbol(c_inv28, &inv, 4);
-  for (int bps : {2, 4}) { run24<1>(bps); run24<2>(bps); }
+  for (int bps : {2, 4}) { run24<1, false>(bps); run24<1, true>(bps); }
   for (int bps : {2, 4, 8}) {
     run<0, 1>("cios32 even/odd", bps);
     run<0, 2>("cios32 even/odd", bps);
+    run<3, 1>("dedicated sqr (+add)", bps);
     run<1, 1>("reduced radix 14x28", bps);
     run<1, 2>("reduced radix 14x28", bps);
   }
