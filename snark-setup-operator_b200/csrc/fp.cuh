@@ -332,14 +332,20 @@ template <class P_> struct Fp {
   __device__ __forceinline__ static T mul(const T& a, const T& b) {
     if constexpr (L > SSO_INLINE_MUL_MAX_L) { return mul_outlined(a, b); } else { T r; mont_mul<P>(r.v, a.v, b.v); return r; }
   }
-#ifndef SSO_NO_DEDICATED_SQR
+  // Dedicated squaring.  Measured on B200 (tools/mulbench, profiles/r1_mulbench.txt): +13 % over mul(a, a) on 12 limbs,
+  // +22 % on 24 limbs in isolation; inside the point formulas the 24-limb version does not pay (the out-of-line
+  // squaring needs more registers than the multiplication and the callers spill around it: batch_exp -1..3 %), so the
+  // point formulas use it up to SSO_SQR_EC_MAX_L limbs and the exponentiation chains (sqrt, pow) always.
+#ifndef SSO_SQR_EC_MAX_L
+#define SSO_SQR_EC_MAX_L 12
+#endif
   __device__ __noinline__ static T sqr_outlined(T a) { T r; mont_sqr<P>(r.v, a.v); return r; }
-  __device__ __forceinline__ static T sqr(const T& a) {
+  __device__ __forceinline__ static T sqr_dedicated(const T& a) {
     if constexpr (L > SSO_INLINE_MUL_MAX_L) { return sqr_outlined(a); } else { T r; mont_sqr<P>(r.v, a.v); return r; }
   }
-#else
-  __device__ __forceinline__ static T sqr(const T& a) { return mul(a, a); }
-#endif
+  __device__ __forceinline__ static T sqr(const T& a) {
+    if constexpr (L <= SSO_SQR_EC_MAX_L) return sqr_dedicated(a); else return mul(a, a);
+  }
   // always-inlined multiplication, for callers that want independent multiplications interleaved by the scheduler
   __device__ __forceinline__ static T mul_inl(const T& a, const T& b) { T r; mont_mul<P>(r.v, a.v, b.v); return r; }
   // multiply by a small non-negative integer constant
@@ -368,7 +374,7 @@ template <class P_> struct Fp {
     T r = one();
     bool started = false;
     for (int i = L * 32 - 1; i >= 0; i--) {
-      if (started) r = sqr(r);
+      if (started) r = sqr_dedicated(r);
       if ((e[i >> 5] >> (i & 31)) & 1) { r = started ? mul(r, a) : a; started = true; }
     }
     return r;

@@ -36,6 +36,7 @@ template <class F> static int field_op(int op, const uint8_t* a, const uint8_t* 
     case 3: r = F::sqr(x); break;
     case 4: r = F::neg(x); break;
     case 5: r = F::inv(x); break;
+    case 6: if constexpr (F::DEG == 1) r = F::sqr_dedicated(x); else r = F::sqr(x); break;
     case 7: r = x; rc = F::lex_is_neg(x) ? 1 : 0; break;
     default: return -2;
   }

@@ -50,7 +50,7 @@ def test_field_ops(emul, fid):
         return rnd.randrange(F.p) if F.deg == 1 else tuple(rnd.randrange(F.p) for _ in range(F.deg))
 
     ops = {0: lambda a, b: F.mul(a, b), 1: lambda a, b: F.add(a, b), 2: lambda a, b: F.sub(a, b), 3: lambda a, b: F.sqr(a),
-           4: lambda a, b: F.neg(a), 5: lambda a, b: F.inv(a)}
+           4: lambda a, b: F.neg(a), 5: lambda a, b: F.inv(a), 6: lambda a, b: F.sqr(a)}     # 6 = dedicated squaring
     cases = [(relem(), relem()) for _ in range(6)]
     top = F.p - 1 if F.deg == 1 else (F.p - 1,) * F.deg
     cases += [(F.zero, relem()), (top, top), (F.one, top)]
