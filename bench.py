@@ -40,9 +40,10 @@ def macs_per_fq_mul(limbs: int) -> int:
 
 GLV_KBITS = {"bls12_377": 129, "bw6_761": 191}
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_batch_exp_chunk launch on the bench workload, from the committed
-# `ncu --set full` capture (profiles/r1_ncu_batch_exp_chunk_summary.csv): window tables and spills in local memory;
-# the algorithmic bytes are 31.5 MB in + 15.7 MB out + 38 MB of Jacobian intermediates
-NCU_DRAM_BYTES_PER_LAUNCH = {"bls12_377": 1.26e9}      # csrc/constants.cuh GLV_*::KBITS (half-size scalars)
+# `ncu --set full` capture (profiles/r1_ncu_batch_exp_chunk_summary.csv): 3.64 GB read + 1.95 GB written.  The algorithmic
+# bytes are 31.5 MB in + 38 MB of Jacobian intermediates out; the rest is the per-thread stack (window tables, by-reference
+# point arguments, spills: 4.8 KB/thread x 37.9 k resident threads = 181 MB, more than the 126 MB L2).  207 GB/s: 3 % of HBM.
+NCU_DRAM_BYTES_PER_LAUNCH = {"bls12_377": 5.59e9}
 
 
 def declared_work_per_point(curve: str, group: int):
@@ -89,7 +90,10 @@ def declared_work_per_point(curve: str, group: int):
 
 
 def macs_per_fq_sqr(limbs: int) -> int:
-    return limbs * (limbs + 1) // 2 + limbs * limbs + limbs      # csrc/fp.cuh::mont_sqr
+    """csrc/fp.cuh: the point formulas use the dedicated squaring up to 12 limbs (SSO_SQR_EC_MAX_L), mul(a, a) above"""
+    if limbs > 12:
+        return macs_per_fq_mul(limbs)
+    return limbs * (limbs + 1) // 2 + limbs * limbs + limbs      # mont_sqr
 
 
 def declared_fq_muls_per_point(curve: str, group: int) -> float:

@@ -83,8 +83,11 @@ __global__ void __launch_bounds__(128) k_reencode(uint32_t n, const uint8_t* in,
 // Both groups of a chunk in ONE launch: blocks [0, nb2) take G2 points (the long-running ones, scheduled first),
 // the rest take G1 points.  All blocks have the same register footprint, so G1 blocks fill the SMs that the last,
 // partial wave of G2 blocks leaves idle (two separate launches lose ~13 % each to wave quantisation).
+#ifndef SSO_CHUNK_MIN_BLOCKS
+#define SSO_CHUNK_MIN_BLOCKS 1
+#endif
 template <class G1, class G2>
-__global__ void __launch_bounds__(128) k_batch_exp_chunk(const __grid_constant__ VecBatch b1, const __grid_constant__ VecBatch b2,
+__global__ void __launch_bounds__(128, SSO_CHUNK_MIN_BLOCKS) k_batch_exp_chunk(const __grid_constant__ VecBatch b1, const __grid_constant__ VecBatch b2,
                                                           uint32_t nb2, uint32_t in_compressed, const uint32_t* table, uint32_t check,
                                                           uint32_t* jac1, uint32_t* jac2, uint32_t* status) {
   // one dynamic shared buffer, sized by the host for the wider of the two coordinate fields (2 * EXP_BLOCK elements)
