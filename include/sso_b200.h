@@ -145,14 +145,24 @@ int32_t sso_p1_contribute_buf(const sso_p1_params_t* p, const uint8_t* challenge
 /* sso_p1_contribute_buf over several chunks in flight, as the reference's Process lane holds several chunks
  * (src/bin/contribute.rs:64-71, 158-163: --max-in-process-lane; chunks are independent, :1132-1139).
  * params[i], challenges[i], responses[i] describe chunk i; the same scalars and public key are applied to all.
- * host_threads workers (0 = default 3) each run one chunk at a time on their own CUDA streams: the sequential
- * Blake2b of one chunk overlaps the copies and kernels of the others.  Results are byte-identical to n_chunks
- * separate sso_p1_contribute_buf calls.  On failure the first error is returned and no further chunks start. */
+ * host_threads workers (0 = default: 3 per device) each run one chunk at a time on their own CUDA streams: the
+ * sequential Blake2b of one chunk overlaps the copies and kernels of the others.  device < 0 spreads the workers
+ * over all visible devices (worker t on device t mod count).  Results are byte-identical to n_chunks separate
+ * sso_p1_contribute_buf calls.  On failure the first error is returned and no further chunks start. */
 int32_t sso_p1_contribute_many_buf(const sso_p1_params_t* params, size_t n_chunks, const uint8_t* const* challenges,
                                    const size_t* challenge_lens, uint8_t* const* responses, const size_t* response_lens,
                                    const uint8_t* tau, const uint8_t* alpha, const uint8_t* beta, const uint8_t* pubkey,
                                    size_t pubkey_len, uint32_t check_input, uint32_t host_threads, int device, char* err,
                                    size_t errcap);
+
+/* sso_p1_verify_chunk_buf over several chunks in flight: the chunk loop of verify_transcript
+ * (src/bin/verify_transcript.rs:293-569) as a work queue.  Same worker / device semantics as
+ * sso_p1_contribute_many_buf; the first failing chunk's code and message are returned (SSO_E_VERIFY names the check). */
+int32_t sso_p1_verify_chunk_many_buf(const sso_p1_params_t* params, size_t n_chunks, const uint8_t* const* challenges,
+                                     const size_t* challenge_lens, const uint8_t* const* responses, const size_t* response_lens,
+                                     uint8_t* const* new_challenges, const size_t* new_challenge_lens, uint32_t check_input,
+                                     uint32_t check_output, uint32_t subgroup_check_mode, uint32_t ratio_check,
+                                     const uint8_t* rlc_seed32, uint32_t host_threads, int device, char* err, size_t errcap);
 
 /* phase1_cli::new_challenge (reference src/bin/new_setup.rs:105-109, src/bin/verify_transcript.rs:322-326):
  * the initial accumulator — every element is the group generator, hash slot = Blake2b-512 of the empty

@@ -412,45 +412,21 @@ int32_t sso_p1_contribute_buf(const sso_p1_params_t* p, const uint8_t* challenge
 }
 
 // Several chunks in flight (the reference runs up to --max-in-process-lane chunks through its Process lane,
-// src/bin/contribute.rs:64-71, 158-163, 1132-1139): `host_threads` workers each take the next chunk and run the
-// single-chunk call on their own streams, so the sequential Blake2b of one chunk overlaps the copies and kernels of
-// the others and the throughput of the call is bound by the GPU, not by one host core.
+// src/bin/contribute.rs:64-71, 158-163, 1132-1139; verify_transcript loops over the chunks of a round,
+// src/bin/verify_transcript.rs:293-569): `host_threads` workers each take the next chunk and run the single-chunk
+// call on their own streams, so the sequential Blake2b of one chunk overlaps the copies and kernels of the others and
+// the throughput of the call is bound by the GPU, not by one host core.  device < 0: all visible devices, worker t on
+// device t mod count (default 3 workers per device).
 int32_t sso_p1_contribute_many_buf(const sso_p1_params_t* params, size_t n_chunks, const uint8_t* const* challenges,
                                    const size_t* challenge_lens, uint8_t* const* responses, const size_t* response_lens,
                                    const uint8_t* tau, const uint8_t* alpha, const uint8_t* beta, const uint8_t* pubkey,
                                    size_t pubkey_len, uint32_t check_input, uint32_t host_threads, int device, char* err,
                                    size_t errcap) {
   if (!params || !challenges || !challenge_lens || !responses || !response_lens) { set_err(err, errcap, "null argument"); return SSO_E_ARG; }
-  if (n_chunks == 0) return SSO_OK;
-  size_t workers = host_threads ? host_threads : 3;
-  if (workers > n_chunks) workers = n_chunks;
-  if (workers > 16) workers = 16;
-  std::atomic<size_t> next{0};
-  std::atomic<int32_t> first_rc{SSO_OK};
-  std::mutex err_lock;
-  auto work = [&]() {
-    char local[512];
-    for (;;) {
-      size_t i = next.fetch_add(1);
-      if (i >= n_chunks || first_rc.load() != SSO_OK) return;
-      local[0] = 0;
-      int32_t rc = sso_p1_contribute_buf(&params[i], challenges[i], challenge_lens[i], responses[i], response_lens[i], tau, alpha, beta,
-                                         pubkey, pubkey_len, check_input, device, local, sizeof(local));
-      if (rc != SSO_OK) {
-        std::lock_guard<std::mutex> g(err_lock);
-        if (first_rc.load() == SSO_OK) {
-          first_rc.store(rc);
-          set_err(err, errcap, "chunk %zu of the batch: %s", i, local);
-        }
-        return;
-      }
-    }
-  };
-  std::vector<std::thread> pool;
-  for (size_t t = 1; t < workers; t++) pool.emplace_back(work);
-  work();
-  for (auto& t : pool) t.join();
-  return first_rc.load();
+  return run_chunks_in_flight(n_chunks, host_threads, device, err, errcap, [&](size_t i, int dev, char* e, size_t ec) {
+    return sso_p1_contribute_buf(&params[i], challenges[i], challenge_lens[i], responses[i], response_lens[i], tau, alpha, beta,
+                                 pubkey, pubkey_len, check_input, dev, e, ec);
+  });
 }
 
 int32_t sso_p1_new_challenge_dev(const sso_p1_params_t* p, void* d_challenge, int device, char* err, size_t errcap) {
@@ -567,6 +543,23 @@ int32_t sso_p1_verify_chunk_buf(const sso_p1_params_t* p, const uint8_t* challen
   uint64_t chunk_index = p->contribution_mode == SSO_MODE_FULL ? 0 : p->chunk_index;
   return verify_chunk_host(c, ops, L, p->curve, chunk_index, challenge, response, new_challenge, check_output, subgroup_check_mode,
                            ratio_check, rlc_seed32, err, errcap);
+}
+
+// The chunk loop of verify_transcript (src/bin/verify_transcript.rs:293-569) as a work queue: chunks are verified
+// independently (the hash-chain order across rounds stays with the caller), several in flight per device.
+int32_t sso_p1_verify_chunk_many_buf(const sso_p1_params_t* params, size_t n_chunks, const uint8_t* const* challenges,
+                                     const size_t* challenge_lens, const uint8_t* const* responses, const size_t* response_lens,
+                                     uint8_t* const* new_challenges, const size_t* new_challenge_lens, uint32_t check_input,
+                                     uint32_t check_output, uint32_t subgroup_check_mode, uint32_t ratio_check,
+                                     const uint8_t* rlc_seed32, uint32_t host_threads, int device, char* err, size_t errcap) {
+  if (!params || !challenges || !challenge_lens || !responses || !response_lens || !new_challenges || !new_challenge_lens) {
+    set_err(err, errcap, "null argument");
+    return SSO_E_ARG;
+  }
+  return run_chunks_in_flight(n_chunks, host_threads, device, err, errcap, [&](size_t i, int dev, char* e, size_t ec) {
+    return sso_p1_verify_chunk_buf(&params[i], challenges[i], challenge_lens[i], responses[i], response_lens[i], new_challenges[i],
+                                   new_challenge_lens[i], check_input, check_output, subgroup_check_mode, ratio_check, rlc_seed32, dev, e, ec);
+  });
 }
 
 // phase1_cli::transform_pok_and_correctness(challenge_fn, challenge_hash_fn, check_input, response_fn, response_hash_fn,

@@ -3,6 +3,9 @@
 // size asserts, the Blake2b hash chain, key generation from the seeded RNG, the proof-of-knowledge and
 // ratio checks — expressed over the CurveOps table.  All arithmetic runs on the device.
 #pragma once
+#include <thread>
+#include <mutex>
+#include <atomic>
 #include <fcntl.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -244,5 +247,46 @@ inline int verify_chunk_host(Ctx& c, const CurveOps* ops, const P1Layout& L, uin
   c.mark("verify: pairings");
   return rc;
 }
+
+// Work queue over the chunks of a batch: `host_threads` host workers, each running one chunk at a time through
+// `one_chunk(index, device, err, errcap)`; device < 0 spreads the workers over all visible devices.
+template <class Fn>
+inline int32_t run_chunks_in_flight(size_t n_chunks, uint32_t host_threads, int device, char* err, size_t errcap, Fn one_chunk) {
+  if (n_chunks == 0) return SSO_OK;
+  int ndev = 1;
+  if (device < 0) {
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { set_err(err, errcap, "no CUDA device available (this library has no CPU fallback)"); return SSO_E_CUDA; }
+  }
+  size_t workers = host_threads ? host_threads : (size_t)3 * ndev;
+  if (workers > n_chunks) workers = n_chunks;
+  if (workers > 64) workers = 64;
+  std::atomic<size_t> next{0};
+  std::atomic<int32_t> first_rc{SSO_OK};
+  std::mutex err_lock;
+  auto work = [&](size_t t) {
+    char local[512];
+    const int dev = device < 0 ? (int)(t % (size_t)ndev) : device;
+    for (;;) {
+      size_t i = next.fetch_add(1);
+      if (i >= n_chunks || first_rc.load() != SSO_OK) return;
+      local[0] = 0;
+      int32_t rc = one_chunk(i, dev, local, sizeof(local));
+      if (rc != SSO_OK) {
+        std::lock_guard<std::mutex> g(err_lock);
+        if (first_rc.load() == SSO_OK) {
+          first_rc.store(rc);
+          set_err(err, errcap, "chunk %zu of the batch: %s", i, local);
+        }
+        return;
+      }
+    }
+  };
+  std::vector<std::thread> pool;
+  for (size_t t = 1; t < workers; t++) pool.emplace_back(work, t);
+  work(0);
+  for (auto& t : pool) t.join();
+  return first_rc.load();
+}
+
 
 }  // namespace sso

@@ -147,11 +147,24 @@ def contribute_buf(params: Phase1Parameters, challenge, response, tau: int, alph
     return response
 
 
+def _ptr_arrays(bufs):
+    """list of host buffers -> (void*[n], size_t[n], keepalives)"""
+    n = len(bufs)
+    keep, ptrs, lens = [], [], []
+    for b in bufs:
+        p, ln, k = _host_ptr(b)
+        keep.append(k)
+        ptrs.append(p if isinstance(p, int) else ctypes.cast(p, ctypes.c_void_p).value)
+        lens.append(ln)
+    return (ctypes.c_void_p * n)(*ptrs), (ctypes.c_size_t * n)(*lens), keep
+
+
 def contribute_many_buf(params_list, challenges, responses, tau: int, alpha: int, beta: int, pubkey: bytes | None = None,
                         check=CHECK_NONZERO, host_threads=0, device=0):
     """contribute_buf over several chunks in flight (the reference's Process lane, src/bin/contribute.rs:64-71,158-163):
-    `host_threads` workers (0 = library default) each run one chunk at a time, so one chunk's Blake2b overlaps the
-    copies and kernels of the others.  params_list[i] / challenges[i] / responses[i] describe chunk i."""
+    `host_threads` workers (0 = library default, 3 per device) each run one chunk at a time, so one chunk's Blake2b
+    overlaps the copies and kernels of the others.  params_list[i] / challenges[i] / responses[i] describe chunk i;
+    device < 0 spreads the workers over all visible GPUs."""
     n = len(params_list)
     if not (len(challenges) == len(responses) == n):
         raise SsoError(-1, "params, challenges and responses must have the same length")
@@ -159,25 +172,31 @@ def contribute_many_buf(params_list, challenges, responses, tau: int, alpha: int
         return responses
     c = params_list[0].curve
     P = (_lib.P1Params * n)(*[p.c_struct() for p in params_list])
-    keep, ch, rs = [], [], []
-    for a, b in zip(challenges, responses):
-        pa, la, ka = _host_ptr(a)
-        pb, lb, kb = _host_ptr(b)
-        keep += [ka, kb]
-        ch.append((pa, la))
-        rs.append((pb, lb))
-
-    def addr(x):
-        return x if isinstance(x, int) else ctypes.cast(x, ctypes.c_void_p).value
-
-    ch_p = (ctypes.c_void_p * n)(*[addr(x[0]) for x in ch])
-    ch_l = (ctypes.c_size_t * n)(*[x[1] for x in ch])
-    rs_p = (ctypes.c_void_p * n)(*[addr(x[0]) for x in rs])
-    rs_l = (ctypes.c_size_t * n)(*[x[1] for x in rs])
+    ch_p, ch_l, k1 = _ptr_arrays(challenges)
+    rs_p, rs_l, k2 = _ptr_arrays(responses)
     call("sso_p1_contribute_many_buf", P, n, ch_p, ch_l, rs_p, rs_l, scalar_bytes(c, tau), scalar_bytes(c, alpha),
          scalar_bytes(c, beta), pubkey, 0 if pubkey is None else len(pubkey), check, host_threads, device)
-    del keep
+    del k1, k2
     return responses
+
+
+def verify_chunk_many_buf(params_list, challenges, responses, new_challenges, check_input=CHECK_NO, check_output=CHECK_FULL,
+                          subgroup_check_mode=0, ratio_check=True, rlc_seed32=None, host_threads=0, device=0):
+    """verify_chunk_buf over several chunks in flight: the chunk loop of verify_transcript (src/bin/verify_transcript.rs:293-569)
+    as a work queue.  Raises SsoError for the first rejected chunk ("chunk i of the batch: ...")."""
+    n = len(params_list)
+    if not (len(challenges) == len(responses) == len(new_challenges) == n):
+        raise SsoError(-1, "params, challenges, responses and new challenges must have the same length")
+    if n == 0:
+        return new_challenges
+    P = (_lib.P1Params * n)(*[p.c_struct() for p in params_list])
+    ch_p, ch_l, k1 = _ptr_arrays(challenges)
+    rs_p, rs_l, k2 = _ptr_arrays(responses)
+    nc_p, nc_l, k3 = _ptr_arrays(new_challenges)
+    call("sso_p1_verify_chunk_many_buf", P, n, ch_p, ch_l, rs_p, rs_l, nc_p, nc_l, check_input, check_output, subgroup_check_mode,
+         int(ratio_check), rlc_seed32, host_threads, device)
+    del k1, k2, k3
+    return new_challenges
 
 
 def new_challenge_dev(params: Phase1Parameters, d_challenge, device=0):

@@ -51,6 +51,25 @@ def test_verify_accepts_honest_contribution(name, k):
         assert phase1.verify_chunk(o, ch, resp, rlc_seed32=bytes(range(32))) == bytes(new_ch)
 
 
+def test_verify_many_chunks_in_flight():
+    """sso_p1_verify_chunk_many_buf: the chunk loop of verify_transcript as a work queue — same new challenges as the
+    single-chunk call, and a bad chunk in the batch is reported with its index."""
+    items = [_contribution("bls12_377", k) for k in (0, 1, 3, 1, 0)]
+    params = [it[1] for it in items]
+    chs = [it[2] for it in items]
+    resps = [it[3] for it in items]
+    news = [bytearray(it[0].accumulator_size) for it in items]
+    sso.verify_chunk_many_buf(params, chs, resps, news, rlc_seed32=bytes(range(32)), host_threads=3)
+    for it, new in zip(items, news):
+        assert bytes(new) == phase1.decompress_response(it[0], it[3])
+    sso.verify_chunk_many_buf(params, chs, resps, news, rlc_seed32=bytes(range(32)), host_threads=0, device=-1)   # all devices
+    bad = bytearray(resps[3])
+    bad[-1] ^= 1                                                  # corrupt the public key of chunk 3
+    with pytest.raises(sso.SsoError) as e:
+        sso.verify_chunk_many_buf(params, chs, resps[:3] + [bytes(bad)] + resps[4:], news, rlc_seed32=bytes(range(32)), host_threads=2)
+    assert e.value.code in (-3, -4) and "chunk 3 of the batch" in str(e.value)
+
+
 def test_verify_rejects_bad_contributions():
     o, p, ch, resp = _contribution("bls12_377", 0)
     c = o.curve
