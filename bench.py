@@ -314,6 +314,12 @@ def main():
     barrier()
     ms_e2e_single_total = run_steps(step_e2e, args.steps, True)
     barrier()
+    h_resp_single = h_resp.clone()
+    # (a') the whole of phase1_cli::contribute on host buffers: key generation from the seed, proofs of knowledge, computation
+    step_seeded = lambda: sso.contribute_seeded_buf(p, h_ch, h_resp, bytes(range(32)), check=sso.CHECK_NONZERO, device=dev)
+    run_steps(step_seeded, 1, False)
+    ms_e2e_seeded_total = run_steps(step_seeded, args.steps, True)
+    barrier()
     # (b) the headline: the same K steps with several chunks in flight (sso_p1_contribute_many_buf, the reference's
     # Process lane): every step still copies its own challenge from pinned host memory and reads its own response back
     n_resp = min(args.steps, 64)
@@ -336,7 +342,25 @@ def main():
     e1.synchronize()
     ms_e2e_total = e0.elapsed_time(e1)
     barrier()
-    e2e_same = all(torch.equal(h_resps[i], h_resp) for i in range(n_resp))
+    e2e_same = all(torch.equal(h_resps[i], h_resp_single) for i in range(n_resp))
+    # (b') the same with the full call (key generation + proofs of knowledge per chunk), four host workers
+    def many_seeded(n):
+        done = 0
+        while done < n:
+            k = min(n_resp, n - done)
+            sso.contribute_seeded_many_buf([p] * k, [h_ch] * k, h_resps[:k], bytes(range(32)), check=sso.CHECK_NONZERO, host_threads=4,
+                                           device=dev)
+            done += k
+
+    many_seeded(min(4, args.steps))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    many_seeded(args.steps)
+    e1.record()
+    e1.synchronize()
+    ms_e2e_seeded_many_total = e0.elapsed_time(e1)
+    barrier()
     sampler.stop_flag = True
     if sampler.is_alive():
         sampler.join(timeout=2)
@@ -366,12 +390,15 @@ def main():
                   "what": "sso_p1_verify_chunk_buf: hash chain, PoK pairings, decompress + direct subgroup checks of %d points, "
                           "RLC power-ratio MSMs, same_ratio pairings; host buffers" % npts}
 
-    t = torch.tensor([ms_total, ms_e2e_total, ms_e2e_single_total], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms_total, ms_e2e_total, ms_e2e_single_total, ms_e2e_seeded_total, ms_e2e_seeded_many_total], dtype=torch.float64,
+                     device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = t[0].item() / args.steps
     ms_e2e = t[1].item() / args.steps
     ms_e2e_single = t[2].item() / args.steps
+    ms_e2e_seeded = t[3].item() / args.steps
+    ms_e2e_seeded_many = t[4].item() / args.steps
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -416,7 +443,12 @@ def main():
                 "call": "sso_p1_contribute_many_buf: K chunks from pinned host buffers, 3 host workers, each chunk = H2D + kernels + "
                         "Blake2b(challenge) + D2H; responses identical to the single-chunk call: %s" % e2e_same,
                 "single_call": {"value": world * npts / (ms_e2e_single * 1e-3), "ms_per_step": ms_e2e_single,
-                                "call": "sso_p1_contribute_buf, one chunk per call (Blake2b of the challenge on one host core is the floor)"}},
+                                "call": "sso_p1_contribute_buf, one chunk per call (Blake2b of the challenge on one host core is the floor)"},
+                "seeded_call": {"value": world * npts / (ms_e2e_seeded * 1e-3), "ms_per_step": ms_e2e_seeded,
+                                "call": "sso_p1_contribute_seeded_buf, one chunk per call: key generation from the seed, proofs of "
+                                        "knowledge (hash_to_g2), computation — all of phase1_cli::contribute but the file I/O"},
+                "seeded_in_flight": {"value": world * npts / (ms_e2e_seeded_many * 1e-3), "ms_per_step": ms_e2e_seeded_many,
+                                     "call": "sso_p1_contribute_seeded_many_buf: the full call with K chunks in flight, 4 host workers"}},
         "gpu_launches": launches,
         "roofline": {"bound": "imad",
                      "kernel": dom["kernel"], "achieved": dom["achieved_tmacs"], "peak": peak / 1e12, "unit": "TMAC/s",

@@ -155,6 +155,14 @@ int32_t sso_p1_contribute_many_buf(const sso_p1_params_t* params, size_t n_chunk
                                    size_t pubkey_len, uint32_t check_input, uint32_t host_threads, int device, char* err,
                                    size_t errcap);
 
+/* sso_p1_contribute_seeded_buf (all of phase1_cli::contribute but the file I/O) over several chunks in flight: the
+ * contributor applies the same seed-derived key to every chunk (src/bin/contribute.rs:789, 809-823).  Worker / device
+ * semantics as sso_p1_contribute_many_buf. */
+int32_t sso_p1_contribute_seeded_many_buf(const sso_p1_params_t* params, size_t n_chunks, const uint8_t* const* challenges,
+                                          const size_t* challenge_lens, uint8_t* const* responses, const size_t* response_lens,
+                                          const uint8_t seed32[32], uint32_t check_input, uint32_t host_threads, int device,
+                                          char* err, size_t errcap);
+
 /* sso_p1_verify_chunk_buf over several chunks in flight: the chunk loop of verify_transcript
  * (src/bin/verify_transcript.rs:293-569) as a work queue.  Same worker / device semantics as
  * sso_p1_contribute_many_buf; the first failing chunk's code and message are returned (SSO_E_VERIFY names the check). */

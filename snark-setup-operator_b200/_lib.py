@@ -65,6 +65,8 @@ def lib() -> ctypes.CDLL:
         L.sso_p1_new_challenge_dev.argtypes = [ctypes.POINTER(P1Params), vp, i32, cp, sz]
         L.sso_p1_contribute_many_buf.argtypes = [pp, sz, ctypes.POINTER(vp), ctypes.POINTER(sz), ctypes.POINTER(vp), ctypes.POINTER(sz),
                                                  u8p, u8p, u8p, u8p, sz, u32, u32, i32, cp, sz]
+        L.sso_p1_contribute_seeded_many_buf.argtypes = [pp, sz, ctypes.POINTER(vp), ctypes.POINTER(sz), ctypes.POINTER(vp), ctypes.POINTER(sz),
+                                                        u8p, u32, u32, i32, cp, sz]
         L.sso_p1_verify_chunk_many_buf.argtypes = [pp, sz, ctypes.POINTER(vp), ctypes.POINTER(sz), ctypes.POINTER(vp), ctypes.POINTER(sz),
                                                    ctypes.POINTER(vp), ctypes.POINTER(sz), u32, u32, u32, u32, u8p, u32, i32, cp, sz]
         L.sso_profile_enable.argtypes = [ctypes.c_int32]
@@ -76,7 +78,7 @@ def lib() -> ctypes.CDLL:
                      "sso_test_field_mul", "sso_p1_new_challenge_dev", "sso_profile_enable", "sso_profile_reset",
                      "sso_profile_read", "sso_power_pairs_dev", "sso_merge_pairs_dev", "sso_same_ratio", "sso_p1_keygen",
                      "sso_p1_contribute_seeded_buf", "sso_p1_contribute_file", "sso_p1_verify_chunk_buf", "sso_p1_verify_chunk_file", "sso_points_sum",
-                     "sso_p2_scale_queries_buf", "sso_p2_verify_queries_buf", "sso_p1_contribute_many_buf", "sso_p1_verify_chunk_many_buf"):
+                     "sso_p2_scale_queries_buf", "sso_p2_verify_queries_buf", "sso_p1_contribute_many_buf", "sso_p1_verify_chunk_many_buf", "sso_p1_contribute_seeded_many_buf"):
             getattr(L, name).restype = ctypes.c_int32
         _lib = L
     return _lib

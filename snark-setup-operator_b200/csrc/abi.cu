@@ -375,20 +375,38 @@ int32_t sso_p1_contribute_dev(const sso_p1_params_t* p, const void* d_challenge,
   return check_status(c, d_status, "challenge", err, errcap);
 }
 
-int32_t sso_p1_contribute_buf(const sso_p1_params_t* p, const uint8_t* challenge, size_t challenge_len,
-                              uint8_t* response, size_t response_len, const uint8_t* tau, const uint8_t* alpha,
-                              const uint8_t* beta, const uint8_t* pubkey, size_t pubkey_len, uint32_t check_input,
-                              int device, char* err, size_t errcap) {
+// Shared body of sso_p1_contribute_buf (scalars and public key given) and sso_p1_contribute_seeded_buf (seed32 given:
+// scalars drawn first, proofs of knowledge computed once the challenge hash is known, on a high-priority stream beside
+// the main kernels).  The challenge is hashed ONCE, on the host, while the GPU works.
+static int32_t contribute_buf_core(const sso_p1_params_t* p, const uint8_t* challenge, size_t challenge_len, uint8_t* response,
+                                   size_t response_len, const uint8_t* tau, const uint8_t* alpha, const uint8_t* beta,
+                                   const uint8_t* pubkey, size_t pubkey_len, const uint8_t* seed32, uint32_t check_input, int device,
+                                   char* err, size_t errcap) {
   P1Layout L;
   int rc = p1_layout(p, L, err, errcap);
   if (rc) return rc;
   const CurveOps* ops = ops_for(p->curve);
-  if (!tau || !alpha || !beta || !challenge || !response) { set_err(err, errcap, "null argument"); return SSO_E_ARG; }
+  if (!challenge || !response || (!seed32 && (!tau || !alpha || !beta))) { set_err(err, errcap, "null argument"); return SSO_E_ARG; }
   if (challenge_len != L.acc_size) { set_err(err, errcap, "challenge has %zu bytes, expected accumulator_size %llu", challenge_len, (unsigned long long)L.acc_size); return SSO_E_ARG; }
   if (response_len != L.contrib_size) { set_err(err, errcap, "response has %zu bytes, expected contribution_size %llu", response_len, (unsigned long long)L.contrib_size); return SSO_E_ARG; }
   if (pubkey && pubkey_len != L.pk_size) { set_err(err, errcap, "public key has %zu bytes, expected %llu", pubkey_len, (unsigned long long)L.pk_size); return SSO_E_ARG; }
   Ctx c(err, errcap);
-  if ((rc = c.init(device, 2))) return rc;
+  if ((rc = c.init(device, seed32 ? 3 : 2))) return rc;
+  std::vector<uint8_t> scalars;
+  KeygenState keys;
+  // the hash-chain link is computed on the host while the GPU works; with a seed it starts before the key generation
+  // (whose first stage is a ~19 ms single-thread kernel the host would otherwise wait for)
+  std::thread hasher;
+  struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{hasher};
+  if (seed32) {
+    hasher = std::thread([=] { blake2b_512(challenge, challenge_len, response); });
+    scalars.resize(3 * (size_t)L.cs.fr);
+    if ((rc = keygen_stage1(c, ops, L.cs, seed32, 3, keys, scalars.data(), err, errcap))) return rc;
+    tau = scalars.data();
+    alpha = scalars.data() + L.cs.fr;
+    beta = scalars.data() + 2 * (size_t)L.cs.fr;
+    c.mark("keygen: scalars");
+  }
   uint8_t *d_ch, *d_resp;
   uint32_t* d_status;
   if ((rc = c.alloc((void**)&d_ch, L.acc_size))) return rc;
@@ -400,15 +418,28 @@ int32_t sso_p1_contribute_buf(const sso_p1_params_t* p, const uint8_t* challenge
   c.mark("challenge H2D enqueued");
   if ((rc = p1_contribute_streams(c, ops, L, d_ch, d_resp, tau, alpha, beta, check_input, d_status, err, errcap))) return rc;
   c.mark("kernels enqueued");
-  // the hash-chain link is computed on the host while the GPU works
-  blake2b_512(challenge, challenge_len, response);
+  if (hasher.joinable()) hasher.join();
+  else blake2b_512(challenge, challenge_len, response);
   c.mark("blake2b(challenge)");
+  if (seed32) {
+    if ((rc = keygen_stage2(c, 2, ops, L.cs, response, keys, response + L.off_c[5], err, errcap))) return rc;
+    c.mark("keygen: proofs of knowledge enqueued");
+  }
   if ((rc = sync_all(c, err, errcap))) return rc;
   if ((rc = check_status(c, d_status, "challenge", err, errcap))) return rc;
   CUDA_TRY(cudaMemcpy(response + 64, d_resp + 64, L.off_c[5] - 64, cudaMemcpyDeviceToHost));
   c.mark("response D2H");
   if (pubkey) memcpy(response + L.off_c[5], pubkey, L.pk_size);
   return SSO_OK;
+}
+
+int32_t sso_p1_contribute_buf(const sso_p1_params_t* p, const uint8_t* challenge, size_t challenge_len,
+                              uint8_t* response, size_t response_len, const uint8_t* tau, const uint8_t* alpha,
+                              const uint8_t* beta, const uint8_t* pubkey, size_t pubkey_len, uint32_t check_input,
+                              int device, char* err, size_t errcap) {
+  if (!tau || !alpha || !beta) { set_err(err, errcap, "null argument"); return SSO_E_ARG; }
+  return contribute_buf_core(p, challenge, challenge_len, response, response_len, tau, alpha, beta, pubkey, pubkey_len, nullptr,
+                             check_input, device, err, errcap);
 }
 
 // Several chunks in flight (the reference runs up to --max-in-process-lane chunks through its Process lane,
@@ -485,23 +516,22 @@ int32_t sso_p1_keygen(uint32_t curve, const uint8_t seed32[32], const uint8_t di
 int32_t sso_p1_contribute_seeded_buf(const sso_p1_params_t* p, const uint8_t* challenge, size_t challenge_len, uint8_t* response,
                                      size_t response_len, const uint8_t seed32[32], uint32_t check_input, int device, char* err,
                                      size_t errcap) {
-  P1Layout L;
-  int rc = p1_layout(p, L, err, errcap);
-  if (rc) return rc;
-  if (!challenge || !response || !seed32) { set_err(err, errcap, "null argument"); return SSO_E_ARG; }
-  if (challenge_len != L.acc_size) { set_err(err, errcap, "challenge has %zu bytes, expected accumulator_size %llu", challenge_len, (unsigned long long)L.acc_size); return SSO_E_ARG; }
-  if (response_len != L.contrib_size) { set_err(err, errcap, "response has %zu bytes, expected contribution_size %llu", response_len, (unsigned long long)L.contrib_size); return SSO_E_ARG; }
-  const CurveOps* ops = ops_for(p->curve);
-  uint8_t digest[64];
-  blake2b_512(challenge, challenge_len, digest);
-  std::vector<uint8_t> scalars(3 * L.cs.fr), pubkey(L.pk_size);
-  {
-    Ctx c(err, errcap);
-    if ((rc = c.init(device))) return rc;
-    if ((rc = keygen_host(c, ops, L.cs, seed32, digest, 3, scalars.data(), pubkey.data(), err, errcap))) return rc;
-  }
-  return sso_p1_contribute_buf(p, challenge, challenge_len, response, response_len, scalars.data(), scalars.data() + L.cs.fr,
-                               scalars.data() + 2 * L.cs.fr, pubkey.data(), pubkey.size(), check_input, device, err, errcap);
+  if (!seed32) { set_err(err, errcap, "null argument"); return SSO_E_ARG; }
+  return contribute_buf_core(p, challenge, challenge_len, response, response_len, nullptr, nullptr, nullptr, nullptr, 0, seed32,
+                             check_input, device, err, errcap);
+}
+
+// phase1_cli::contribute for several chunks in flight: the contributor applies the same seed-derived key to every
+// chunk it holds (src/bin/contribute.rs:789, 809-823); worker / device semantics of sso_p1_contribute_many_buf
+int32_t sso_p1_contribute_seeded_many_buf(const sso_p1_params_t* params, size_t n_chunks, const uint8_t* const* challenges,
+                                          const size_t* challenge_lens, uint8_t* const* responses, const size_t* response_lens,
+                                          const uint8_t seed32[32], uint32_t check_input, uint32_t host_threads, int device,
+                                          char* err, size_t errcap) {
+  if (!params || !challenges || !challenge_lens || !responses || !response_lens || !seed32) { set_err(err, errcap, "null argument"); return SSO_E_ARG; }
+  return run_chunks_in_flight(n_chunks, host_threads, device, err, errcap, [&](size_t i, int dev, char* e, size_t ec) {
+    return sso_p1_contribute_seeded_buf(&params[i], challenges[i], challenge_lens[i], responses[i], response_lens[i], seed32,
+                                        check_input, dev, e, ec);
+  });
 }
 
 // phase1_cli::contribute(challenge_fn, challenge_hash_fn, response_fn, response_hash_fn, check_input, batch_exp_mode, params, rng)

@@ -47,43 +47,70 @@ inline int write_new_file(const char* path, const uint8_t* data, size_t len, cha
 // ---- key generation (Phase1::key_generation) ---------------------------------------------------
 // seed32: ChaCha20 seed of the contributor RNG; digest64: Blake2b(challenge).
 // scalars_out: nscalars canonical scalars (fr_bytes each); pubkey_out: 2*nscalars G1 + nscalars G2 uncompressed.
-inline int keygen_host(Ctx& c, const CurveOps* ops, const CurveSizes& cs, const uint8_t seed32[32], const uint8_t digest64[64],
-                       uint32_t nscalars, uint8_t* scalars_out, uint8_t* pubkey_out, char* err, size_t errcap) {
+// Key generation in two stages so that the digest-independent half can run before the challenge hash is known:
+//   stage 1 (seed only)   : the private scalars and the (s, s^x) G1 pairs of the proofs of knowledge — the RNG draws
+//   stage 2 (needs digest): compute_g2_s = hash_to_g2(Blake2b(personalization || digest || g1_s || g1_s_x)[..32]) and
+//                           its multiple by the scalar; the public key is the G1 pairs followed by the G2 points
+struct KeygenState {
+  uint32_t nscalars = 0;
+  uint32_t *d_scalars = nullptr, *d_seeds2 = nullptr;
+  uint8_t *d_g2s = nullptr, *d_g2sx = nullptr;
+  std::vector<uint8_t> g1, seeds2;
+  std::vector<uint32_t> sc;
+};
+inline int keygen_stage1(Ctx& c, const CurveOps* ops, const CurveSizes& cs, const uint8_t seed32[32], uint32_t nscalars,
+                         KeygenState& k, uint8_t* scalars_out, char* err, size_t errcap) {
   int rc;
-  uint32_t *d_seed, *d_scalars, *d_seeds2;
-  uint8_t *d_g1, *d_g2s, *d_g2sx;
+  uint32_t* d_seed;
+  uint8_t* d_g1;
   const size_t g1u = cs.g1u, g2u = cs.g2u;
+  k.nscalars = nscalars;
   if ((rc = c.alloc((void**)&d_seed, 32))) return rc;
-  if ((rc = c.alloc((void**)&d_scalars, (size_t)nscalars * ops->fr_words * 4))) return rc;
+  if ((rc = c.alloc((void**)&k.d_scalars, (size_t)nscalars * ops->fr_words * 4))) return rc;
   if ((rc = c.alloc((void**)&d_g1, 2 * nscalars * g1u))) return rc;
-  if ((rc = c.alloc((void**)&d_seeds2, (size_t)nscalars * 32))) return rc;
-  if ((rc = c.alloc((void**)&d_g2s, nscalars * g2u))) return rc;
-  if ((rc = c.alloc((void**)&d_g2sx, nscalars * g2u))) return rc;
+  if ((rc = c.alloc((void**)&k.d_seeds2, (size_t)nscalars * 32))) return rc;
+  if ((rc = c.alloc((void**)&k.d_g2s, nscalars * g2u))) return rc;
+  if ((rc = c.alloc((void**)&k.d_g2sx, nscalars * g2u))) return rc;
   CUDA_TRY(cudaMemcpyAsync(d_seed, seed32, 32, cudaMemcpyHostToDevice, c.s[0]));
-  if ((rc = ops->keygen_g1(c, 0, d_seed, nscalars, d_scalars, d_g1, err, errcap))) return rc;
-  std::vector<uint8_t> g1(2 * nscalars * g1u);
-  std::vector<uint32_t> sc((size_t)nscalars * ops->fr_words);
-  CUDA_TRY(cudaMemcpyAsync(g1.data(), d_g1, g1.size(), cudaMemcpyDeviceToHost, c.s[0]));
-  CUDA_TRY(cudaMemcpyAsync(sc.data(), d_scalars, sc.size() * 4, cudaMemcpyDeviceToHost, c.s[0]));
+  if ((rc = ops->keygen_g1(c, 0, d_seed, nscalars, k.d_scalars, d_g1, err, errcap))) return rc;
+  k.g1.resize(2 * nscalars * g1u);
+  k.sc.resize((size_t)nscalars * ops->fr_words);
+  CUDA_TRY(cudaMemcpyAsync(k.g1.data(), d_g1, k.g1.size(), cudaMemcpyDeviceToHost, c.s[0]));
+  CUDA_TRY(cudaMemcpyAsync(k.sc.data(), k.d_scalars, k.sc.size() * 4, cudaMemcpyDeviceToHost, c.s[0]));
   CUDA_TRY(cudaStreamSynchronize(c.s[0]));
+  for (uint32_t i = 0; i < nscalars; i++)
+    memcpy(scalars_out + (size_t)i * ops->fr_bytes, k.sc.data() + (size_t)i * ops->fr_words, ops->fr_bytes);
+  return SSO_OK;
+}
+// enqueues on stream si (which must be ordered after stage 1: same context); pubkey_out is complete once si drained
+inline int keygen_stage2(Ctx& c, int si, const CurveOps* ops, const CurveSizes& cs, const uint8_t digest64[64], KeygenState& k,
+                         uint8_t* pubkey_out, char* err, size_t errcap) {
+  int rc;
+  const size_t g1u = cs.g1u, g2u = cs.g2u;
   // compute_g2_s: Blake2b(personalization || digest || g1_s || g1_s_x)[..32] seeds hash_to_g2
-  std::vector<uint8_t> seeds2((size_t)nscalars * 32);
-  for (uint32_t i = 0; i < nscalars; i++) {
+  k.seeds2.resize((size_t)k.nscalars * 32);
+  for (uint32_t i = 0; i < k.nscalars; i++) {
     Blake2b h(64);
     uint8_t pers = (uint8_t)i, full[64];
     h.update(&pers, 1);
     h.update(digest64, 64);
-    h.update(g1.data() + (size_t)2 * i * g1u, 2 * g1u);
+    h.update(k.g1.data() + (size_t)2 * i * g1u, 2 * g1u);
     h.final(full, 64);
-    memcpy(seeds2.data() + 32 * i, full, 32);
+    memcpy(k.seeds2.data() + 32 * i, full, 32);
   }
-  CUDA_TRY(cudaMemcpyAsync(d_seeds2, seeds2.data(), seeds2.size(), cudaMemcpyHostToDevice, c.s[0]));
-  if ((rc = ops->hash_to_g2(c, 0, nscalars, d_seeds2, d_scalars, d_g2s, d_g2sx, err, errcap))) return rc;
-  memcpy(pubkey_out, g1.data(), g1.size());
-  CUDA_TRY(cudaMemcpyAsync(pubkey_out + g1.size(), d_g2sx, nscalars * g2u, cudaMemcpyDeviceToHost, c.s[0]));
+  CUDA_TRY(cudaMemcpyAsync(k.d_seeds2, k.seeds2.data(), k.seeds2.size(), cudaMemcpyHostToDevice, c.s[si]));
+  if ((rc = ops->hash_to_g2(c, si, k.nscalars, k.d_seeds2, k.d_scalars, k.d_g2s, k.d_g2sx, err, errcap))) return rc;
+  memcpy(pubkey_out, k.g1.data(), k.g1.size());
+  CUDA_TRY(cudaMemcpyAsync(pubkey_out + k.g1.size(), k.d_g2sx, k.nscalars * g2u, cudaMemcpyDeviceToHost, c.s[si]));
+  return SSO_OK;
+}
+inline int keygen_host(Ctx& c, const CurveOps* ops, const CurveSizes& cs, const uint8_t seed32[32], const uint8_t digest64[64],
+                       uint32_t nscalars, uint8_t* scalars_out, uint8_t* pubkey_out, char* err, size_t errcap) {
+  KeygenState k;
+  int rc;
+  if ((rc = keygen_stage1(c, ops, cs, seed32, nscalars, k, scalars_out, err, errcap))) return rc;
+  if ((rc = keygen_stage2(c, 0, ops, cs, digest64, k, pubkey_out, err, errcap))) return rc;
   CUDA_TRY(cudaStreamSynchronize(c.s[0]));
-  for (uint32_t i = 0; i < nscalars; i++)
-    memcpy(scalars_out + (size_t)i * ops->fr_bytes, sc.data() + (size_t)i * ops->fr_words, ops->fr_bytes);
   return SSO_OK;
 }
 

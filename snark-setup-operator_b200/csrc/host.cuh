@@ -103,7 +103,8 @@ extern std::atomic<int> g_prof_enabled;
 struct Ctx {
   int dev = -1, prev = -1;
   bool aliased = false;
-  cudaStream_t s[2] = {nullptr, nullptr};
+  cudaStream_t s[3] = {nullptr, nullptr, nullptr};    // s[2] (when asked for) has the highest priority: short latency-critical kernels
+  bool owned[3] = {false, false, false};
   std::vector<void*> allocs;
   std::vector<std::vector<uint32_t>> staging;     // host copies that must outlive async H2D
   struct Timed { int kind; cudaEvent_t e0, e1; };
@@ -150,8 +151,14 @@ struct Ctx {
     // profiling mode 2 serialises the call on ONE stream so that per-kernel event times are not inflated by
     // kernels of the other stream sharing the SMs (used for the roofline pass of bench.py)
     aliased = nstreams > 1 && g_prof_enabled.load(std::memory_order_relaxed) == 2;
-    for (int i = 0; i < (aliased ? 1 : nstreams); i++) CUDA_TRY(cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking));
-    if (aliased) s[1] = s[0];
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);                 // hi = numerically lowest = highest priority
+    for (int i = 0; i < (aliased ? 1 : nstreams) && i < 3; i++) {
+      if (i == 2) CUDA_TRY(cudaStreamCreateWithPriority(&s[i], cudaStreamNonBlocking, hi));
+      else CUDA_TRY(cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking));
+      owned[i] = true;
+    }
+    if (aliased) for (int i = 1; i < nstreams && i < 3; i++) s[i] = s[0];
     mark("init: device + streams");
     return SSO_OK;
   }
@@ -200,8 +207,7 @@ struct Ctx {
       resolve_timings();
       mark("dtor: streams drained");
       for (void* p : allocs) cudaFreeAsync(p, s[0]);
-      if (aliased) s[1] = nullptr;
-      for (auto& st : s) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+      for (int i = 0; i < 3; i++) if (s[i] && owned[i]) { cudaStreamSynchronize(s[i]); cudaStreamDestroy(s[i]); }
       if (prev >= 0) cudaSetDevice(prev);
       mark("dtor: freed + destroyed");
     }

@@ -180,6 +180,22 @@ def contribute_many_buf(params_list, challenges, responses, tau: int, alpha: int
     return responses
 
 
+def contribute_seeded_many_buf(params_list, challenges, responses, seed32: bytes, check=CHECK_NONZERO, host_threads=0, device=0):
+    """contribute_seeded_buf (key generation, proofs of knowledge, computation) over several chunks in flight with the same
+    seed-derived key, as the contributor does for the chunks it holds (src/bin/contribute.rs:789, 809-823)."""
+    n = len(params_list)
+    if not (len(challenges) == len(responses) == n):
+        raise SsoError(-1, "params, challenges and responses must have the same length")
+    if n == 0:
+        return responses
+    P = (_lib.P1Params * n)(*[p.c_struct() for p in params_list])
+    ch_p, ch_l, k1 = _ptr_arrays(challenges)
+    rs_p, rs_l, k2 = _ptr_arrays(responses)
+    call("sso_p1_contribute_seeded_many_buf", P, n, ch_p, ch_l, rs_p, rs_l, seed32, check, host_threads, device)
+    del k1, k2
+    return responses
+
+
 def verify_chunk_many_buf(params_list, challenges, responses, new_challenges, check_input=CHECK_NO, check_output=CHECK_FULL,
                           subgroup_check_mode=0, ratio_check=True, rlc_seed32=None, host_threads=0, device=0):
     """verify_chunk_buf over several chunks in flight: the chunk loop of verify_transcript (src/bin/verify_transcript.rs:293-569)

@@ -51,6 +51,19 @@ def test_verify_accepts_honest_contribution(name, k):
         assert phase1.verify_chunk(o, ch, resp, rlc_seed32=bytes(range(32))) == bytes(new_ch)
 
 
+def test_full_contribute_many_chunks_in_flight():
+    """sso_p1_contribute_seeded_many_buf = phase1_cli::contribute per chunk (same seed-derived key, per-chunk proofs of knowledge)"""
+    ks = [0, 1, 3, 1]
+    os_ = [Phase1Params.new_chunk("bls12_377", k, 4, 3, 4) for k in ks]
+    ps = [sso.Phase1Parameters.new_chunk("bls12_377", k, 4, 3, 4) for k in ks]
+    chs = [synth.synthetic_challenge(o) for o in os_]
+    resps = [bytearray(o.contribution_size) for o in os_]
+    sso.contribute_seeded_many_buf(ps, chs, resps, synth.SEED_CONTRIB, host_threads=4)
+    for o, ch, r in zip(os_, chs, resps):
+        want, _, _ = phase1.contribute(o, ch, ChaChaRng(synth.SEED_CONTRIB))
+        assert bytes(r) == want
+
+
 def test_verify_many_chunks_in_flight():
     """sso_p1_verify_chunk_many_buf: the chunk loop of verify_transcript as a work queue — same new challenges as the
     single-chunk call, and a bad chunk in the batch is reported with its index."""
