@@ -401,7 +401,7 @@ static int32_t contribute_buf_core(const sso_p1_params_t* p, const uint8_t* chal
   if (seed32) {
     hasher = std::thread([=] { blake2b_512(challenge, challenge_len, response); });
     scalars.resize(3 * (size_t)L.cs.fr);
-    if ((rc = keygen_stage1(c, ops, L.cs, seed32, 3, keys, scalars.data(), err, errcap))) return rc;
+    if ((rc = keygen_stage1(c, 2, ops, L.cs, seed32, 3, keys, scalars.data(), err, errcap))) return rc;   // high-priority stream: not queued behind other chunks' kernels
     tau = scalars.data();
     alpha = scalars.data() + L.cs.fr;
     beta = scalars.data() + 2 * (size_t)L.cs.fr;

@@ -266,7 +266,13 @@ inline int run_same_ratio(Ctx& c, int si, const uint8_t* d_checks, uint64_t n, u
 
 template <class G1>
 __global__ void k_keygen_g1(const uint32_t* seed, uint32_t nscalars, uint32_t* scalars_out, uint8_t* g1_out) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) body_keygen_g1<G1>(seed, nscalars, scalars_out, g1_out);
+  // thread 0 draws from the RNG; then the first lane of warp i finishes proof i (cofactor clearing, [x]s): the three long
+  // single-thread chains run side by side instead of one after the other
+  __shared__ typename SW<G1>::Affine raw[3];
+  if (threadIdx.x == 0) keygen_g1_sample<G1>(seed, nscalars, scalars_out, raw);
+  __syncthreads();
+  uint32_t i = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0 && i < nscalars) keygen_g1_finish<G1>(i, raw[i], scalars_out, g1_out);
 }
 template <class G2>
 __global__ void k_hash_to_g2(uint32_t n, const uint32_t* seeds, const uint32_t* scalars, uint8_t* g2_s, uint8_t* g2_sx) {
@@ -401,7 +407,7 @@ template <class G1, class G2, class PP> struct CurveImpl {
   static int keygen_g1(Ctx& c, int si, const uint32_t* d_seed, uint32_t nscalars, uint32_t* d_scalars, uint8_t* d_g1, char* err, size_t errcap) {
     if (nscalars < 1 || nscalars > 3) { set_err(err, errcap, "keygen: 1..3 scalars"); return SSO_E_ARG; }
     c.begin(PK_OTHER, si, nscalars);
-    k_keygen_g1<G1><<<1, 32, 0, c.s[si]>>>(d_seed, nscalars, d_scalars, d_g1);
+    k_keygen_g1<G1><<<1, 96, 0, c.s[si]>>>(d_seed, nscalars, d_scalars, d_g1);
     c.end(si);
     CUDA_TRY(cudaGetLastError());
     return SSO_OK;

@@ -58,31 +58,31 @@ struct KeygenState {
   std::vector<uint8_t> g1, seeds2;
   std::vector<uint32_t> sc;
 };
-inline int keygen_stage1(Ctx& c, const CurveOps* ops, const CurveSizes& cs, const uint8_t seed32[32], uint32_t nscalars,
+inline int keygen_stage1(Ctx& c, int si, const CurveOps* ops, const CurveSizes& cs, const uint8_t seed32[32], uint32_t nscalars,
                          KeygenState& k, uint8_t* scalars_out, char* err, size_t errcap) {
   int rc;
   uint32_t* d_seed;
   uint8_t* d_g1;
   const size_t g1u = cs.g1u, g2u = cs.g2u;
   k.nscalars = nscalars;
-  if ((rc = c.alloc((void**)&d_seed, 32))) return rc;
-  if ((rc = c.alloc((void**)&k.d_scalars, (size_t)nscalars * ops->fr_words * 4))) return rc;
-  if ((rc = c.alloc((void**)&d_g1, 2 * nscalars * g1u))) return rc;
-  if ((rc = c.alloc((void**)&k.d_seeds2, (size_t)nscalars * 32))) return rc;
-  if ((rc = c.alloc((void**)&k.d_g2s, nscalars * g2u))) return rc;
-  if ((rc = c.alloc((void**)&k.d_g2sx, nscalars * g2u))) return rc;
-  CUDA_TRY(cudaMemcpyAsync(d_seed, seed32, 32, cudaMemcpyHostToDevice, c.s[0]));
-  if ((rc = ops->keygen_g1(c, 0, d_seed, nscalars, k.d_scalars, d_g1, err, errcap))) return rc;
+  if ((rc = c.alloc((void**)&d_seed, 32, si))) return rc;
+  if ((rc = c.alloc((void**)&k.d_scalars, (size_t)nscalars * ops->fr_words * 4, si))) return rc;
+  if ((rc = c.alloc((void**)&d_g1, 2 * nscalars * g1u, si))) return rc;
+  if ((rc = c.alloc((void**)&k.d_seeds2, (size_t)nscalars * 32, si))) return rc;
+  if ((rc = c.alloc((void**)&k.d_g2s, nscalars * g2u, si))) return rc;
+  if ((rc = c.alloc((void**)&k.d_g2sx, nscalars * g2u, si))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(d_seed, seed32, 32, cudaMemcpyHostToDevice, c.s[si]));
+  if ((rc = ops->keygen_g1(c, si, d_seed, nscalars, k.d_scalars, d_g1, err, errcap))) return rc;
   k.g1.resize(2 * nscalars * g1u);
   k.sc.resize((size_t)nscalars * ops->fr_words);
-  CUDA_TRY(cudaMemcpyAsync(k.g1.data(), d_g1, k.g1.size(), cudaMemcpyDeviceToHost, c.s[0]));
-  CUDA_TRY(cudaMemcpyAsync(k.sc.data(), k.d_scalars, k.sc.size() * 4, cudaMemcpyDeviceToHost, c.s[0]));
-  CUDA_TRY(cudaStreamSynchronize(c.s[0]));
+  CUDA_TRY(cudaMemcpyAsync(k.g1.data(), d_g1, k.g1.size(), cudaMemcpyDeviceToHost, c.s[si]));
+  CUDA_TRY(cudaMemcpyAsync(k.sc.data(), k.d_scalars, k.sc.size() * 4, cudaMemcpyDeviceToHost, c.s[si]));
+  CUDA_TRY(cudaStreamSynchronize(c.s[si]));
   for (uint32_t i = 0; i < nscalars; i++)
     memcpy(scalars_out + (size_t)i * ops->fr_bytes, k.sc.data() + (size_t)i * ops->fr_words, ops->fr_bytes);
   return SSO_OK;
 }
-// enqueues on stream si (which must be ordered after stage 1: same context); pubkey_out is complete once si drained
+// enqueues on stream si (the stream stage 1 ran on); pubkey_out is complete once si drained
 inline int keygen_stage2(Ctx& c, int si, const CurveOps* ops, const CurveSizes& cs, const uint8_t digest64[64], KeygenState& k,
                          uint8_t* pubkey_out, char* err, size_t errcap) {
   int rc;
@@ -108,7 +108,7 @@ inline int keygen_host(Ctx& c, const CurveOps* ops, const CurveSizes& cs, const 
                        uint32_t nscalars, uint8_t* scalars_out, uint8_t* pubkey_out, char* err, size_t errcap) {
   KeygenState k;
   int rc;
-  if ((rc = keygen_stage1(c, ops, cs, seed32, nscalars, k, scalars_out, err, errcap))) return rc;
+  if ((rc = keygen_stage1(c, 0, ops, cs, seed32, nscalars, k, scalars_out, err, errcap))) return rc;
   if ((rc = keygen_stage2(c, 0, ops, cs, digest64, k, pubkey_out, err, errcap))) return rc;
   CUDA_TRY(cudaStreamSynchronize(c.s[0]));
   return SSO_OK;

@@ -47,8 +47,9 @@ template <class F> __device__ __forceinline__ typename F::T field_rand(ChaChaStr
   else { typename F::T r; r.c0 = fp_rand<typename F::Base>(rng); r.c1 = fp_rand<typename F::Base>(rng); r.c2 = fp_rand<typename F::Base>(rng); return r; }
 }
 
-// ark-ec Projective::rand
-template <class G> __device__ __noinline__ typename SW<G>::Jac group_rand(ChaChaStream& rng) {
+// ark-ec Projective::rand, first half: the curve point before the cofactor is cleared (the acceptance test — is
+// x^3 + ax + b a square — decides how many words the RNG hands out, so this part is sequential in the RNG)
+template <class G> __device__ __noinline__ typename SW<G>::Affine group_rand_point(ChaChaStream& rng) {
   using C = SW<G>;
   using F = typename G::F;
   for (;;) {
@@ -57,9 +58,12 @@ template <class G> __device__ __noinline__ typename SW<G>::Jac group_rand(ChaCha
     typename F::T y;
     if (!G::field_sqrt(C::rhs(x), y)) continue;
     if (F::lex_is_neg(y) != greatest) y = F::neg(y);
-    typename C::Affine p{x, y, false};
-    return C::mul_const(p, G::cofactor(), G::COFACTOR_WORDS);
+    return typename C::Affine{x, y, false};
   }
+}
+template <class G> __device__ __forceinline__ typename SW<G>::Jac group_rand(ChaChaStream& rng) {
+  typename SW<G>::Affine p = group_rand_point<G>(rng);
+  return SW<G>::mul_const(p, G::cofactor(), G::COFACTOR_WORDS);
 }
 
 template <class G> __device__ __forceinline__ typename SW<G>::Affine jac_to_affine(const typename SW<G>::Jac& j) {
@@ -71,30 +75,42 @@ template <class G> __device__ __forceinline__ typename SW<G>::Affine jac_to_affi
   return a;
 }
 
-// Thread 0: tau, alpha, beta <- Fr::rand; for each x: g1_s <- G1::rand, g1_s_x = x g1_s.
+// Key generation, G1 half: tau, alpha, beta <- Fr::rand; for each scalar x: g1_s <- G1::rand, g1_s_x = x g1_s.
 //   scalars_out : 3 canonical scalars, Fr::L words each
 //   g1_out      : g1_s(tau) | g1_s_x(tau) | g1_s(alpha) | ... uncompressed (public-key order)
-// nscalars = 3 for phase 1 (tau, alpha, beta), 1 for phase 2 (delta)
+// nscalars = 3 for phase 1 (tau, alpha, beta), 1 for phase 2 (delta).
+// Two steps so that the kernel can hand the long group operations of the three proofs to three warps:
+//   sample (one thread, sequential in the RNG): the scalars and the three curve points before cofactor clearing
+//   finish (independent per scalar)           : cofactor clearing, multiplication by the scalar, serialisation
 template <class G1>
-__device__ __forceinline__ void body_keygen_g1(const uint32_t* seed, uint32_t nscalars, uint32_t* scalars_out, uint8_t* g1_out) {
-  using C = SW<G1>;
+__device__ __forceinline__ void keygen_g1_sample(const uint32_t* seed, uint32_t nscalars, uint32_t* scalars_out,
+                                                 typename SW<G1>::Affine* raw) {
   using Fr = typename G1::Fr;
   ChaChaStream rng;
   rng.init(seed);
-  typename Fr::T x[3];
   for (uint32_t i = 0; i < nscalars; i++) {
-    x[i] = fp_rand<Fr>(rng);
-    typename Fr::T c = Fr::from_mont(x[i]);
+    typename Fr::T c = Fr::from_mont(fp_rand<Fr>(rng));
     for (int w = 0; w < Fr::L; w++) scalars_out[i * Fr::L + w] = c.v[w];
   }
-  for (uint32_t i = 0; i < nscalars; i++) {
-    typename C::Affine s = jac_to_affine<G1>(group_rand<G1>(rng));
-    uint32_t k[Fr::L];
-    for (int w = 0; w < Fr::L; w++) k[w] = scalars_out[i * Fr::L + w];
-    typename C::Affine sx = jac_to_affine<G1>(C::template scalar_mul<Fr::L, Fr::P::BITS>(s, k));
-    C::write_uncompressed(g1_out + (size_t)(2 * i) * C::SIZE_U, s);
-    C::write_uncompressed(g1_out + (size_t)(2 * i + 1) * C::SIZE_U, sx);
-  }
+  for (uint32_t i = 0; i < nscalars; i++) raw[i] = group_rand_point<G1>(rng);
+}
+template <class G1>
+__device__ __forceinline__ void keygen_g1_finish(uint32_t i, const typename SW<G1>::Affine& raw, const uint32_t* scalars, uint8_t* g1_out) {
+  using C = SW<G1>;
+  using Fr = typename G1::Fr;
+  typename C::Affine s = jac_to_affine<G1>(C::mul_const(raw, G1::cofactor(), G1::COFACTOR_WORDS));
+  uint32_t k[Fr::L];
+  for (int w = 0; w < Fr::L; w++) k[w] = scalars[i * Fr::L + w];
+  typename C::Affine sx = jac_to_affine<G1>(C::template scalar_mul<Fr::L, Fr::P::BITS>(s, k));
+  C::write_uncompressed(g1_out + (size_t)(2 * i) * C::SIZE_U, s);
+  C::write_uncompressed(g1_out + (size_t)(2 * i + 1) * C::SIZE_U, sx);
+}
+// single-thread form (emulation harness)
+template <class G1>
+__device__ __forceinline__ void body_keygen_g1(const uint32_t* seed, uint32_t nscalars, uint32_t* scalars_out, uint8_t* g1_out) {
+  typename SW<G1>::Affine raw[3];
+  keygen_g1_sample<G1>(seed, nscalars, scalars_out, raw);
+  for (uint32_t i = 0; i < nscalars; i++) keygen_g1_finish<G1>(i, raw[i], scalars_out, g1_out);
 }
 
 // Thread i: g2_s = G2::rand(ChaCha20(seeds[i])); optionally g2_s_x = scalars[i] * g2_s.
