@@ -120,8 +120,8 @@ inline int run_batch_exp_chunk(Ctx& c, int si, const VecBatch& b1, const VecBatc
   uint32_t nb2 = div_up(n2, EXP_BLOCK), nb1 = div_up(n1, EXP_BLOCK);
   constexpr size_t TREE_BYTES = 2 * EXP_BLOCK * (sizeof(typename G1::F::T) > sizeof(typename G2::F::T) ? sizeof(typename G1::F::T)
                                                                                                         : sizeof(typename G2::F::T));
-  static std::atomic<int> smem_set{0};
-  if (TREE_BYTES > 48 * 1024 && !smem_set.exchange(1))
+  // per device and cheap: set on every call (a process-wide "done" flag would leave the other GPUs of the box unset)
+  if (TREE_BYTES > 48 * 1024)
     CUDA_TRY(cudaFuncSetAttribute(k_batch_exp_chunk<G1, G2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TREE_BYTES));
   c.begin(PK_BATCH_EXP_CHUNK, si, n1 + n2);
   k_batch_exp_chunk<G1, G2><<<nb1 + nb2, EXP_BLOCK, TREE_BYTES, st>>>(b1, b2, nb2, in_compressed, d_table, check, d_jac1, d_jac2, d_status);
@@ -172,8 +172,7 @@ inline int run_batch_exp(Ctx& c, int si, const VecBatch& batch, uint32_t in_comp
   if ((rc = c.alloc((void**)&d_jac, (size_t)n * 3 * F::WORDS * 4, si))) return rc;
   constexpr bool IS_G1 = G::GROUP == 0;
   constexpr size_t TREE_BYTES = 2 * EXP_BLOCK * sizeof(typename F::T);
-  static std::atomic<int> smem_set{0};
-  if (TREE_BYTES > 48 * 1024 && !smem_set.exchange(1))
+  if (TREE_BYTES > 48 * 1024)
     CUDA_TRY(cudaFuncSetAttribute(k_batch_exp<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TREE_BYTES));
   c.begin(IS_G1 ? PK_BATCH_EXP_G1 : PK_BATCH_EXP_G2, si, n);
   k_batch_exp<G><<<div_up(n, EXP_BLOCK), EXP_BLOCK, TREE_BYTES, st>>>(batch, in_compressed, d_table, check, d_jac, d_status);
