@@ -305,7 +305,7 @@ inline int run_points_sum(Ctx& c, int si, const uint8_t* d_points, uint32_t n, u
 inline uint32_t msm_window_bits(uint64_t n) {
   uint32_t lg = 0;
   while ((2ull << lg) <= n) lg++;
-  int c = (int)lg - 6;
+  int c = (int)lg - 5;        // 2^5 points per bucket on average: the bucket phase is one thread per bucket and latency-bound
   return (uint32_t)(c < 4 ? 4 : (c > 14 ? 14 : c));
 }
 

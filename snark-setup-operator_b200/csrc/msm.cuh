@@ -159,18 +159,6 @@ __device__ __forceinline__ void body_msm_fold(uint32_t tid, uint32_t nwin, uint3
   store_jac<G>(seg_out + (size_t)tid * 6 * F::WORDS + 3 * F::WORDS, acc);
 }
 
-// small-scalar multiplication by double-and-add (k < 2^16)
-template <class G>
-__device__ __forceinline__ typename SW<G>::Jac mul_small_scalar(const typename SW<G>::Jac& p, uint32_t k) {
-  using C = SW<G>;
-  typename C::Jac r = C::identity();
-  for (int i = 15; i >= 0; i--) {
-    r = C::dbl(r);
-    if ((k >> i) & 1) r = C::add(r, p);
-  }
-  return r;
-}
-
 // One thread per (vector, window): window sum = sum_s (T_s + s*SEG * S_s)
 template <class G>
 __device__ __forceinline__ void body_msm_window(uint32_t tid, uint32_t nwin, uint32_t c, const uint32_t* seg_in, uint32_t* win_out) {
@@ -180,13 +168,19 @@ __device__ __forceinline__ void body_msm_window(uint32_t tid, uint32_t nwin, uin
   uint32_t seg = nb < MSM_SEG ? nb : MSM_SEG;
   uint32_t nseg = nb / seg;
   if (tid >= 2 * nwin) return;
-  typename C::Jac total = C::identity();
-  for (uint32_t s = 0; s < nseg; s++) {
+  // window sum = sum_s T_s + seg * sum_{s >= 1} s * S_s : the second term by the running-sum trick over the segments
+  // (two additions per segment) and log2(seg) doublings at the end, instead of one 16-bit scalar multiplication per segment
+  typename C::Jac tsum = C::identity(), run = C::identity(), acc = C::identity();
+  for (int s = (int)nseg - 1; s >= 0; s--) {
     const uint32_t* p = seg_in + ((size_t)tid * nseg + s) * 6 * F::WORDS;
-    typename C::Jac S = load_jac<G>(p), T = load_jac<G>(p + 3 * F::WORDS);
-    total = C::add(total, T);
-    if (s) total = C::add(total, mul_small_scalar<G>(S, s * seg));
+    tsum = C::add(tsum, load_jac<G>(p + 3 * F::WORDS));
+    if (s >= 1) {
+      run = C::add(run, load_jac<G>(p));
+      acc = C::add(acc, run);
+    }
   }
+  for (uint32_t b = 1; b < seg; b <<= 1) acc = C::dbl(acc);
+  typename C::Jac total = C::add(tsum, acc);
   store_jac<G>(win_out + (size_t)tid * 3 * F::WORDS, total);
 }
 

@@ -233,7 +233,7 @@ def test_multi_vector_launch(emul, name, gi):
     assert out0.raw == want0 and out1.raw == want1 and st[0] == 0
 
 
-@pytest.mark.parametrize("name,gi,wb", [("bls12_377", 0, 4), ("bls12_377", 1, 7), ("bw6_761", 0, 5), ("mnt4_753", 0, 6)])
+@pytest.mark.parametrize("name,gi,wb", [("bls12_377", 0, 4), ("bls12_377", 1, 7), ("bls12_377", 0, 9), ("bw6_761", 0, 5), ("mnt4_753", 0, 6)])
 def test_power_pairs_msm(emul, name, gi, wb):
     """Pippenger pipeline (keys, buckets, segmented fold, window sums, Horner) against the oracle's
     plain sum r_i P_i with the same ChaCha20-derived scalars."""
