@@ -108,7 +108,10 @@ __device__ __forceinline__ void scalar_for_index(const uint32_t* table, uint32_t
 //   tree : 2 * BS field elements; the leaf of thread t sits at tree[BS + t] and is replaced by its inverse.
 // Leaves must be non-zero.  tree_up / tree_down are the per-thread steps (also driven by tests/emul).
 // ---------------------------------------------------------------------------------------------
-static constexpr int EXP_BLOCK = 128;
+#ifndef SSO_EXP_BLOCK
+#define SSO_EXP_BLOCK 128
+#endif
+static constexpr int EXP_BLOCK = SSO_EXP_BLOCK;        // threads (= points) per block of the batch_exp kernels: one field inversion per block
 
 template <class F> __device__ __forceinline__ void tree_up(typename F::T* tree, int n, int t) {
   if (t < n) tree[n + t] = F::mul(tree[2 * (n + t)], tree[2 * (n + t) + 1]);
