@@ -6,9 +6,10 @@
 // ladder (w = 4, digits in [-8, 7], table 1P..8P) — the scalar multiple is mathematically the
 // same point, and results are compared after normalisation to affine.
 //
-// Field-multiplication counts (S = M), used by the roofline in DESIGN.md:
-//   dbl  (a = 0)  7 M      dbl (a != 0)  9 M + mul_a
-//   madd          11 M     add           16 M
+// Field-operation counts used by the roofline in DESIGN.md / bench.py::declared_work_per_point (M = multiplication,
+// S = squaring, counted separately because prime fields of up to 12 limbs use the dedicated squaring):
+//   dbl  (a = 0)  2 M + 5 S     dbl (a != 0)  1 M + 8 S + mul_a
+//   madd          7 M + 4 S     add           11 M + 5 S
 #pragma once
 #include "ext.cuh"
 

@@ -9,6 +9,11 @@
 // ("even" and "odd" accumulators) so that every 32x32->64 product lands in an adjacent register
 // pair and ptxas can emit one IMAD.WIDE-class instruction per product with the carry riding the
 // chain.  Work per multiplication: 2 L^2 + L multiply-accumulates.
+//
+// Attribution: the even/odd split of the CIOS rows (helpers mul_n / cmad_n / madc_n_rshift / mad_n_redc below) is the
+// well-known public formulation used by Supranational's sppark (ff/mont_t.cuh, Apache-2.0) and several GPU bigint
+// libraries after it; it is restated here from the published technique, not taken from /root/reference (which holds
+// no arithmetic).  The dedicated squaring, the run-time Montgomery factor and the out-of-line by-value policy are ours.
 #pragma once
 #include <cstdint>
 #include "constants.cuh"
