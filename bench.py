@@ -314,59 +314,63 @@ def main():
     sampler.stop_flag = True
     if sampler.is_alive():
         sampler.join(timeout=2)
-    # ---- end-to-end timing through the host-buffer entry point
-    # (a) one chunk per call: the latency of a single reference-facing call (hash of the 31 MB challenge on one core inside)
-    run_steps(step_e2e, 1, False)
-    barrier()
-    ms_e2e_single_total = run_steps(step_e2e, args.steps, True)
-    barrier()
-    h_resp_single = h_resp.clone()
-    # (a') the whole of phase1_cli::contribute on host buffers: key generation from the seed, proofs of knowledge, computation
-    step_seeded = lambda: sso.contribute_seeded_buf(p, h_ch, h_resp, bytes(range(32)), check=sso.CHECK_NONZERO, device=dev)
-    run_steps(step_seeded, 1, False)
-    ms_e2e_seeded_total = run_steps(step_seeded, args.steps, True)
-    barrier()
-    # (b) the headline: the same K steps with several chunks in flight (sso_p1_contribute_many_buf, the reference's
-    # Process lane): every step still copies its own challenge from pinned host memory and reads its own response back
-    n_resp = min(args.steps, 64)
-    h_resps = [torch.empty(contrib, dtype=torch.uint8).pin_memory() for _ in range(n_resp)]
+    quick = bool(os.environ.get("SSO_BENCH_QUICK"))       # kernel A/B runs: device-resident value + roofline pass only
+    ms_e2e_total = ms_e2e_single_total = ms_e2e_seeded_total = ms_e2e_seeded_many_total = float("nan")
+    e2e_same = None
+    if not quick:
+        # ---- end-to-end timing through the host-buffer entry point
+        # (a) one chunk per call: the latency of a single reference-facing call (hash of the 31 MB challenge on one core inside)
+        run_steps(step_e2e, 1, False)
+        barrier()
+        ms_e2e_single_total = run_steps(step_e2e, args.steps, True)
+        barrier()
+        h_resp_single = h_resp.clone()
+        # (a') the whole of phase1_cli::contribute on host buffers: key generation from the seed, proofs of knowledge, computation
+        step_seeded = lambda: sso.contribute_seeded_buf(p, h_ch, h_resp, bytes(range(32)), check=sso.CHECK_NONZERO, device=dev)
+        run_steps(step_seeded, 1, False)
+        ms_e2e_seeded_total = run_steps(step_seeded, args.steps, True)
+        barrier()
+        # (b) the headline: the same K steps with several chunks in flight (sso_p1_contribute_many_buf, the reference's
+        # Process lane): every step still copies its own challenge from pinned host memory and reads its own response back
+        n_resp = min(args.steps, 64)
+        h_resps = [torch.empty(contrib, dtype=torch.uint8).pin_memory() for _ in range(n_resp)]
 
-    def many(n):
-        done = 0
-        while done < n:
-            k = min(n_resp, n - done)
-            sso.contribute_many_buf([p] * k, [h_ch] * k, h_resps[:k], *mine, pubkey=pubkey, check=sso.CHECK_NONZERO, device=dev)
-            done += k
+        def many(n):
+            done = 0
+            while done < n:
+                k = min(n_resp, n - done)
+                sso.contribute_many_buf([p] * k, [h_ch] * k, h_resps[:k], *mine, pubkey=pubkey, check=sso.CHECK_NONZERO, device=dev)
+                done += k
 
-    many(min(3, args.steps))
-    flush.zero_()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    many(args.steps)
-    e1.record()
-    e1.synchronize()
-    ms_e2e_total = e0.elapsed_time(e1)
-    barrier()
-    e2e_same = all(torch.equal(h_resps[i], h_resp_single) for i in range(n_resp))
-    # (b') the same with the full call (key generation + proofs of knowledge per chunk), six host workers
-    def many_seeded(n):
-        done = 0
-        while done < n:
-            k = min(n_resp, n - done)
-            sso.contribute_seeded_many_buf([p] * k, [h_ch] * k, h_resps[:k], bytes(range(32)), check=sso.CHECK_NONZERO, host_threads=6,
-                                           device=dev)
-            done += k
+        many(min(3, args.steps))
+        flush.zero_()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        many(args.steps)
+        e1.record()
+        e1.synchronize()
+        ms_e2e_total = e0.elapsed_time(e1)
+        barrier()
+        e2e_same = all(torch.equal(h_resps[i], h_resp_single) for i in range(n_resp))
+        # (b') the same with the full call (key generation + proofs of knowledge per chunk), six host workers
+        def many_seeded(n):
+            done = 0
+            while done < n:
+                k = min(n_resp, n - done)
+                sso.contribute_seeded_many_buf([p] * k, [h_ch] * k, h_resps[:k], bytes(range(32)), check=sso.CHECK_NONZERO, host_threads=6,
+                                               device=dev)
+                done += k
 
-    many_seeded(min(4, args.steps))
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    many_seeded(args.steps)
-    e1.record()
-    e1.synchronize()
-    ms_e2e_seeded_many_total = e0.elapsed_time(e1)
-    barrier()
+        many_seeded(min(4, args.steps))
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        many_seeded(args.steps)
+        e1.record()
+        e1.synchronize()
+        ms_e2e_seeded_many_total = e0.elapsed_time(e1)
+        barrier()
     sampler.stop_flag = True
     if sampler.is_alive():
         sampler.join(timeout=2)

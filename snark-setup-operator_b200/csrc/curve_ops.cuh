@@ -58,8 +58,22 @@ __global__ void k_tau_tables(const uint32_t* tau_canon, const uint32_t* coeff_ca
 #ifndef SSO_EXP_MIN_BLOCKS
 #define SSO_EXP_MIN_BLOCKS 1
 #endif
+// Resident blocks per SM the register allocation of the single-group kernels aims at, per group (the G1 bodies need far
+// fewer registers than the extension-field G2 bodies; a lower register cap buys warps per scheduler to hide the
+// fixed-latency dependencies of the carry chains)
+#ifndef SSO_EXP_MIN_BLOCKS_G1
+#define SSO_EXP_MIN_BLOCKS_G1 SSO_EXP_MIN_BLOCKS
+#endif
+#ifndef SSO_EXP_MIN_BLOCKS_G2
+#define SSO_EXP_MIN_BLOCKS_G2 SSO_EXP_MIN_BLOCKS
+#endif
+// 1: the two groups of a chunk run as two single-group kernels on two streams (each with its own register budget)
+// instead of the one fused launch
+#ifndef SSO_SPLIT_GROUPS
+#define SSO_SPLIT_GROUPS 0
+#endif
 template <class G>
-__global__ void __launch_bounds__(128, SSO_EXP_MIN_BLOCKS) k_batch_exp(const __grid_constant__ VecBatch batch, uint32_t in_compressed,
+__global__ void __launch_bounds__(128, (G::GROUP == 0 ? SSO_EXP_MIN_BLOCKS_G1 : SSO_EXP_MIN_BLOCKS_G2)) k_batch_exp(const __grid_constant__ VecBatch batch, uint32_t in_compressed,
                                                     const uint32_t* table, uint32_t check, uint32_t* jac_out, uint32_t* status) {
   extern __shared__ __align__(16) unsigned char tree_raw[];          // 2 * EXP_BLOCK field elements (dynamic: up to 72 KB)
   block_batch_exp<G>(blockIdx.x, batch, in_compressed, table, check, jac_out, status, reinterpret_cast<typename G::F::T*>(tree_raw));
@@ -123,9 +137,31 @@ inline int run_batch_exp_chunk(Ctx& c, int si, const VecBatch& b1, const VecBatc
   // per device and cheap: set on every call (a process-wide "done" flag would leave the other GPUs of the box unset)
   if (TREE_BYTES > 48 * 1024)
     CUDA_TRY(cudaFuncSetAttribute(k_batch_exp_chunk<G1, G2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TREE_BYTES));
+#if SSO_SPLIT_GROUPS
+  {
+    // G2 (the longer blocks) on the call's stream, G1 beside it on the second stream; both drain before the normalisation
+    const int sj = (c.s[1] && !c.aliased) ? 1 : si;
+    constexpr size_t TREE1 = 2 * EXP_BLOCK * sizeof(typename G1::F::T), TREE2 = 2 * EXP_BLOCK * sizeof(typename G2::F::T);
+    if (TREE1 > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_batch_exp<G1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TREE1));
+    if (TREE2 > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_batch_exp<G2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TREE2));
+    if (sj != si && (rc = c.fork(si, sj))) return rc;
+    if (n2) {
+      c.begin(PK_BATCH_EXP_G2, si, n2);
+      k_batch_exp<G2><<<nb2, EXP_BLOCK, TREE2, st>>>(b2, in_compressed, d_table, check, d_jac2, d_status);
+      c.end(si);
+    }
+    if (n1) {
+      c.begin(PK_BATCH_EXP_G1, sj, n1);
+      k_batch_exp<G1><<<nb1, EXP_BLOCK, TREE1, c.s[sj]>>>(b1, in_compressed, d_table, check, d_jac1, d_status);
+      c.end(sj);
+    }
+    if (sj != si && (rc = c.fork(sj, si))) return rc;
+  }
+#else
   c.begin(PK_BATCH_EXP_CHUNK, si, n1 + n2);
   k_batch_exp_chunk<G1, G2><<<nb1 + nb2, EXP_BLOCK, TREE_BYTES, st>>>(b1, b2, nb2, in_compressed, d_table, check, d_jac1, d_jac2, d_status);
   c.end(si);
+#endif
   uint32_t mb2 = div_up(div_up(n2, NORM_BATCH), 128), mb1 = div_up(div_up(n1, NORM_BATCH), 128);
   c.begin(PK_NORMALIZE_CHUNK, si, n1 + n2);
   k_normalize_chunk<G1, G2><<<mb1 + mb2, 128, 0, st>>>(b1, b2, mb2, d_jac1, d_jac2, out_compressed);
