@@ -111,7 +111,9 @@ int32_t sso_reencode_dev(uint32_t curve, uint32_t group, const void* d_in, uint3
  * (sum r_i v_i, sum r_i v_{i+1}) over i < n-1 as two uncompressed points in out_pair (host).  The reference
  * draws r_i from thread_rng, so only the verdict downstream is comparable; seed32 == NULL uses fresh host
  * entropy, a 32-byte seed makes the scalars reproducible (tests): r_i = first bits(r)-1 bits of the
- * ChaCha20(seed32) keystream blocks 2i, 2i+1. */
+ * ChaCha20(seed32) keystream blocks 2i, 2i+1.  TEST-ONLY: two MSMs run with the same seed share their r_i, which
+ * makes a G1-vs-G2 comparison of their results vacuous; the verification flows (sso_p1_verify_chunk_*, sso_p1_verify_ratios_file,
+ * sso_p2_verify_queries_buf) derive a distinct ChaCha20 key per MSM, Blake2b-256(seed || vector id || chunk || piece || rank). */
 int32_t sso_power_pairs_dev(uint32_t curve, uint32_t group, const void* d_in, uint32_t in_compressed, uint64_t n,
                             uint32_t check, uint32_t subgroup_check, const uint8_t* seed32, uint8_t* out_pair, size_t out_len,
                             int device, char* err, size_t errcap);
@@ -212,7 +214,16 @@ int32_t sso_p1_contribute_file(const sso_p1_params_t* p, const char* challenge_f
 /* Phase1::verification of one chunk on host buffers (row a5): hash chain, proofs of knowledge, per-element checks of
  * the response (check_output, subgroup_check_mode), chunk-0 update checks, optional power-ratio checks via random
  * linear combinations (ratio_check), and the decompressed new challenge whose hash slot is Blake2b(response).
- * A rejected contribution is SSO_E_VERIFY with the failed check named in err.  rlc_seed32 == NULL: fresh entropy. */
+ * A rejected contribution is SSO_E_VERIFY with the failed check named in err.  rlc_seed32 == NULL: fresh entropy.
+ *   check_input  : CheckForCorrectness applied to the challenge vectors (No: skipped — the operator's default; Full: on the
+ *                  curve and in the subgroup)
+ *   check_output : every response element must be non-zero whatever the setting; Full also forces the membership test
+ *   subgroup_check_mode : Auto / Direct / Batched run the membership test [r]P = O on every response element, No skips it —
+ *                  independent of check_output, as in the reference call (src/bin/contribute.rs:971-984)
+ *   ratio_check  : power ratios of the chunk's vectors against its tau_g2 combination; a chunk past 2^power holds tau_g1 only
+ *                  (no G2 element to compare with): its ratios are covered by sso_p1_verify_ratios_file on the combined file
+ * The nine public-key points must be non-zero and in their subgroups.  Full mode (and chunks beyond 2^22 elements) stream the
+ * vectors in `batch_size` pieces. */
 int32_t sso_p1_verify_chunk_buf(const sso_p1_params_t* p, const uint8_t* challenge, size_t challenge_len, const uint8_t* response,
                                 size_t response_len, uint8_t* new_challenge, size_t new_challenge_len, uint32_t check_input,
                                 uint32_t check_output, uint32_t subgroup_check_mode, uint32_t ratio_check, const uint8_t* rlc_seed32,
@@ -225,6 +236,51 @@ int32_t sso_p1_verify_chunk_file(const sso_p1_params_t* p, const char* challenge
                                  const char* response_fn, const char* response_hash_fn, uint32_t check_output,
                                  const char* new_challenge_fn, const char* new_challenge_hash_fn, uint32_t subgroup_check_mode,
                                  uint32_t ratio_check, int device, char* err, size_t errcap);
+
+/* phase1_cli::new_challenge(challenge_fn, challenge_hash_fn, &parameters) — reference src/bin/new_setup.rs:105-109,
+ * src/bin/verify_transcript.rs:322-326: the initial accumulator of a chunk (or of the whole ceremony in Full mode): every
+ * element the group generator, hash slot = Blake2b-512 of the empty input; writes the file and the 64 raw bytes of its hash.
+ * Output files must not exist. */
+int32_t sso_p1_new_challenge_file(const char* challenge_fn, const char* challenge_hash_fn, const sso_p1_params_t* p, int device,
+                                  char* err, size_t errcap);
+
+/* The generators new_challenge writes and chunk-0 / transform_ratios verification compare against, per curve and process:
+ * one uncompressed G1 point and one uncompressed G2 point (checked: non-zero, on the curve, in the order-r subgroup).
+ * Built in: arkworks' constants except the G2 generators of MNT4-753 / MNT6-753, which could not be recovered in the build
+ * environment and default to a derived point — an integrator hands the reference's over once (e.g. from the round-0
+ * challenge the operator regenerates, reference src/bin/verify_transcript.rs:316-361).  Both NULL: back to the built-ins. */
+int32_t sso_p1_set_generators(uint32_t curve, const uint8_t* g1_uncompressed, size_t g1_len, const uint8_t* g2_uncompressed,
+                              size_t g2_len, int device, char* err, size_t errcap);
+
+/* phase1_cli::combine(response_list_fn, combined_fn, &parameters) — reference src/bin/verify_transcript.rs:603-607,
+ * src/bin/control.rs:564-568.  `p`: the chunk-0 parameters of the ceremony, as the reference passes them.  The list file names
+ * one response file (compressed + public key) per chunk, one path per line, in chunk order.  Output: the Full-mode accumulator,
+ * uncompressed, hash slot zero.  Decoding is streamed in `batch_size` pieces over devices[0..ndev) (NULL / 0: `device`; -1: all). */
+int32_t sso_p1_combine_file(const char* response_list_fn, const char* combined_fn, const sso_p1_params_t* p, const int* devices,
+                            int ndev, int device, char* err, size_t errcap);
+
+/* phase1_cli::transform_ratios(response_fn, check_input, &parameters) — reference src/bin/verify_transcript.rs:646-653, 811-822,
+ * src/bin/control.rs:587-591, 866-873: consistency of a whole uncompressed accumulator (generators in element 0, power ratios of
+ * the four vectors by random linear combinations, beta_g2).  The vectors are streamed in `batch_size` pieces over
+ * devices[0..ndev) of this process — or over the ranks of the process group (sso_dist_init) —, every participant sums the
+ * partial pairs of its pieces, ONE NCCL all-gather exchanges the per-participant sums and a point addition folds them
+ * (SURVEY.md §8e).  rlc_seed32 == NULL: fresh entropy (the only sound setting outside tests).  SSO_E_VERIFY on rejection. */
+int32_t sso_p1_verify_ratios_file(const sso_p1_params_t* p, const char* combined_fn, uint32_t check_input, const int* devices,
+                                  int ndev, int device, const uint8_t* rlc_seed32, char* err, size_t errcap);
+
+/* Process group for the cooperative calls: one process per GPU (torchrun), every rank makes the same call on the same
+ * files.  Cooperative are the Full-mode calls (sso_p1_contribute_file / _seeded_buf / sso_p1_verify_chunk_file / _buf with
+ * contribution_mode = SSO_MODE_FULL), sso_p1_combine_file and sso_p1_verify_ratios_file: pieces are dealt round-robin over
+ * the ranks, outputs are written into the shared file mapping, rank 0 creates and commits the files, and the partial MSM
+ * results meet in one ncclAllGather.  Chunk-level calls stay local to the calling rank.
+ *   sso_dist_unique_id : ncclGetUniqueId on one rank; the caller broadcasts the 128 bytes (e.g. over torch.distributed)
+ *   sso_dist_init      : ncclCommInitRank on `device`;  sso_dist_barrier: all ranks;  sso_dist_finalize: destroys it
+ *   sso_dist_stats     : [0] initialised [1] rank [2] world [3] all-gathers issued so far [4] NCCL version code */
+int32_t sso_dist_unique_id(uint8_t out[128], char* err, size_t errcap);
+int32_t sso_dist_init(int32_t rank, int32_t world, const uint8_t id128[128], int device, char* err, size_t errcap);
+int32_t sso_dist_barrier(char* err, size_t errcap);
+int32_t sso_dist_finalize(void);
+int32_t sso_dist_stats(uint64_t out[5]);
 
 /* Sum of n uncompressed points (host buffers) -> one uncompressed point.  Used to combine the per-GPU partial
  * results of a sharded power_pairs / merge_pairs after the NCCL all-gather. */

@@ -110,3 +110,28 @@ def field_mul(field: int, a: bytes, b: bytes, n: int) -> bytes:
     out = ctypes.create_string_buffer(len(a))
     assert lib().orc_field_mul(field, a, b, out, ctypes.c_uint64(n)) == 0
     return out.raw
+
+
+def new_challenge(params: Phase1Params) -> bytes:
+    """oracle.phase1.new_challenge without the per-element Python loop (every element is the same generator)."""
+    from . import serialize as ser
+    c = params.curve
+    g1 = ser.point_to_bytes(c.g1, c.g1.gen, False)
+    g2 = ser.point_to_bytes(c.g2, c.g2.gen, False)
+    out = calculate_hash(b"") + g1 * params.g1_count + g2 * params.other_count + g1 * (2 * params.other_count) + g2
+    assert len(out) == params.accumulator_size
+    return out
+
+
+def decompress_vectors(params: Phase1Params, response: bytes, threads: int = 0):
+    """the five vectors of a response, uncompressed, no checks (the `decompress` hook of oracle.phase1.combine)"""
+    oc = params.offsets(True)
+    counts = (params.g1_count, params.other_count, params.other_count, params.other_count, 1)
+    groups = (0, 1, 0, 0, 1)
+    return [reencode(params.curve, groups[i], response[oc[i]:oc[i + 1]], counts[i], check=0, subgroup=False, threads=threads)
+            for i in range(5)]
+
+
+def combine(params: Phase1Params, responses, threads: int = 0) -> bytes:
+    from . import phase1
+    return phase1.combine(params, responses, decompress=lambda cp, r: decompress_vectors(cp, r, threads))

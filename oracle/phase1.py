@@ -285,27 +285,65 @@ def verify_chunk_with_key(params: Phase1Params, challenge: bytes, response: byte
     return write_chunk(params, calculate_hash(response), vout, False)
 
 
-def rlc_scalars(curve: Curve, seed32: bytes, n: int):
+TWEAK_P1_VERIFY, TWEAK_P1_RATIOS, TWEAK_P2_VERIFY = 0x7031760000000000, 0x7031720000000000, 0x7032760000000000
+
+
+def rlc_key(seed32: bytes, tweak) -> bytes:
+    """ChaCha20 key of one MSM of a verification flow (csrc/curve_ops.cuh::run_msm_pairs): Blake2b-256(seed || tweak), tweak =
+    (vector id, chunk index, piece offset, rank * 64 + worker slot) as four little-endian u64 — two MSMs never share their r_i
+    (identical r_i on a G1 and a G2 vector would make their same_ratio comparison vacuous)."""
+    import struct
+    return hashlib.blake2b(seed32 + struct.pack("<4Q", *tweak), digest_size=32).digest()
+
+
+def rlc_scalars(curve: Curve, seed32: bytes, n: int, tweak=None):
     """The product's reproducible random-linear-combination scalars (include/sso_b200.h,
-    sso_power_pairs_dev): r_i = first bits(r)-1 bits of the ChaCha20(seed32) keystream blocks 2i, 2i+1."""
+    sso_power_pairs_dev): r_i = first bits(r)-1 bits of the ChaCha20(key) keystream blocks 2i, 2i+1; key = seed32 for the
+    test-only primitives, rlc_key(seed32, tweak) inside the verification flows."""
     import struct
     from .chacha import chacha20_block
+    if tweak is not None:
+        seed32 = rlc_key(seed32, tweak)
     key = struct.unpack("<8I", seed32)
     sbits = curve.Fr.bits - 1
     out = []
     for i in range(n):
-        words = chacha20_block(key, 2 * i) + chacha20_block(key, 2 * i + 1)
+        words = chacha20_block(key, 2 * i)
+        if sbits > 512:
+            words = words + chacha20_block(key, 2 * i + 1)
         v = sum(w << (32 * j) for j, w in enumerate(words))
         out.append(v & ((1 << sbits) - 1))
     return out
 
 
-def verify_chunk(params: Phase1Params, challenge: bytes, response: bytes, check_out: int = CHECK_FULL, subgroup: bool = True,
-                 ratio_check: bool = True, rlc_seed32: bytes = bytes(32)) -> bytes:
-    """Phase1::verification of one chunk with real pairings (oracle/pairing.py): hash chain, the three proofs of
-    knowledge, per-element checks, chunk-0 update checks, power-ratio checks on random linear combinations.
-    Returns the new challenge; raises VerificationError naming the failed check.  [UP] for the exact list of
-    checks; the product (csrc/flows.cuh) performs the same list."""
+def elem_policy(check_out: int, subgroup_mode: int):
+    """[UP] per-element policy of Phase1::verification (the product: csrc/flows.cuh::verify_elem_check / verify_subgroup):
+    response elements are always checked for zero; the membership test follows SubgroupCheckMode (No skips it) and is also
+    forced by CheckForCorrectness::Full — the two knobs are independent arguments of the reference call
+    (src/bin/contribute.rs:971-984)."""
+    check = CHECK_NONZERO if check_out == CHECK_NO else check_out
+    subgroup = subgroup_mode != SUBGROUP_NO or check_out == CHECK_FULL
+    return check, subgroup
+
+
+def check_point_policy(G: Group, P, check: int, subgroup: bool, uncompressed_input: bool = False):
+    """csrc/kernels.cuh::body_reencode after parsing."""
+    if P is None:
+        if check != CHECK_NO:
+            raise VerificationError("point at infinity")
+        return
+    if uncompressed_input and (check == CHECK_FULL or subgroup) and not G.on_curve(P):
+        raise VerificationError("point not on curve")
+    if subgroup and G.mul(P, G.r) is not None:
+        raise VerificationError("point not in the prime-order subgroup")
+
+
+def verify_chunk(params: Phase1Params, challenge: bytes, response: bytes, check_out: int = CHECK_NO, subgroup_mode: int = SUBGROUP_AUTO,
+                 ratio_check: bool = True, rlc_seed32: bytes = bytes(32), check_in: int = CHECK_NO) -> bytes:
+    """Phase1::verification of one chunk (or of a whole accumulator in Full mode) with real pairings (oracle/pairing.py):
+    hash chain, public-key validation, the three proofs of knowledge, per-element checks, chunk-0 update checks, power-ratio
+    checks on random linear combinations.  Returns the new challenge; raises VerificationError naming the failed check.
+    [UP] for the exact list of checks; the product (csrc/flows.cuh::verify_chunk_host) performs the same list."""
     from .pairing import same_ratio
     c = params.curve
     g1, g2 = c.g1, c.g2
@@ -315,15 +353,26 @@ def verify_chunk(params: Phase1Params, challenge: bytes, response: bytes, check_
     if response[:HASH_SIZE] != digest:
         raise VerificationError("hash chain broken: response does not continue the challenge")
     body = response[:len(response) - params.public_key_size]
-    pub = PublicKey.from_bytes(c, response[len(body):])
     try:
+        pub = PublicKey.from_bytes(c, response[len(body):])
         vout = read_chunk(params, body, True)
+        vin = read_chunk(params, challenge, False)
     except ser.FormatError as e:
         raise VerificationError(str(e))
+    check, subgroup = elem_policy(check_out, subgroup_mode)
     for G, pts in ((g1, vout.tau_g1), (g2, vout.tau_g2), (g1, vout.alpha_g1), (g1, vout.beta_g1), (g2, [vout.beta_g2])):
         for P in pts:
-            check_point(G, P, check_out, subgroup)
-    vin = read_chunk(params, challenge, False)
+            check_point_policy(G, P, check, subgroup)
+    if check_in != CHECK_NO:
+        for G, pts in ((g1, vin.tau_g1), (g2, vin.tau_g2), (g1, vin.alpha_g1), (g1, vin.beta_g1), (g2, [vin.beta_g2])):
+            for P in pts:
+                check_point_policy(G, P, check_in, check_in == CHECK_FULL, uncompressed_input=True)
+    for G, pts in ((g1, pub.tau_g1 + pub.alpha_g1 + pub.beta_g1), (g2, (pub.tau_g2, pub.alpha_g2, pub.beta_g2))):
+        for P in pts:
+            try:
+                check_point_policy(G, P, CHECK_FULL, True, uncompressed_input=True)
+            except VerificationError as e:
+                raise VerificationError("public key: " + str(e))
     g2_s = [compute_g2_s(c, digest, pair[0], pair[1], i) for i, pair in enumerate((pub.tau_g1, pub.alpha_g1, pub.beta_g1))]
     g2_sx = [pub.tau_g2, pub.alpha_g2, pub.beta_g2]
     checks = [("proof of knowledge: tau", pub.tau_g1, (g2_s[0], g2_sx[0])),
@@ -339,16 +388,87 @@ def verify_chunk(params: Phase1Params, challenge: bytes, response: bytes, check_
                    ("before/after: beta_g1[0] vs beta proof", (vin.beta_g1[0], vout.beta_g1[0]), (g2_s[2], g2_sx[2])),
                    ("before/after: beta_g2 vs beta_g1[0]", (vin.beta_g1[0], vout.beta_g1[0]), (vin.beta_g2, vout.beta_g2))]
     if ratio_check and params.other_count >= 2:
-        def pp(G, v):
-            return power_pairs_with(G, v, rlc_scalars(c, rlc_seed32, len(v) - 1))
-        g2p = pp(g2, vout.tau_g2)
+        # a chunk past 2^power holds tau_g1 only (no G2 element): its ratios are left to transform_ratios on the combined file
+        def pp(G, v, vec):
+            return power_pairs_with(G, v, rlc_scalars(c, rlc_seed32, len(v) - 1, (TWEAK_P1_VERIFY | vec, params.chunk_index, 0, 0)))
+        g2p = pp(g2, vout.tau_g2, 1)
         g2_exact = (vout.tau_g2[0], vout.tau_g2[1]) if params.chunk_index == 0 else g2p
-        checks.append(("power ratio: tau_g1", pp(g1, vout.tau_g1), g2_exact))
-        checks.append(("power ratio: alpha_g1", pp(g1, vout.alpha_g1), g2_exact))
-        checks.append(("power ratio: beta_g1", pp(g1, vout.beta_g1), g2_exact))
+        checks.append(("power ratio: tau_g1", pp(g1, vout.tau_g1, 0), g2_exact))
+        checks.append(("power ratio: alpha_g1", pp(g1, vout.alpha_g1, 2), g2_exact))
+        checks.append(("power ratio: beta_g1", pp(g1, vout.beta_g1, 3), g2_exact))
         if params.chunk_index == 0:
             checks.append(("power ratio: tau_g2", (vout.tau_g1[0], vout.tau_g1[1]), g2p))
     for name, p1, p2 in checks:
         if not same_ratio(c, p1, p2):
             raise VerificationError("same_ratio check failed: " + name)
     return write_chunk(params, calculate_hash(response), vout, False)
+
+
+# ---------------------------------------------------------------------------------------------
+# whole accumulators: combine, transform_ratios
+# ---------------------------------------------------------------------------------------------
+def chunk_params_of(params: Phase1Params):
+    """the chunk parameters of every chunk of the ceremony `params` (any chunk of it) belongs to"""
+    return [Phase1Params.new_chunk(params.curve, k, params.chunk_size, params.power, params.batch_size) for k in range(params.num_chunks)]
+
+
+def combine(params: Phase1Params, responses, decompress=None) -> bytes:
+    """phase1_cli::combine (src/bin/verify_transcript.rs:603-607): the vectors of all chunk responses (compressed + public key)
+    concatenated into the Full-mode accumulator, uncompressed; the hash slot stays zero ([UP] Phase1::aggregation writes the
+    vectors only); beta_g2 from the first chunk.  `decompress(chunk_params, response) -> five uncompressed byte strings`
+    lets the C++ leg do the square roots."""
+    cps = chunk_params_of(params)
+    assert len(responses) == len(cps)
+    vecs = [[], [], [], []]
+    beta_g2 = None
+    for cp, resp in zip(cps, responses):
+        assert len(resp) == cp.contribution_size
+        if decompress is None:
+            v = read_chunk(cp, resp[:len(resp) - cp.public_key_size], True)
+            c = cp.curve
+            parts = (ser.points_to_bytes(c.g1, v.tau_g1, False), ser.points_to_bytes(c.g2, v.tau_g2, False),
+                     ser.points_to_bytes(c.g1, v.alpha_g1, False), ser.points_to_bytes(c.g1, v.beta_g1, False),
+                     ser.point_to_bytes(c.g2, v.beta_g2, False))
+        else:
+            parts = decompress(cp, resp)
+        for i in range(4):
+            vecs[i].append(parts[i])
+        if beta_g2 is None:
+            beta_g2 = parts[4]
+    out = bytes(HASH_SIZE) + b"".join(b"".join(v) for v in vecs) + beta_g2
+    full = Phase1Params.new_full(params.curve, params.power, params.batch_size)
+    assert len(out) == full.accumulator_size
+    return out
+
+
+def transform_ratios(full: Phase1Params, combined: bytes, check_in: int = CHECK_NO, rlc_seed32: bytes = bytes(32)):
+    """phase1_cli::transform_ratios (src/bin/verify_transcript.rs:811-822; [UP] Phase1::aggregate_verification): element 0 of
+    tau_g1 / tau_g2 are the generators, the power ratios of the four vectors, beta_g2 against beta_g1[0].  Real pairings:
+    small sizes only.  Raises VerificationError naming the failed check."""
+    from .pairing import same_ratio
+    c = full.curve
+    g1, g2 = c.g1, c.g2
+    if len(combined) != full.accumulator_size:
+        raise VerificationError("wrong size")
+    try:
+        v = read_chunk(full, combined, False)
+    except ser.FormatError as e:
+        raise VerificationError(str(e))
+    for G, pts in ((g1, v.tau_g1), (g2, v.tau_g2), (g1, v.alpha_g1), (g1, v.beta_g1), (g2, [v.beta_g2])):
+        for P in pts:
+            check_point_policy(G, P, CHECK_FULL, check_in == CHECK_FULL, uncompressed_input=True)
+    if not g1.eq(v.tau_g1[0], g1.gen):
+        raise VerificationError("tau_g1[0] is not the G1 generator")
+    if not g2.eq(v.tau_g2[0], g2.gen):
+        raise VerificationError("tau_g2[0] is not the G2 generator")
+
+    def pp(G, vec, i):
+        return power_pairs_with(G, vec, rlc_scalars(c, rlc_seed32, len(vec) - 1, (TWEAK_P1_RATIOS | i, 0, 0, 0)))
+    g1p, g2p = (v.tau_g1[0], v.tau_g1[1]), (v.tau_g2[0], v.tau_g2[1])
+    checks = [("power ratio: tau_g1", pp(g1, v.tau_g1, 0), g2p), ("power ratio: tau_g2", g1p, pp(g2, v.tau_g2, 1)),
+              ("power ratio: alpha_g1", pp(g1, v.alpha_g1, 2), g2p), ("power ratio: beta_g1", pp(g1, v.beta_g1, 3), g2p),
+              ("beta_g1[0] vs beta_g2", (v.tau_g1[0], v.beta_g1[0]), (v.tau_g2[0], v.beta_g2))]
+    for name, p1, p2 in checks:
+        if not same_ratio(c, p1, p2):
+            raise VerificationError("same_ratio check failed: " + name)
+    return True

@@ -11,4 +11,5 @@ from ._lib import SsoError, lib, library_path  # noqa: F401
 from .phase1 import (  # noqa: F401
     CHECK_FULL, CHECK_NO, CHECK_NONZERO, CURVES, Phase1Parameters, batch_exp, batch_mul, contribute_buf, contribute_many_buf, contribute_seeded_many_buf, verify_chunk_many_buf,
     contribute, contribute_dev, contribute_seeded_buf, keygen, transform_pok_and_correctness, verify_chunk_buf, imad_peak, merge_pairs, new_challenge_dev, power_pairs, profile_enable, profile_read, profile_reset, reencode, same_ratio,
+    new_challenge, set_generators, combine, transform_ratios, dist_init_from_torch, dist_barrier, dist_finalize, dist_stats,
 )

@@ -69,6 +69,15 @@ def lib() -> ctypes.CDLL:
                                                         u8p, u32, u32, i32, cp, sz]
         L.sso_p1_verify_chunk_many_buf.argtypes = [pp, sz, ctypes.POINTER(vp), ctypes.POINTER(sz), ctypes.POINTER(vp), ctypes.POINTER(sz),
                                                    ctypes.POINTER(vp), ctypes.POINTER(sz), u32, u32, u32, u32, u8p, u32, i32, cp, sz]
+        ip = ctypes.POINTER(ctypes.c_int)
+        L.sso_p1_new_challenge_file.argtypes = [cp, cp, pp, i32, cp, sz]
+        L.sso_p1_set_generators.argtypes = [u32, u8p, sz, u8p, sz, i32, cp, sz]
+        L.sso_p1_combine_file.argtypes = [cp, cp, pp, ip, i32, i32, cp, sz]
+        L.sso_p1_verify_ratios_file.argtypes = [pp, cp, u32, ip, i32, i32, u8p, cp, sz]
+        L.sso_dist_unique_id.argtypes = [cp, cp, sz]
+        L.sso_dist_init.argtypes = [ctypes.c_int32, ctypes.c_int32, u8p, i32, cp, sz]
+        L.sso_dist_barrier.argtypes = [cp, sz]
+        L.sso_dist_stats.argtypes = [ctypes.POINTER(u64)]
         L.sso_profile_enable.argtypes = [ctypes.c_int32]
         L.sso_profile_read.argtypes = [ctypes.POINTER(u64), sz]
         L.sso_imad_peak.argtypes = [i32, i32, ctypes.POINTER(ctypes.c_double), cp, sz]
@@ -78,7 +87,9 @@ def lib() -> ctypes.CDLL:
                      "sso_test_field_mul", "sso_p1_new_challenge_dev", "sso_profile_enable", "sso_profile_reset",
                      "sso_profile_read", "sso_power_pairs_dev", "sso_merge_pairs_dev", "sso_same_ratio", "sso_p1_keygen",
                      "sso_p1_contribute_seeded_buf", "sso_p1_contribute_file", "sso_p1_verify_chunk_buf", "sso_p1_verify_chunk_file", "sso_points_sum",
-                     "sso_p2_scale_queries_buf", "sso_p2_verify_queries_buf", "sso_p1_contribute_many_buf", "sso_p1_verify_chunk_many_buf", "sso_p1_contribute_seeded_many_buf"):
+                     "sso_p2_scale_queries_buf", "sso_p2_verify_queries_buf", "sso_p1_contribute_many_buf", "sso_p1_verify_chunk_many_buf",
+                     "sso_p1_new_challenge_file", "sso_p1_set_generators", "sso_p1_combine_file", "sso_p1_verify_ratios_file",
+                     "sso_dist_unique_id", "sso_dist_init", "sso_dist_barrier", "sso_dist_finalize", "sso_dist_stats", "sso_p1_contribute_seeded_many_buf"):
             getattr(L, name).restype = ctypes.c_int32
         _lib = L
     return _lib

@@ -5,6 +5,8 @@
 // only moves bytes, hashes (Blake2b, sequential by construction) and checks sizes.
 // There is no CPU fallback: without a device every compute entry returns SSO_E_CUDA.
 #include "flows.cuh"
+#include "files.cuh"
+#include <memory>
 #include <thread>
 #include <mutex>
 #include <atomic>
@@ -113,9 +115,10 @@ const CurveOps* ops_for(uint32_t curve) {
   return nullptr;
 }
 
+// n is bounded by the callers: vectors longer than 2^24 elements go through the piece engine (stream.cuh)
 inline VecSeg seg(const uint8_t* in, uint8_t* out, uint64_t n, uint32_t slot, uint32_t has_coeff, uint32_t mode) {
   VecSeg s;
-  s.in = in; s.out = out; s.n = (uint32_t)n; s.coeff_slot = slot; s.has_coeff = has_coeff; s.mode = mode;
+  s.in = in; s.out = out; s.n = n > 0xffffffffull ? 0xffffffffu : (uint32_t)n; s.coeff_slot = slot; s.has_coeff = has_coeff; s.mode = mode;
   return s;
 }
 inline VecBatch batch_of(std::initializer_list<VecSeg> segs) {
@@ -137,6 +140,14 @@ int p1_contribute_streams(Ctx& c, const CurveOps* ops, const P1Layout& L, const 
   int rc;
   const uint8_t* coeffs[TAU_COEFF_SLOTS] = {nullptr, alpha, beta};
   uint32_t* d_table;
+  if (check == CHECK_FULL) {
+    // CheckForCorrectness::Full on the inputs (--force-correctness-checks, reference src/bin/contribute.rs:816-819): on
+    // the curve AND in the prime-order subgroup — a separate pass, so that the hot kernel keeps its register budget
+    const uint64_t counts[5] = {L.g1n, L.on, L.on, L.on, 1};
+    static const uint32_t groups[5] = {GROUP_G1, GROUP_G2, GROUP_G1, GROUP_G1, GROUP_G2};
+    for (int v = 0; v < 5; v++)
+      if (counts[v] && (rc = ops->reencode(c, 0, groups[v], d_ch + L.off_u[v], 0, counts[v], nullptr, 0, CHECK_FULL, 1, nullptr, d_status, err, errcap))) return rc;
+  }
   if ((rc = ops->tau_tables(c, 0, L.start, tau, coeffs, &d_table, err, errcap))) return rc;
   VecBatch g2 = batch_of({seg(d_ch + L.off_u[1], d_resp + L.off_c[1], L.on, 0, 0, 0),
                           seg(d_ch + L.off_u[4], d_resp + L.off_c[4], 1, 2, 1, 1)});
@@ -227,8 +238,16 @@ int32_t sso_batch_exp_dev(uint32_t curve, uint32_t group, const void* d_in, uint
   uint32_t* d_status;
   if ((rc = status_buffer(c, &d_status, err, errcap))) return rc;
   if (group > 1) { set_err(err, errcap, "unknown group %u", group); return SSO_E_ARG; }
-  if ((rc = single_vector(c, ops, group, (const uint8_t*)d_in, in_compressed, n, first_index, tau, coeff, 0, (uint8_t*)d_out,
-                          out_compressed, check_input, d_status, err, errcap))) return rc;
+  // vectors longer than the span of one tau table (2^24 indices) are processed in segments, each with its own table base
+  CurveSizes cs;
+  curve_sizes(curve, cs);
+  const uint64_t in_sz = point_size(cs, group, in_compressed), out_sz = point_size(cs, group, out_compressed);
+  const uint64_t SEG = 1ull << 22;
+  for (uint64_t off = 0; off < n; off += SEG) {
+    uint64_t m = n - off < SEG ? n - off : SEG;
+    if ((rc = single_vector(c, ops, group, (const uint8_t*)d_in + off * in_sz, in_compressed, m, first_index + off, tau, coeff, 0,
+                            (uint8_t*)d_out + off * out_sz, out_compressed, check_input, d_status, err, errcap))) return rc;
+  }
   if ((rc = sync_all(c, err, errcap))) return rc;
   return check_status(c, d_status, "batch_exp input", err, errcap);
 }
@@ -297,7 +316,7 @@ int32_t sso_power_pairs_dev(uint32_t curve, uint32_t group, const void* d_in, ui
   if ((rc = c.alloc((void**)&d_aff, n * ops->aff_words[group] * 4))) return rc;
   if ((rc = c.alloc((void**)&d_out, 2 * usz))) return rc;
   if ((rc = ops->reencode(c, 0, group, (const uint8_t*)d_in, in_compressed, n, nullptr, 0, check, subgroup_check, d_aff, d_status, err, errcap))) return rc;
-  if ((rc = ops->msm_pairs(c, 0, group, d_aff, d_aff + ops->aff_words[group], n - 1, seed32, d_out, err, errcap))) return rc;
+  if ((rc = ops->msm_pairs(c, 0, group, d_aff, d_aff + ops->aff_words[group], n - 1, seed32, nullptr, d_out, err, errcap))) return rc;
   if ((rc = sync_all(c, err, errcap))) return rc;
   if ((rc = check_status(c, d_status, "point", err, errcap))) return rc;
   CUDA_TRY(cudaMemcpy(out_pair, d_out, 2 * usz, cudaMemcpyDeviceToHost));
@@ -326,7 +345,7 @@ int32_t sso_merge_pairs_dev(uint32_t curve, uint32_t group, const void* d_a, con
   if ((rc = c.alloc((void**)&d_out, 2 * usz))) return rc;
   if ((rc = ops->reencode(c, 0, group, (const uint8_t*)d_a, in_compressed, n, nullptr, 0, check, subgroup_check, d_aff_a, d_status, err, errcap))) return rc;
   if ((rc = ops->reencode(c, 0, group, (const uint8_t*)d_b, in_compressed, n, nullptr, 0, check, subgroup_check, d_aff_b, d_status, err, errcap))) return rc;
-  if ((rc = ops->msm_pairs(c, 0, group, d_aff_a, d_aff_b, n, seed32, d_out, err, errcap))) return rc;
+  if ((rc = ops->msm_pairs(c, 0, group, d_aff_a, d_aff_b, n, seed32, nullptr, d_out, err, errcap))) return rc;
   if ((rc = sync_all(c, err, errcap))) return rc;
   if ((rc = check_status(c, d_status, "point", err, errcap))) return rc;
   CUDA_TRY(cudaMemcpy(out_pair, d_out, 2 * usz, cudaMemcpyDeviceToHost));
@@ -375,6 +394,43 @@ int32_t sso_p1_contribute_dev(const sso_p1_params_t* p, const void* d_challenge,
   return check_status(c, d_status, "challenge", err, errcap);
 }
 
+// Full-mode accumulators and chunks beyond what one launch set should hold are streamed in pieces (stream.cuh)
+static bool needs_streaming(const sso_p1_params_t* p, const P1Layout& L) {
+  // Full mode is the whole-accumulator case (beacon contribution and its verification): always in `batch_size` pieces
+  const uint64_t big = 1ull << 22;
+  return L.g1n > big || L.on > big || p->contribution_mode == SSO_MODE_FULL;
+}
+
+// phase1_cli::contribute on an accumulator streamed in `batch_size` pieces over the participants (devices of this process or
+// the ranks of the process group): the beacon contribution on the combined file (reference src/bin/verify_transcript.rs:675-696,
+// src/bin/control.rs:792-808).  With a process group every rank computes its own pieces into the shared response mapping;
+// the hash and the proofs of knowledge are computed redundantly (identical bytes).
+static int32_t contribute_streamed(const sso_p1_params_t* p, const P1Layout& L, const CurveOps* ops, const uint8_t* challenge, uint8_t* response,
+                                   const uint8_t* tau, const uint8_t* alpha, const uint8_t* beta, const uint8_t* pubkey, const uint8_t* seed32,
+                                   uint32_t check_input, int device, char* err, size_t errcap) {
+  int rc;
+  Participants P;
+  if ((rc = resolve_participants(nullptr, 0, device, p->contribution_mode == SSO_MODE_FULL, P, err, errcap))) return rc;
+  std::thread hasher([=] { blake2b_512(challenge, L.acc_size, response); });
+  struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{hasher};
+  Ctx c(err, errcap);
+  if ((rc = c.init(P.devices[0], 1))) return rc;
+  std::vector<uint8_t> scalars;
+  KeygenState keys;
+  if (seed32) {
+    scalars.resize(3 * (size_t)L.cs.fr);
+    if ((rc = keygen_stage1(c, 0, ops, L.cs, seed32, 3, keys, scalars.data(), err, errcap))) return rc;
+    tau = scalars.data(); alpha = scalars.data() + L.cs.fr; beta = scalars.data() + 2 * (size_t)L.cs.fr;
+  }
+  if ((rc = stream_contribute(ops, L, challenge, response, tau, alpha, beta, check_input, p->batch_size, P, err, errcap))) return rc;
+  hasher.join();
+  if (seed32) {
+    if ((rc = keygen_stage2(c, 0, ops, L.cs, response, keys, response + L.off_c[5], err, errcap))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c.s[0]));
+  } else if (pubkey) memcpy(response + L.off_c[5], pubkey, L.pk_size);
+  return SSO_OK;
+}
+
 // Shared body of sso_p1_contribute_buf (scalars and public key given) and sso_p1_contribute_seeded_buf (seed32 given:
 // scalars drawn first, proofs of knowledge computed once the challenge hash is known, on a high-priority stream beside
 // the main kernels).  The challenge is hashed ONCE, on the host, while the GPU works.
@@ -390,6 +446,7 @@ static int32_t contribute_buf_core(const sso_p1_params_t* p, const uint8_t* chal
   if (challenge_len != L.acc_size) { set_err(err, errcap, "challenge has %zu bytes, expected accumulator_size %llu", challenge_len, (unsigned long long)L.acc_size); return SSO_E_ARG; }
   if (response_len != L.contrib_size) { set_err(err, errcap, "response has %zu bytes, expected contribution_size %llu", response_len, (unsigned long long)L.contrib_size); return SSO_E_ARG; }
   if (pubkey && pubkey_len != L.pk_size) { set_err(err, errcap, "public key has %zu bytes, expected %llu", pubkey_len, (unsigned long long)L.pk_size); return SSO_E_ARG; }
+  if (needs_streaming(p, L)) return contribute_streamed(p, L, ops, challenge, response, tau, alpha, beta, pubkey, seed32, check_input, device, err, errcap);
   Ctx c(err, errcap);
   if ((rc = c.init(device, seed32 ? 3 : 2))) return rc;
   std::vector<uint8_t> scalars;
@@ -534,33 +591,11 @@ int32_t sso_p1_contribute_seeded_many_buf(const sso_p1_params_t* params, size_t 
   });
 }
 
-// phase1_cli::contribute(challenge_fn, challenge_hash_fn, response_fn, response_hash_fn, check_input, batch_exp_mode, params, rng)
-int32_t sso_p1_contribute_file(const sso_p1_params_t* p, const char* challenge_fn, const char* challenge_hash_fn,
-                               const char* response_fn, const char* response_hash_fn, uint32_t check_input, uint32_t batch_exp_mode,
-                               const uint8_t seed32[32], int device, char* err, size_t errcap) {
-  (void)batch_exp_mode;                                    // outputs are mode-independent
-  P1Layout L;
-  int rc = p1_layout(p, L, err, errcap);
-  if (rc) return rc;
-  std::vector<uint8_t> challenge;
-  if ((rc = read_file(challenge_fn, challenge, err, errcap))) return rc;
-  if (challenge.size() != L.acc_size) { set_err(err, errcap, "The size of challenge file should be correct: %zu != %llu", challenge.size(), (unsigned long long)L.acc_size); return SSO_E_ARG; }
-  std::vector<uint8_t> response(L.contrib_size);
-  if ((rc = sso_p1_contribute_seeded_buf(p, challenge.data(), challenge.size(), response.data(), response.size(), seed32, check_input,
-                                         device, err, errcap))) return rc;
-  uint8_t h[64];
-  if ((rc = write_new_file(challenge_hash_fn, response.data(), 64, err, errcap))) return rc;     // response[0..64) = hash(challenge)
-  if ((rc = write_new_file(response_fn, response.data(), response.size(), err, errcap))) return rc;
-  blake2b_512(response.data(), response.size(), h);
-  return write_new_file(response_hash_fn, h, 64, err, errcap);
-}
-
 // Phase1::verification for one chunk on host buffers (a5)
-int32_t sso_p1_verify_chunk_buf(const sso_p1_params_t* p, const uint8_t* challenge, size_t challenge_len, const uint8_t* response,
+static int32_t verify_chunk_core(const sso_p1_params_t* p, const uint8_t* challenge, size_t challenge_len, const uint8_t* response,
                                 size_t response_len, uint8_t* new_challenge, size_t new_challenge_len, uint32_t check_input,
                                 uint32_t check_output, uint32_t subgroup_check_mode, uint32_t ratio_check, const uint8_t* rlc_seed32,
-                                int device, char* err, size_t errcap) {
-  (void)check_input;   // the challenge was produced (and checked) by the previous verification; kept for signature parity
+                                int device, uint8_t* ch_hash_out, char* err, size_t errcap) {
   P1Layout L;
   int rc = p1_layout(p, L, err, errcap);
   if (rc) return rc;
@@ -568,11 +603,27 @@ int32_t sso_p1_verify_chunk_buf(const sso_p1_params_t* p, const uint8_t* challen
   if (challenge_len != L.acc_size || new_challenge_len != L.acc_size) { set_err(err, errcap, "challenge / new challenge must have accumulator_size %llu bytes", (unsigned long long)L.acc_size); return SSO_E_ARG; }
   if (response_len != L.contrib_size) { set_err(err, errcap, "response has %zu bytes, expected contribution_size %llu", response_len, (unsigned long long)L.contrib_size); return SSO_E_ARG; }
   const CurveOps* ops = ops_for(p->curve);
+  uint64_t chunk_index = p->contribution_mode == SSO_MODE_FULL ? 0 : p->chunk_index;
+  if (needs_streaming(p, L)) {
+    Participants P;
+    if ((rc = resolve_participants(nullptr, 0, device, p->contribution_mode == SSO_MODE_FULL, P, err, errcap))) return rc;
+    Ctx c(err, errcap);
+    if ((rc = c.init(P.devices[0], 1))) return rc;
+    return verify_chunk_host(c, ops, L, p->curve, chunk_index, challenge, response, new_challenge, check_input, check_output,
+                             subgroup_check_mode, ratio_check, rlc_seed32, &P, p->batch_size, ch_hash_out, err, errcap);
+  }
   Ctx c(err, errcap);
   if ((rc = c.init(device, 2))) return rc;
-  uint64_t chunk_index = p->contribution_mode == SSO_MODE_FULL ? 0 : p->chunk_index;
-  return verify_chunk_host(c, ops, L, p->curve, chunk_index, challenge, response, new_challenge, check_output, subgroup_check_mode,
-                           ratio_check, rlc_seed32, err, errcap);
+  return verify_chunk_host(c, ops, L, p->curve, chunk_index, challenge, response, new_challenge, check_input, check_output,
+                           subgroup_check_mode, ratio_check, rlc_seed32, nullptr, 0, ch_hash_out, err, errcap);
+}
+
+int32_t sso_p1_verify_chunk_buf(const sso_p1_params_t* p, const uint8_t* challenge, size_t challenge_len, const uint8_t* response,
+                                size_t response_len, uint8_t* new_challenge, size_t new_challenge_len, uint32_t check_input,
+                                uint32_t check_output, uint32_t subgroup_check_mode, uint32_t ratio_check, const uint8_t* rlc_seed32,
+                                int device, char* err, size_t errcap) {
+  return verify_chunk_core(p, challenge, challenge_len, response, response_len, new_challenge, new_challenge_len, check_input, check_output,
+                           subgroup_check_mode, ratio_check, rlc_seed32, device, nullptr, err, errcap);
 }
 
 // The chunk loop of verify_transcript (src/bin/verify_transcript.rs:293-569) as a work queue: chunks are verified
@@ -590,33 +641,6 @@ int32_t sso_p1_verify_chunk_many_buf(const sso_p1_params_t* params, size_t n_chu
     return sso_p1_verify_chunk_buf(&params[i], challenges[i], challenge_lens[i], responses[i], response_lens[i], new_challenges[i],
                                    new_challenge_lens[i], check_input, check_output, subgroup_check_mode, ratio_check, rlc_seed32, dev, e, ec);
   });
-}
-
-// phase1_cli::transform_pok_and_correctness(challenge_fn, challenge_hash_fn, check_input, response_fn, response_hash_fn,
-//                                           check_output, new_challenge_fn, new_challenge_hash_fn, subgroup_check_mode, ratio_check, params)
-int32_t sso_p1_verify_chunk_file(const sso_p1_params_t* p, const char* challenge_fn, const char* challenge_hash_fn, uint32_t check_input,
-                                 const char* response_fn, const char* response_hash_fn, uint32_t check_output,
-                                 const char* new_challenge_fn, const char* new_challenge_hash_fn, uint32_t subgroup_check_mode,
-                                 uint32_t ratio_check, int device, char* err, size_t errcap) {
-  P1Layout L;
-  int rc = p1_layout(p, L, err, errcap);
-  if (rc) return rc;
-  std::vector<uint8_t> challenge, response;
-  if ((rc = read_file(challenge_fn, challenge, err, errcap))) return rc;
-  if ((rc = read_file(response_fn, response, err, errcap))) return rc;
-  if (challenge.size() != L.acc_size) { set_err(err, errcap, "The size of challenge file should be correct: %zu != %llu", challenge.size(), (unsigned long long)L.acc_size); return SSO_E_ARG; }
-  if (response.size() != L.contrib_size) { set_err(err, errcap, "The size of response file should be correct: %zu != %llu", response.size(), (unsigned long long)L.contrib_size); return SSO_E_ARG; }
-  std::vector<uint8_t> new_challenge(L.acc_size);
-  if ((rc = sso_p1_verify_chunk_buf(p, challenge.data(), challenge.size(), response.data(), response.size(), new_challenge.data(),
-                                    new_challenge.size(), check_input, check_output, subgroup_check_mode, ratio_check, nullptr, device,
-                                    err, errcap))) return rc;
-  uint8_t h[64];
-  blake2b_512(challenge.data(), challenge.size(), h);
-  if ((rc = write_new_file(challenge_hash_fn, h, 64, err, errcap))) return rc;
-  if ((rc = write_new_file(response_hash_fn, new_challenge.data(), 64, err, errcap))) return rc;   // new_challenge[0..64) = hash(response)
-  if ((rc = write_new_file(new_challenge_fn, new_challenge.data(), new_challenge.size(), err, errcap))) return rc;
-  blake2b_512(new_challenge.data(), new_challenge.size(), h);
-  return write_new_file(new_challenge_hash_fn, h, 64, err, errcap);
 }
 
 // sum of n uncompressed points on host buffers (combining all-gathered per-GPU partial MSM results)
@@ -690,7 +714,8 @@ int32_t sso_p2_verify_queries_buf(uint32_t curve, const uint8_t* before, size_t 
   CUDA_TRY(cudaMemcpyAsync(d_a, after, after_len, cudaMemcpyHostToDevice, c.s[0]));
   if ((rc = ops->reencode(c, 0, GROUP_G1, d_b, before_compressed, n, nullptr, 0, SSO_CHECK_NO, 0, d_aff_b, d_status, err, errcap))) return rc;
   if ((rc = ops->reencode(c, 0, GROUP_G1, d_a, after_compressed, n, nullptr, 0, check, subgroup_check, d_aff_a, d_status, err, errcap))) return rc;
-  if ((rc = ops->msm_pairs(c, 0, GROUP_G1, d_aff_b, d_aff_a, n, rlc_seed32, d_pair, err, errcap))) return rc;
+  const uint64_t tweak[4] = {TWEAK_P2_VERIFY, n, 0, 0};
+  if ((rc = ops->msm_pairs(c, 0, GROUP_G1, d_aff_b, d_aff_a, n, rlc_seed32, tweak, d_pair, err, errcap))) return rc;
   if ((rc = sync_all(c, err, errcap))) return rc;
   if ((rc = check_status(c, d_status, "query", err, errcap))) return rc == SSO_E_INPUT ? SSO_E_VERIFY : rc;
   std::vector<uint8_t> pair(2 * cs.g1u);
@@ -698,6 +723,441 @@ int32_t sso_p2_verify_queries_buf(uint32_t curve, const uint8_t* before, size_t 
   std::vector<RatioCheck> checks;
   add_check(checks, "phase-2 query vs delta_g2", pair.data(), pair.data() + cs.g1u, cs.g1u, delta_g2_after, delta_g2_before, cs.g2u);
   return run_checks(c, ops, checks, err, errcap);
+}
+
+// ---------------------------------------------------------------------------------------------
+// process group (one GPU per process, e.g. under torchrun): the communicator of the cooperative calls
+// ---------------------------------------------------------------------------------------------
+int32_t sso_dist_unique_id(uint8_t out[128], char* err, size_t errcap) {
+  const NcclApi* api = nccl_api(err, errcap);
+  if (!api) return SSO_E_CUDA;
+  ncclUniqueId id;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  NCCL_TRY(api, api->GetUniqueId(&id));
+  memcpy(out, &id, 128);
+  return SSO_OK;
+}
+
+int32_t sso_dist_init(int32_t rank, int32_t world, const uint8_t id128[128], int device, char* err, size_t errcap) {
+  if (world < 1 || rank < 0 || rank >= world || !id128) { set_err(err, errcap, "bad process-group arguments"); return SSO_E_ARG; }
+  const NcclApi* api = nccl_api(err, errcap);
+  if (!api) return SSO_E_CUDA;
+  std::lock_guard<std::mutex> g(dist_mutex());
+  DistState& d = dist_state();
+  if (d.on) { set_err(err, errcap, "process group already initialised"); return SSO_E_ARG; }
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess || device < 0 || device >= cnt) { set_err(err, errcap, "device %d out of range", device); return SSO_E_ARG; }
+  int prev = 0;
+  cudaGetDevice(&prev);
+  CUDA_TRY(cudaSetDevice(device));
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  NCCL_TRY(api, api->CommInitRank(&d.comm, world, id, rank));
+  cudaSetDevice(prev);
+  d.rank = rank; d.world = world; d.device = device; d.on = true; d.collectives = 0;
+  return SSO_OK;
+}
+
+// all-reduce (sum) of one integer across the group: a barrier that also spreads a failure flag
+static int32_t dist_sum(int32_t mine, int32_t* total, char* err, size_t errcap) {
+  DistState& d = dist_state();
+  *total = mine;
+  if (!d.on || d.world == 1) return SSO_OK;
+  const NcclApi* api = nccl_api(err, errcap);
+  if (!api) return SSO_E_CUDA;
+  Ctx c(err, errcap);
+  int rc = c.init(d.device);
+  if (rc) return rc;
+  int32_t* d_v;
+  if ((rc = c.alloc((void**)&d_v, 4))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(d_v, &mine, 4, cudaMemcpyHostToDevice, c.s[0]));
+  {
+    std::lock_guard<std::mutex> g(dist_mutex());
+    NCCL_TRY(api, api->AllReduce(d_v, d_v, 1, ncclInt32, ncclSum, d.comm, c.s[0]));
+  }
+  CUDA_TRY(cudaMemcpyAsync(total, d_v, 4, cudaMemcpyDeviceToHost, c.s[0]));
+  CUDA_TRY(cudaStreamSynchronize(c.s[0]));
+  return SSO_OK;
+}
+
+int32_t sso_dist_barrier(char* err, size_t errcap) {
+  int32_t t;
+  return dist_sum(0, &t, err, errcap);
+}
+
+int32_t sso_dist_finalize(void) {
+  std::lock_guard<std::mutex> g(dist_mutex());
+  DistState& d = dist_state();
+  if (d.on) {
+    char e[64];
+    const NcclApi* api = nccl_api(e, sizeof e);
+    if (api && d.comm) api->CommDestroy(d.comm);
+    d = DistState();
+  }
+  return SSO_OK;
+}
+
+// out: [0] initialised, [1] rank, [2] world size, [3] all-gathers issued by the cooperative calls so far, [4] NCCL version
+int32_t sso_dist_stats(uint64_t out[5]) {
+  DistState& d = dist_state();
+  out[0] = d.on; out[1] = (uint64_t)d.rank; out[2] = (uint64_t)d.world; out[3] = d.collectives; out[4] = 0;
+  char e[64];
+  const NcclApi* api = d.on || d.collectives ? nccl_api(e, sizeof e) : nullptr;
+  int v = 0;
+  if (api && api->GetVersion(&v) == ncclSuccess) out[4] = (uint64_t)v;
+  return SSO_OK;
+}
+
+// every rank of a cooperative call must leave it with the same verdict: the failure flags are summed
+static int32_t coop_result(bool coop, int32_t rc, char* err, size_t errcap) {
+  if (!coop) return rc;
+  int32_t total = 0;
+  char e2[256];
+  int32_t rc2 = dist_sum(rc != SSO_OK ? 1 : 0, &total, e2, sizeof e2);
+  if (rc != SSO_OK) return rc;
+  if (rc2 != SSO_OK) { set_err(err, errcap, "%s", e2); return rc2; }
+  if (total != 0) { set_err(err, errcap, "another rank of the process group failed this call"); return SSO_E_VERIFY; }
+  return SSO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// generators
+// ---------------------------------------------------------------------------------------------
+int32_t sso_p1_set_generators(uint32_t curve, const uint8_t* g1_uncompressed, size_t g1_len, const uint8_t* g2_uncompressed, size_t g2_len,
+                              int device, char* err, size_t errcap) {
+  const CurveOps* ops = ops_for(curve);
+  CurveSizes cs;
+  if (!ops || !curve_sizes(curve, cs)) { set_err(err, errcap, "unknown curve %u", curve); return SSO_E_ARG; }
+  if (!g1_uncompressed && !g2_uncompressed) {                       // back to the built-in constants
+    std::lock_guard<std::mutex> g(gen_mutex());
+    gen_override(curve) = GenOverride();
+    return SSO_OK;
+  }
+  if (!g1_uncompressed || !g2_uncompressed || g1_len != cs.g1u || g2_len != cs.g2u) { set_err(err, errcap, "generators must be one uncompressed G1 point (%llu bytes) and one uncompressed G2 point (%llu bytes)", (unsigned long long)cs.g1u, (unsigned long long)cs.g2u); return SSO_E_ARG; }
+  // a generator must be a non-zero point of the order-r subgroup
+  Ctx c(err, errcap);
+  int rc = c.init(device);
+  if (rc) return rc;
+  uint8_t* d_pts;
+  uint32_t* d_status;
+  if ((rc = c.alloc((void**)&d_pts, cs.g1u + cs.g2u))) return rc;
+  if ((rc = status_buffer(c, &d_status, err, errcap))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(d_pts, g1_uncompressed, cs.g1u, cudaMemcpyHostToDevice, c.s[0]));
+  CUDA_TRY(cudaMemcpyAsync(d_pts + cs.g1u, g2_uncompressed, cs.g2u, cudaMemcpyHostToDevice, c.s[0]));
+  if ((rc = ops->reencode(c, 0, GROUP_G1, d_pts, 0, 1, nullptr, 0, CHECK_FULL, 1, nullptr, d_status, err, errcap))) return rc;
+  if ((rc = ops->reencode(c, 0, GROUP_G2, d_pts + cs.g1u, 0, 1, nullptr, 0, CHECK_FULL, 1, nullptr, d_status, err, errcap))) return rc;
+  if ((rc = sync_all(c, err, errcap))) return rc;
+  if ((rc = check_status(c, d_status, "generator", err, errcap))) return SSO_E_ARG;
+  std::lock_guard<std::mutex> g(gen_mutex());
+  GenOverride& o = gen_override(curve);
+  o.g1u.assign(g1_uncompressed, g1_uncompressed + cs.g1u);
+  o.g2u.assign(g2_uncompressed, g2_uncompressed + cs.g2u);
+  o.set = true;
+  return SSO_OK;
+}
+
+}  // extern "C" (kernel below)
+
+// n copies of one serialized point
+__global__ void k_fill_pattern(uint64_t n, const uint8_t* pattern, uint32_t size, uint8_t* out) {
+  uint64_t total = n * size;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) out[i] = pattern[i % size];
+}
+
+namespace {
+// n copies of the group generator into device memory (built-in constant or the caller's override)
+int fill_generators(Ctx& c, int si, const CurveOps* ops, const CurveSizes& cs, uint32_t curve, uint32_t group, uint64_t n, uint8_t* d_out,
+                    uint32_t out_compressed, char* err, size_t errcap) {
+  if (n == 0) return SSO_OK;
+  std::vector<uint8_t> pt;
+  {
+    std::lock_guard<std::mutex> g(gen_mutex());
+    const GenOverride& o = gen_override(curve);
+    if (o.set) pt = group == GROUP_G1 ? o.g1u : o.g2u;
+  }
+  if (pt.empty()) return ops->fill_generator(c, si, group, n, d_out, out_compressed, err, errcap);
+  int rc;
+  const size_t usz = point_size(cs, group, 0), osz = point_size(cs, group, out_compressed);
+  uint8_t *d_u, *d_pat;
+  uint32_t* d_status;
+  if ((rc = c.alloc((void**)&d_u, usz, si))) return rc;
+  if ((rc = c.alloc((void**)&d_pat, osz, si))) return rc;
+  if ((rc = c.alloc((void**)&d_status, STATUS_BYTES, si))) return rc;
+  c.staging.emplace_back((usz + 3) / 4, 0u);
+  memcpy(c.staging.back().data(), pt.data(), usz);
+  CUDA_TRY(cudaMemsetAsync(d_status, 0, STATUS_BYTES, c.s[si]));
+  CUDA_TRY(cudaMemcpyAsync(d_u, c.staging.back().data(), usz, cudaMemcpyHostToDevice, c.s[si]));
+  if ((rc = ops->reencode(c, si, group, d_u, 0, 1, d_pat, out_compressed, CHECK_NO, 0, nullptr, d_status, err, errcap))) return rc;
+  uint64_t total = n * osz;
+  uint32_t blocks = (uint32_t)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+  c.begin(PK_FILL, si, n);
+  k_fill_pattern<<<blocks, 256, 0, c.s[si]>>>(n, d_pat, (uint32_t)osz, d_out);
+  c.end(si);
+  CUDA_TRY(cudaGetLastError());
+  return SSO_OK;
+}
+
+bool is_coop(const sso_p1_params_t* p) { return p && p->contribution_mode == SSO_MODE_FULL && dist_state().on; }
+}  // namespace
+
+extern "C" {
+
+// phase1_cli::new_challenge(challenge_fn, challenge_hash_fn, params) — reference src/bin/new_setup.rs:105-109,
+// src/bin/verify_transcript.rs:322-326: every element the generator, hash slot = Blake2b-512 of the empty string; writes the
+// accumulator (uncompressed) and the 64 raw bytes of its hash
+int32_t sso_p1_new_challenge_file(const char* challenge_fn, const char* challenge_hash_fn, const sso_p1_params_t* p, int device, char* err,
+                                  size_t errcap) {
+  P1Layout L;
+  int rc = p1_layout(p, L, err, errcap);
+  if (rc) return rc;
+  if (!challenge_fn || !challenge_hash_fn) { set_err(err, errcap, "null argument"); return SSO_E_ARG; }
+  const CurveOps* ops = ops_for(p->curve);
+  MappedFile out;
+  if ((rc = out.create(challenge_fn, L.acc_size, true, err, errcap))) return rc;
+  blake2b_512(nullptr, 0, out.p);
+  const uint64_t counts[5] = {L.g1n, L.on, L.on, L.on, 1};
+  static const uint32_t groups[5] = {GROUP_G1, GROUP_G2, GROUP_G1, GROUP_G1, GROUP_G2};
+  {
+    Ctx c(err, errcap);
+    if ((rc = c.init(device < 0 ? 0 : device, 1))) return rc;
+    const uint64_t piece = 1ull << 20;
+    for (int v = 0; v < 5; v++) {
+      const size_t usz = point_size(L.cs, groups[v], 0);
+      for (uint64_t lo = 0; lo < counts[v]; lo += piece) {
+        uint64_t cnt = lo + piece < counts[v] ? piece : counts[v] - lo;
+        uint8_t* d_buf;
+        if ((rc = c.alloc((void**)&d_buf, cnt * usz))) return rc;
+        if ((rc = fill_generators(c, 0, ops, L.cs, p->curve, groups[v], cnt, d_buf, 0, err, errcap))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(out.p + L.off_u[v] + lo * usz, d_buf, cnt * usz, cudaMemcpyDeviceToHost, c.s[0]));
+        if ((rc = c.recycle())) return rc;
+      }
+    }
+  }
+  uint8_t h[64];
+  blake2b_512(out.p, L.acc_size, h);
+  std::vector<SmallFile> small;
+  if ((rc = write_small(small, challenge_hash_fn, h, 64, err, errcap))) return rc;
+  if ((rc = out.commit(err, errcap))) { discard_small(small); return rc; }
+  return commit_small(small, err, errcap);
+}
+
+// phase1_cli::contribute(challenge_fn, challenge_hash_fn, response_fn, response_hash_fn, check_input, batch_exp_mode, params, rng)
+// — reference src/bin/contribute.rs:811-823, src/bin/verify_transcript.rs:678-696 (beacon, Full mode), src/bin/control.rs:793-808.
+// rng -> the 32-byte seed of derive_rng_from_seed.  Full-mode calls with a process group are cooperative (every rank calls).
+int32_t sso_p1_contribute_file(const sso_p1_params_t* p, const char* challenge_fn, const char* challenge_hash_fn,
+                               const char* response_fn, const char* response_hash_fn, uint32_t check_input, uint32_t batch_exp_mode,
+                               const uint8_t seed32[32], int device, char* err, size_t errcap) {
+  (void)batch_exp_mode;                                    // outputs are mode-independent
+  P1Layout L;
+  int rc = p1_layout(p, L, err, errcap);
+  if (rc) return rc;
+  if (!challenge_fn || !challenge_hash_fn || !response_fn || !response_hash_fn || !seed32) { set_err(err, errcap, "null argument"); return SSO_E_ARG; }
+  const bool coop = is_coop(p), lead = !coop || dist_state().rank == 0;
+  MappedFile in, out;
+  std::vector<SmallFile> small;
+  auto body = [&]() -> int32_t {
+    int32_t rc;
+    if ((rc = in.open_ro(challenge_fn, err, errcap))) return rc;
+    if (in.len != L.acc_size) { set_err(err, errcap, "The size of challenge file should be correct: %zu != %llu", in.len, (unsigned long long)L.acc_size); return SSO_E_ARG; }
+    if (lead && (rc = out.create(response_fn, L.contrib_size, true, err, errcap))) return rc;
+    return SSO_OK;
+  };
+  rc = coop_result(coop, body(), err, errcap);                       // the leader's partial file exists before the others open it
+  if (rc) return rc;
+  auto body2 = [&]() -> int32_t {
+    int32_t rc;
+    if (!lead && (rc = out.create(response_fn, L.contrib_size, false, err, errcap))) return rc;
+    return contribute_buf_core(p, in.p, in.len, out.p, out.len, nullptr, nullptr, nullptr, nullptr, 0, seed32, check_input, device, err, errcap);
+  };
+  rc = coop_result(coop, body2(), err, errcap);                      // every rank's pieces are in the shared mapping
+  if (rc) return rc;
+  auto body3 = [&]() -> int32_t {
+    int32_t rc;
+    if (!lead) { out.unmap(); out.committed = true; return SSO_OK; }
+    uint8_t h[64];
+    if ((rc = write_small(small, challenge_hash_fn, out.p, 64, err, errcap))) return rc;       // response[0..64) = hash(challenge)
+    blake2b_512(out.p, out.len, h);
+    if ((rc = write_small(small, response_hash_fn, h, 64, err, errcap))) return rc;
+    if ((rc = out.commit(err, errcap))) return rc;
+    return commit_small(small, err, errcap);
+  };
+  rc = body3();
+  if (rc) discard_small(small);
+  return coop_result(coop, rc, err, errcap);
+}
+
+// phase1_cli::transform_pok_and_correctness(challenge_fn, challenge_hash_fn, check_input, response_fn, response_hash_fn,
+//                                           check_output, new_challenge_fn, new_challenge_hash_fn, subgroup_check_mode, ratio_check, params)
+// — reference src/bin/contribute.rs:968-986, src/bin/verify_transcript.rs:466-484, 746-776 (Full mode), src/bin/control.rs:841-865
+int32_t sso_p1_verify_chunk_file(const sso_p1_params_t* p, const char* challenge_fn, const char* challenge_hash_fn, uint32_t check_input,
+                                 const char* response_fn, const char* response_hash_fn, uint32_t check_output,
+                                 const char* new_challenge_fn, const char* new_challenge_hash_fn, uint32_t subgroup_check_mode,
+                                 uint32_t ratio_check, int device, char* err, size_t errcap) {
+  P1Layout L;
+  int rc = p1_layout(p, L, err, errcap);
+  if (rc) return rc;
+  if (!challenge_fn || !challenge_hash_fn || !response_fn || !response_hash_fn || !new_challenge_fn || !new_challenge_hash_fn) { set_err(err, errcap, "null argument"); return SSO_E_ARG; }
+  const bool coop = is_coop(p), lead = !coop || dist_state().rank == 0;
+  MappedFile ch, resp, out;
+  std::vector<SmallFile> small;
+  uint8_t ch_hash[64];
+  auto body = [&]() -> int32_t {
+    int32_t rc;
+    if ((rc = ch.open_ro(challenge_fn, err, errcap))) return rc;
+    if ((rc = resp.open_ro(response_fn, err, errcap))) return rc;
+    if (ch.len != L.acc_size) { set_err(err, errcap, "The size of challenge file should be correct: %zu != %llu", ch.len, (unsigned long long)L.acc_size); return SSO_E_ARG; }
+    if (resp.len != L.contrib_size) { set_err(err, errcap, "The size of response file should be correct: %zu != %llu", resp.len, (unsigned long long)L.contrib_size); return SSO_E_ARG; }
+    if (lead && (rc = out.create(new_challenge_fn, L.acc_size, true, err, errcap))) return rc;
+    return SSO_OK;
+  };
+  rc = coop_result(coop, body(), err, errcap);
+  if (rc) return rc;
+  auto body2 = [&]() -> int32_t {
+    int32_t rc;
+    if (!lead && (rc = out.create(new_challenge_fn, L.acc_size, false, err, errcap))) return rc;
+    return verify_chunk_core(p, ch.p, ch.len, resp.p, resp.len, out.p, out.len, check_input, check_output, subgroup_check_mode, ratio_check,
+                             nullptr, device, ch_hash, err, errcap);
+  };
+  rc = coop_result(coop, body2(), err, errcap);
+  if (rc) return rc;
+  auto body3 = [&]() -> int32_t {
+    int32_t rc;
+    if (!lead) { out.unmap(); out.committed = true; return SSO_OK; }
+    uint8_t h[64];
+    if ((rc = write_small(small, challenge_hash_fn, ch_hash, 64, err, errcap))) return rc;
+    if ((rc = write_small(small, response_hash_fn, out.p, 64, err, errcap))) return rc;         // new_challenge[0..64) = hash(response)
+    blake2b_512(out.p, out.len, h);
+    if ((rc = write_small(small, new_challenge_hash_fn, h, 64, err, errcap))) return rc;
+    if ((rc = out.commit(err, errcap))) return rc;
+    return commit_small(small, err, errcap);
+  };
+  rc = body3();
+  if (rc) discard_small(small);
+  return coop_result(coop, rc, err, errcap);
+}
+
+// phase1_cli::combine(response_list_fn, combined_fn, params) — reference src/bin/verify_transcript.rs:603-607,
+// src/bin/control.rs:564-568.  `params` are the chunk-0 parameters of the ceremony (as the reference passes them); the list file
+// names one response (compressed + public key) per chunk, in chunk order.  Output: the Full-mode accumulator, uncompressed, hash
+// slot zero ([UP] Phase1::aggregation writes the vectors only).  devices / ndev: the GPUs of this process to decode on (NULL / 0 =
+// `device`); with a process group every rank decodes its share of the pieces into the shared mapping.
+int32_t sso_p1_combine_file(const char* response_list_fn, const char* combined_fn, const sso_p1_params_t* p, const int* devices, int ndev,
+                            int device, char* err, size_t errcap) {
+  if (!response_list_fn || !combined_fn || !p) { set_err(err, errcap, "null argument"); return SSO_E_ARG; }
+  sso_p1_params_t full = *p;
+  full.contribution_mode = SSO_MODE_FULL; full.chunk_index = 0;
+  P1Layout LF;
+  int rc = p1_layout(&full, LF, err, errcap);
+  if (rc) return rc;
+  if (p->chunk_size == 0) { set_err(err, errcap, "combine needs the chunk size of the ceremony"); return SSO_E_ARG; }
+  const CurveOps* ops = ops_for(p->curve);
+  const bool coop = dist_state().on, lead = !coop || dist_state().rank == 0;
+  // the list of response files
+  std::vector<std::string> names;
+  {
+    std::vector<uint8_t> txt;
+    if ((rc = read_file(response_list_fn, txt, err, errcap))) return rc;
+    std::string cur;
+    for (uint8_t ch : txt) {
+      if (ch == '\n' || ch == '\r') { if (!cur.empty()) names.push_back(cur); cur.clear(); }
+      else cur.push_back((char)ch);
+    }
+    if (!cur.empty()) names.push_back(cur);
+  }
+  const uint64_t nchunks = (LF.powers_g1_length + p->chunk_size - 1) / p->chunk_size;
+  if (names.size() != nchunks) { set_err(err, errcap, "response list names %zu files, the ceremony has %llu chunks", names.size(), (unsigned long long)nchunks); return SSO_E_ARG; }
+  std::vector<std::unique_ptr<MappedFile>> ins(nchunks);
+  MappedFile out;
+  std::vector<RVec> vecs;
+  static const uint32_t groups[5] = {GROUP_G1, GROUP_G2, GROUP_G1, GROUP_G1, GROUP_G2};
+  static const char* vnames[5] = {"tau_g1", "tau_g2", "alpha_g1", "beta_g1", "beta_g2"};
+  auto body = [&]() -> int32_t {
+    int32_t rc;
+    if (lead && (rc = out.create(combined_fn, LF.acc_size, true, err, errcap))) return rc;
+    return SSO_OK;
+  };
+  if ((rc = coop_result(coop, body(), err, errcap))) return rc;
+  auto body2 = [&]() -> int32_t {
+    int32_t rc;
+    if (!lead && (rc = out.create(combined_fn, LF.acc_size, false, err, errcap))) return rc;
+    for (uint64_t k = 0; k < nchunks; k++) {
+      sso_p1_params_t pk = *p;
+      pk.contribution_mode = SSO_MODE_CHUNKED; pk.chunk_index = k;
+      P1Layout L;
+      if ((rc = p1_layout(&pk, L, err, errcap))) return rc;
+      ins[k].reset(new MappedFile());
+      if ((rc = ins[k]->open_ro(names[k].c_str(), err, errcap))) return rc;
+      if (ins[k]->len != L.contrib_size) { set_err(err, errcap, "The size of response file %s should be correct: %zu != %llu", names[k].c_str(), ins[k]->len, (unsigned long long)L.contrib_size); return SSO_E_ARG; }
+      const uint64_t counts[5] = {L.g1n, L.on, L.on, L.on, k == 0 ? 1ull : 0ull};       // beta_g2 is taken from the first chunk
+      for (int v = 0; v < 5; v++) {
+        if (counts[v] == 0) continue;
+        const size_t usz = point_size(L.cs, groups[v], 0);
+        vecs.push_back({groups[v], ins[k]->p + L.off_c[v], 1, counts[v], out.p + LF.off_u[v] + (v == 4 ? 0 : L.start * usz), 0, 0,
+                        CHECK_NO, 0, 0, vnames[v]});
+      }
+    }
+    Participants P;
+    if ((rc = resolve_participants(devices, ndev, device, true, P, err, errcap))) return rc;
+    return stream_reencode(ops, LF.cs, vecs, p->batch_size, nullptr, 0, P, nullptr, err, errcap);
+  };
+  if ((rc = coop_result(coop, body2(), err, errcap))) return rc;
+  if (lead) { memset(out.p, 0, 64); rc = out.commit(err, errcap); }
+  else { out.unmap(); out.committed = true; }
+  return coop_result(coop, rc, err, errcap);
+}
+
+// phase1_cli::transform_ratios(response_fn, check_input, params) — reference src/bin/verify_transcript.rs:646-653, 811-822,
+// src/bin/control.rs:587-591, 866-873: consistency of a whole (Full-mode, uncompressed) accumulator.  Element 0 of tau_g1 /
+// tau_g2 must be the generators; power_pairs(tau_g1), power_pairs(alpha_g1), power_pairs(beta_g1) against (tau_g2[0], tau_g2[1]);
+// power_pairs(tau_g2) against (tau_g1[0], tau_g1[1]); beta_g2 against beta_g1[0].  The vectors are streamed in pieces over the
+// participants (devices / ndev of this process, or the ranks of the process group); the per-participant partial sums are
+// exchanged with ONE all-gather and added.  rlc_seed32: NULL (fresh entropy) outside tests.
+int32_t sso_p1_verify_ratios_file(const sso_p1_params_t* p, const char* combined_fn, uint32_t check_input, const int* devices, int ndev,
+                                  int device, const uint8_t* rlc_seed32, char* err, size_t errcap) {
+  if (!p || !combined_fn) { set_err(err, errcap, "null argument"); return SSO_E_ARG; }
+  sso_p1_params_t full = *p;
+  full.contribution_mode = SSO_MODE_FULL; full.chunk_index = 0;
+  P1Layout L;
+  int rc = p1_layout(&full, L, err, errcap);
+  if (rc) return rc;
+  const CurveOps* ops = ops_for(p->curve);
+  const bool coop = dist_state().on;
+  const size_t g1u = L.cs.g1u, g2u = L.cs.g2u;
+  auto body = [&]() -> int32_t {
+    int32_t rc;
+    MappedFile in;
+    if ((rc = in.open_ro(combined_fn, err, errcap))) return rc;
+    if (in.len != L.acc_size) { set_err(err, errcap, "The size of the combined file should be correct: %zu != %llu", in.len, (unsigned long long)L.acc_size); return SSO_E_ARG; }
+    Participants P;
+    if ((rc = resolve_participants(devices, ndev, device, true, P, err, errcap))) return rc;
+    const uint64_t counts[5] = {L.g1n, L.on, L.on, L.on, 1};
+    static const uint32_t groups[5] = {GROUP_G1, GROUP_G2, GROUP_G1, GROUP_G1, GROUP_G2};
+    static const char* vnames[5] = {"tau_g1", "tau_g2", "alpha_g1", "beta_g1", "beta_g2"};
+    // transform_ratios deserialises with the caller's CheckForCorrectness; the pairings below need curve points, so the
+    // on-curve test runs whatever the setting (uncompressed input)
+    const uint32_t check = check_input == CHECK_NO ? (uint32_t)CHECK_NONZERO : check_input;
+    std::vector<RVec> vecs;
+    for (int v = 0; v < 5; v++)
+      vecs.push_back({groups[v], in.p + L.off_u[v], 0, counts[v], nullptr, 0, v < 4 ? 1u : 0u, CHECK_FULL, check == CHECK_FULL ? 1u : 0u,
+                      TWEAK_P1_RATIOS | (uint64_t)v, vnames[v]});
+    std::vector<std::vector<uint8_t>> pairs;
+    if ((rc = stream_reencode(ops, L.cs, vecs, p->batch_size, rlc_seed32, 0, P, &pairs, err, errcap))) return rc == SSO_E_INPUT ? SSO_E_VERIFY : rc;
+    Ctx c(err, errcap);
+    if ((rc = c.init(P.devices[0], 1))) return rc;
+    std::vector<uint8_t> gen(g1u + g2u);
+    if ((rc = generator_bytes(c, ops, L.cs, p->curve, gen.data(), err, errcap))) return rc;
+    const uint8_t *g1_0 = in.p + L.off_u[0], *g1_1 = g1_0 + g1u, *g2_0 = in.p + L.off_u[1], *g2_1 = g2_0 + g2u;
+    if (memcmp(g1_0, gen.data(), g1u) != 0) { set_err(err, errcap, "tau_g1[0] is not the G1 generator"); return SSO_E_VERIFY; }
+    if (memcmp(g2_0, gen.data() + g1u, g2u) != 0) { set_err(err, errcap, "tau_g2[0] is not the G2 generator"); return SSO_E_VERIFY; }
+    std::vector<RatioCheck> checks;
+    add_check(checks, "power ratio: tau_g1", pairs[0].data(), pairs[0].data() + g1u, g1u, g2_0, g2_1, g2u);
+    add_check(checks, "power ratio: tau_g2", g1_0, g1_1, g1u, pairs[1].data(), pairs[1].data() + g2u, g2u);
+    add_check(checks, "power ratio: alpha_g1", pairs[2].data(), pairs[2].data() + g1u, g1u, g2_0, g2_1, g2u);
+    add_check(checks, "power ratio: beta_g1", pairs[3].data(), pairs[3].data() + g1u, g1u, g2_0, g2_1, g2u);
+    add_check(checks, "beta_g1[0] vs beta_g2", g1_0, in.p + L.off_u[3], g1u, g2_0, in.p + L.off_u[4], g2u);
+    return run_checks(c, ops, checks, err, errcap);
+  };
+  return coop_result(coop, body(), err, errcap);
 }
 
 int32_t sso_imad_peak(int device, int variant, double* macs_per_s, char* err, size_t errcap) {

@@ -7,6 +7,7 @@
 #include "msm.cuh"
 #include "pairing.cuh"
 #include "keygen.cuh"
+#include "blake2b.h"
 #include <cub/device/device_radix_sort.cuh>
 #include <random>
 
@@ -28,8 +29,10 @@ struct CurveOps {
                   size_t errcap);
   // K5: (sum r_i a_i, sum r_i b_i) for two affine Montgomery point arrays ([point][x|y] words, zero = infinity) with
   // ChaCha20(seed32) scalars; writes the two points uncompressed to d_out (2 * uncompressed size bytes)
+  // tweak (4 words, may be null): with a caller-supplied seed the ChaCha20 key of this MSM is Blake2b-256(seed32 || tweak),
+  // so that the MSMs of one verification (vectors, chunks, pieces, ranks) never share their scalars; null = seed32 as is
   int (*msm_pairs)(Ctx& c, int si, uint32_t group, const uint32_t* d_aff_a, const uint32_t* d_aff_b, uint64_t n,
-                   const uint8_t seed32[32], uint8_t* d_out, char* err, size_t errcap);
+                   const uint8_t seed32[32], const uint64_t* tweak, uint8_t* d_out, char* err, size_t errcap);
   // K8: same_ratio verdicts for n checks laid out a | b | c | d (uncompressed); verdict 1 = equal ratios,
   // 0 = different, 0x100 + code = undecodable input
   int (*same_ratio)(Ctx& c, int si, const uint8_t* d_checks, uint64_t n, uint32_t* d_verdicts, char* err, size_t errcap);
@@ -362,7 +365,7 @@ inline uint32_t msm_window_bits(uint64_t n, uint32_t sbits) {
 
 template <class G>
 inline int run_msm_pairs(Ctx& c, int si, const uint32_t* d_aff_a, const uint32_t* d_aff_b, uint64_t n, const uint8_t seed32[32],
-                         uint8_t* d_out, char* err, size_t errcap) {
+                         const uint64_t* tweak, uint8_t* d_out, char* err, size_t errcap) {
   using F = typename G::F;
   using Fr = typename G::Fr;
   constexpr int KL = Fr::L;
@@ -372,10 +375,17 @@ inline int run_msm_pairs(Ctx& c, int si, const uint32_t* d_aff_a, const uint32_t
   uint32_t wb = msm_window_bits(n, SBITS), nwin = (SBITS + wb - 1) / wb, nb = 1u << wb;
   uint32_t seg = nb < MSM_SEG ? nb : MSM_SEG, nseg = nb / seg;
   size_t pairs = (size_t)n * nwin;
-  if (pairs > 0xffffffffull) { set_err(err, errcap, "msm too large for 32-bit indexing: split the vector"); return SSO_E_ARG; }
-  // scalar key: caller-supplied (tests) or fresh host entropy
+  if (pairs > 0x7fffffffull) { set_err(err, errcap, "msm too large for 32-bit indexing (cub takes an int count): split the vector"); return SSO_E_ARG; }
+  // scalar key: fresh host entropy, or — reproducible runs, tests — derived from the caller's seed and the tweak that
+  // names this MSM (vector, chunk, piece offset, rank): two MSMs with the same r_i would make the G1-vs-G2 power-ratio
+  // check vacuous for correlated vectors
   Key32 key;
-  if (seed32) memcpy(key.w, seed32, 32);
+  if (seed32 && tweak) {
+    Blake2b h(32);
+    h.update(seed32, 32);
+    h.update((const uint8_t*)tweak, 32);
+    h.final((uint8_t*)key.w, 32);
+  } else if (seed32) memcpy(key.w, seed32, 32);
   else { std::random_device rd; for (auto& w : key.w) w = rd(); }
   uint32_t *d_sc, *d_keys, *d_vals, *d_keys2, *d_vals2, *d_buckets, *d_seg, *d_win;
   void* d_tmp = nullptr;
@@ -448,9 +458,9 @@ template <class G1, class G2, class PP> struct CurveImpl {
     return SSO_E_ARG;
   }
   static int msm_pairs(Ctx& c, int si, uint32_t group, const uint32_t* d_aff_a, const uint32_t* d_aff_b, uint64_t n,
-                       const uint8_t seed32[32], uint8_t* d_out, char* err, size_t errcap) {
-    if (group == GROUP_G1) return run_msm_pairs<G1>(c, si, d_aff_a, d_aff_b, n, seed32, d_out, err, errcap);
-    if (group == GROUP_G2) return run_msm_pairs<G2>(c, si, d_aff_a, d_aff_b, n, seed32, d_out, err, errcap);
+                       const uint8_t seed32[32], const uint64_t* tweak, uint8_t* d_out, char* err, size_t errcap) {
+    if (group == GROUP_G1) return run_msm_pairs<G1>(c, si, d_aff_a, d_aff_b, n, seed32, tweak, d_out, err, errcap);
+    if (group == GROUP_G2) return run_msm_pairs<G2>(c, si, d_aff_a, d_aff_b, n, seed32, tweak, d_out, err, errcap);
     set_err(err, errcap, "unknown group %u", group);
     return SSO_E_ARG;
   }

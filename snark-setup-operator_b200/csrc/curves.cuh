@@ -19,6 +19,10 @@ using Fq377x2 = Fp2<Fq377, SmallNR<Fq377, 5, true>>;     // u^2 = -5
 using Fq4x2 = Fp2<Fq4, SmallNR<Fq4, 13, false>>;          // u^2 = 13
 using Fq6x3 = Fp3<Fq6, SmallNR<Fq6, 11, false>>;          // u^3 = 11
 
+// cofactor 1: the curve group itself has prime order r (subgroup membership = being on the curve)
+static constexpr bool PRIME_ORDER_bls12_377_g1 = false, PRIME_ORDER_bls12_377_g2 = false, PRIME_ORDER_bw6_761_g1 = false,
+                      PRIME_ORDER_bw6_761_g2 = false, PRIME_ORDER_mnt4_753_g1 = true, PRIME_ORDER_mnt4_753_g2 = false,
+                      PRIME_ORDER_mnt6_753_g1 = true, PRIME_ORDER_mnt6_753_g2 = false;
 #define SSO_GROUP_COMMON(NAME, FIELD, SCALAR)                                                      \
   using F = FIELD;                                                                                  \
   using Fr = SCALAR;                                                                                \
@@ -27,7 +31,8 @@ using Fq6x3 = Fp3<Fq6, SmallNR<Fq6, 11, false>>;          // u^3 = 11
   __device__ __forceinline__ static typename F::T gen_x() { return F::from_const(c_##NAME##_gx); }  \
   __device__ __forceinline__ static typename F::T gen_y() { return F::from_const(c_##NAME##_gy); }  \
   __device__ __forceinline__ static const uint32_t* cofactor() { return c_##NAME##_cofactor; }      \
-  static constexpr int COFACTOR_WORDS = COFACTOR_WORDS_##NAME;
+  static constexpr int COFACTOR_WORDS = COFACTOR_WORDS_##NAME;                                     \
+  static constexpr bool PRIME_ORDER = PRIME_ORDER_##NAME;
 
 struct Bls12_377_G1 {
   static constexpr bool AFFINE_TABLE = true;

@@ -476,7 +476,9 @@ template <class Cfg> struct SW {
   //   G1: phi(P) = [-x^2]P  <=>  [x^2]P = (beta X, -Y)      127-bit instead of 253-bit multiplication
   //   G2: psi(P) = [x]P     <=>  [x]P = (conj(X) cx, conj(Y) cy)    64-bit instead of 253-bit
   __device__ __forceinline__ static bool in_subgroup(const Affine& p) {
-    if constexpr (Cfg::ENDO_SUBGROUP_TEST == 1) {
+    if constexpr (Cfg::COFACTOR_WORDS == 1 && Cfg::PRIME_ORDER) {
+      return true;                 // cofactor 1 (MNT4-753 / MNT6-753 G1): every curve point is in the group of order r
+    } else if constexpr (Cfg::ENDO_SUBGROUP_TEST == 1) {
       using E = typename Cfg::Endo;
       Jac q = mul_const(p, E::x2(), 4);
       Affine t{F::mul(p.x, F::from_const(E::beta())), F::neg(p.y), false};

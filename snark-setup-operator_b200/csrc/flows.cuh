@@ -12,6 +12,7 @@
 
 #include "blake2b.h"
 #include "curve_ops.cuh"
+#include "stream.cuh"
 
 namespace sso {
 
@@ -114,7 +115,34 @@ inline int keygen_host(Ctx& c, const CurveOps* ops, const CurveSizes& cs, const 
   return SSO_OK;
 }
 
-// ---- chunk verification (Phase1::verification, chunked mode) --------------------------------------
+// ---- generators -------------------------------------------------------------------------------------
+// The G1 / G2 generators new_challenge writes and chunk-0 verification compares against.  The built-in constants are
+// arkworks' for BLS12-377, BW6-761 and both G1 of the MNT curves; the G2 generators of MNT4-753 / MNT6-753 could not be
+// recovered in this environment and default to a derived order-r point, so the host application hands the
+// reference's constants over once per process (sso_p1_set_generators) — e.g. read from the round-0 challenge the
+// operator regenerates and compares by hash (reference src/bin/verify_transcript.rs:316-361).
+struct GenOverride { bool set = false; std::vector<uint8_t> g1u, g2u; };
+inline GenOverride& gen_override(uint32_t curve) { static GenOverride g[4]; return g[curve & 3]; }
+inline std::mutex& gen_mutex() { static std::mutex m; return m; }
+
+// uncompressed generator bytes (g1u | g2u) into `out`
+inline int generator_bytes(Ctx& c, const CurveOps* ops, const CurveSizes& cs, uint32_t curve, uint8_t* out, char* err, size_t errcap) {
+  {
+    std::lock_guard<std::mutex> g(gen_mutex());
+    const GenOverride& o = gen_override(curve);
+    if (o.set) { memcpy(out, o.g1u.data(), cs.g1u); memcpy(out + cs.g1u, o.g2u.data(), cs.g2u); return SSO_OK; }
+  }
+  uint8_t* d_gen;
+  int rc;
+  if ((rc = c.alloc((void**)&d_gen, cs.g1u + cs.g2u))) return rc;
+  if ((rc = ops->fill_generator(c, 0, GROUP_G1, 1, d_gen, 0, err, errcap))) return rc;
+  if ((rc = ops->fill_generator(c, 0, GROUP_G2, 1, d_gen + cs.g1u, 0, err, errcap))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(out, d_gen, cs.g1u + cs.g2u, cudaMemcpyDeviceToHost, c.s[0]));
+  CUDA_TRY(cudaStreamSynchronize(c.s[0]));
+  return SSO_OK;
+}
+
+// ---- chunk verification (Phase1::verification) ----------------------------------------------------------
 struct RatioCheck { std::string name; std::vector<uint8_t> bytes; };
 
 inline void add_check(std::vector<RatioCheck>& v, const char* name, const uint8_t* a, const uint8_t* b, size_t g1u, const uint8_t* cc,
@@ -152,55 +180,132 @@ inline int run_checks(Ctx& c, const CurveOps* ops, const std::vector<RatioCheck>
   return SSO_OK;
 }
 
+// The per-element policy of the verification (reference src/bin/contribute.rs:966-987):
+//   every response element must be non-zero, whatever `check_output` says ([UP] Phase1::verification reads the batches
+//   with OnlyNonZero); CheckForCorrectness::Full adds nothing for compressed input (decompression lands on the curve)
+//   but, being the "force correctness checks" setting, also forces the membership test;
+//   SubgroupCheckMode::{Auto, Direct, Batched} ask for the membership test, ::No skips it.
+inline uint32_t verify_elem_check(uint32_t check_output) { return check_output == CHECK_NO ? (uint32_t)CHECK_NONZERO : check_output; }
+inline uint32_t verify_subgroup(uint32_t check_output, uint32_t subgroup_mode) {
+  return (subgroup_mode != SSO_SUBGROUP_NO || check_output == CHECK_FULL) ? 1u : 0u;
+}
+// tweak words naming the MSMs of one verification (curve_ops.cuh::run_msm_pairs)
+static constexpr uint64_t TWEAK_P1_VERIFY = 0x7031760000000000ull, TWEAK_P1_RATIOS = 0x7031720000000000ull, TWEAK_P2_VERIFY = 0x7032760000000000ull;
+
 // challenge (uncompressed, host) + response (compressed + pubkey, host) -> new_challenge (uncompressed, host).
-// rlc_seed32: NULL = fresh entropy for the random linear combinations.
+//   P == nullptr : the chunk is resident on the context's device (two streams, all vectors at once)
+//   P != nullptr : vectors streamed in pieces of `piece_elems` over the participants (Full mode / large chunks)
+// rlc_seed32: NULL = fresh entropy for the random linear combinations (the only sound setting outside tests).
 inline int verify_chunk_host(Ctx& c, const CurveOps* ops, const P1Layout& L, uint32_t curve, uint64_t chunk_index,
-                             const uint8_t* challenge, const uint8_t* response, uint8_t* new_challenge, uint32_t check_output,
-                             uint32_t subgroup_mode, uint32_t ratio_check, const uint8_t* rlc_seed32, char* err, size_t errcap) {
+                             const uint8_t* challenge, const uint8_t* response, uint8_t* new_challenge, uint32_t check_input,
+                             uint32_t check_output, uint32_t subgroup_mode, uint32_t ratio_check, const uint8_t* rlc_seed32,
+                             const Participants* P, uint64_t piece_elems, uint8_t* ch_hash_out, char* err, size_t errcap) {
   int rc;
   const size_t g1u = L.cs.g1u, g2u = L.cs.g2u;
-  // 1. decode + check the response vectors on the device, producing the new challenge image; the GPU starts
-  //    first so that the two sequential Blake2b passes on the host (challenge, response) overlap with it
-  uint8_t *d_resp, *d_new;
-  uint32_t* d_status;
-  if ((rc = c.alloc((void**)&d_resp, L.contrib_size))) return rc;
-  if ((rc = c.alloc((void**)&d_new, L.acc_size))) return rc;
-  if ((rc = c.alloc((void**)&d_status, STATUS_BYTES))) return rc;
-  CUDA_TRY(cudaMemsetAsync(d_status, 0, STATUS_BYTES, c.s[0]));
-  CUDA_TRY(cudaMemcpyAsync(d_resp, response, L.contrib_size, cudaMemcpyHostToDevice, c.s[0]));
-  CUDA_TRY(cudaStreamSynchronize(c.s[0]));
   const uint64_t counts[5] = {L.g1n, L.on, L.on, L.on, 1};
-  const uint32_t groups[5] = {GROUP_G1, GROUP_G2, GROUP_G1, GROUP_G1, GROUP_G2};
-  const uint32_t subgroup = subgroup_mode == SSO_SUBGROUP_NO ? 0u : 1u;
-  uint32_t* d_aff[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-  if ((rc = c.fork(0, 1))) return rc;
-  for (int v = 0; v < 5; v++) {
-    if (counts[v] == 0) continue;
-    int si = groups[v] == GROUP_G2 ? 1 : 0;
-    if (ratio_check && v < 4 && counts[v] >= 2)
-      if ((rc = c.alloc((void**)&d_aff[v], counts[v] * ops->aff_words[groups[v]] * 4, si))) return rc;
-    if ((rc = ops->reencode(c, si, groups[v], d_resp + L.off_c[v], 1, counts[v], d_new + L.off_u[v], 0, check_output, subgroup,
-                            d_aff[v], d_status, err, errcap))) return rc;
+  static const uint32_t groups[5] = {GROUP_G1, GROUP_G2, GROUP_G1, GROUP_G1, GROUP_G2};
+  static const char* vnames[5] = {"response tau_g1", "response tau_g2", "response alpha_g1", "response beta_g1", "response beta_g2"};
+  static const char* inames[5] = {"challenge tau_g1", "challenge tau_g2", "challenge alpha_g1", "challenge beta_g1", "challenge beta_g2"};
+  const uint32_t elem_check = verify_elem_check(check_output), subgroup = verify_subgroup(check_output, subgroup_mode);
+  // the two sequential Blake2b passes (challenge, response) run on a host thread beside the GPU work
+  uint8_t ch_hash[64], resp_hash[64];
+  std::thread hasher([&] { blake2b_512(challenge, L.acc_size, ch_hash); blake2b_512(response, L.contrib_size, resp_hash); });
+  struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{hasher};
+  std::vector<uint8_t> pairs[4];
+  if (!P) {
+    // 1. decode + check the response vectors on the device, producing the new challenge image
+    uint8_t *d_resp, *d_new;
+    uint32_t* d_status;
+    if ((rc = c.alloc((void**)&d_resp, L.contrib_size))) return rc;
+    if ((rc = c.alloc((void**)&d_new, L.acc_size))) return rc;
+    if ((rc = c.alloc((void**)&d_status, STATUS_BYTES))) return rc;
+    CUDA_TRY(cudaMemsetAsync(d_status, 0, STATUS_BYTES, c.s[0]));
+    CUDA_TRY(cudaMemcpyAsync(d_resp, response, L.contrib_size, cudaMemcpyHostToDevice, c.s[0]));
+    CUDA_TRY(cudaStreamSynchronize(c.s[0]));
+    uint32_t* d_aff[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    if ((rc = c.fork(0, 1))) return rc;
+    for (int v = 0; v < 5; v++) {
+      if (counts[v] == 0) continue;
+      int si = groups[v] == GROUP_G2 ? 1 : 0;
+      if (ratio_check && v < 4 && counts[v] >= 2)
+        if ((rc = c.alloc((void**)&d_aff[v], counts[v] * ops->aff_words[groups[v]] * 4, si))) return rc;
+      if ((rc = ops->reencode(c, si, groups[v], d_resp + L.off_c[v], 1, counts[v], d_new + L.off_u[v], 0, elem_check, subgroup,
+                              d_aff[v], d_status, err, errcap))) return rc;
+    }
+    c.mark("verify: decode launches enqueued");
+    // 2. random-linear-combination pairs for the power-ratio checks (every MSM with its own scalars)
+    uint8_t* d_pairs[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int v = 0; v < 4; v++) {
+      if (!d_aff[v]) continue;
+      int si = groups[v] == GROUP_G2 ? 1 : 0;
+      size_t usz = groups[v] == GROUP_G1 ? g1u : g2u;
+      const uint64_t tweak[4] = {TWEAK_P1_VERIFY | (uint64_t)v, chunk_index, 0, 0};
+      if ((rc = c.alloc((void**)&d_pairs[v], 2 * usz, si))) return rc;
+      if ((rc = ops->msm_pairs(c, si, groups[v], d_aff[v], d_aff[v] + ops->aff_words[groups[v]], counts[v] - 1, rlc_seed32, tweak,
+                               d_pairs[v], err, errcap))) return rc;
+    }
+    c.mark("verify: msm launches enqueued");
+    // 2b. CheckForCorrectness on the challenge, when asked for (the operator's default is No: the challenge is the output
+    // of the previous verification): non-zero, and under Full on the curve and in the subgroup
+    uint32_t* d_status_in = nullptr;
+    if (check_input != CHECK_NO) {
+      uint8_t* d_ch;
+      if ((rc = c.alloc((void**)&d_ch, L.acc_size))) return rc;
+      if ((rc = c.alloc((void**)&d_status_in, STATUS_BYTES))) return rc;
+      CUDA_TRY(cudaMemsetAsync(d_status_in, 0, STATUS_BYTES, c.s[0]));
+      CUDA_TRY(cudaMemcpyAsync(d_ch, challenge, L.acc_size, cudaMemcpyHostToDevice, c.s[0]));
+      for (int v = 0; v < 5; v++) {
+        if (counts[v] == 0) continue;
+        if ((rc = ops->reencode(c, 0, groups[v], d_ch + L.off_u[v], 0, counts[v], nullptr, 0, check_input, check_input == CHECK_FULL ? 1u : 0u,
+                                nullptr, d_status_in, err, errcap))) return rc;
+      }
+    }
+    if ((rc = sync_all(c, err, errcap))) return rc;
+    if (d_status_in && (rc = check_status(c, d_status_in, "challenge", err, errcap))) return rc == SSO_E_INPUT ? SSO_E_VERIFY : rc;
+    if ((rc = check_status(c, d_status, "response", err, errcap))) return rc == SSO_E_INPUT ? SSO_E_VERIFY : rc;
+    CUDA_TRY(cudaMemcpy(new_challenge + 64, d_new + 64, L.acc_size - 64, cudaMemcpyDeviceToHost));
+    for (int v = 0; v < 4; v++) {
+      if (!d_pairs[v]) continue;
+      pairs[v].resize(2 * (groups[v] == GROUP_G1 ? g1u : g2u));
+      CUDA_TRY(cudaMemcpy(pairs[v].data(), d_pairs[v], pairs[v].size(), cudaMemcpyDeviceToHost));
+    }
+    c.mark("verify: results D2H");
+  } else {
+    std::vector<RVec> vecs;
+    if (check_input != CHECK_NO) {
+      for (int v = 0; v < 5; v++)
+        vecs.push_back({groups[v], challenge + L.off_u[v], 0, counts[v], nullptr, 0, 0, check_input, check_input == CHECK_FULL ? 1u : 0u, 0, inames[v]});
+      if ((rc = stream_reencode(ops, L.cs, vecs, piece_elems, nullptr, 0, *P, nullptr, err, errcap))) return rc == SSO_E_INPUT ? SSO_E_VERIFY : rc;
+      vecs.clear();
+    }
+    for (int v = 0; v < 5; v++)
+      vecs.push_back({groups[v], response + L.off_c[v], 1, counts[v], new_challenge + L.off_u[v], 0, (ratio_check && v < 4) ? 1u : 0u,
+                      elem_check, subgroup, TWEAK_P1_VERIFY | (uint64_t)v, vnames[v]});
+    std::vector<std::vector<uint8_t>> out_pairs;
+    if ((rc = stream_reencode(ops, L.cs, vecs, piece_elems, rlc_seed32, chunk_index, *P, &out_pairs, err, errcap))) return rc == SSO_E_INPUT ? SSO_E_VERIFY : rc;
+    for (int v = 0; v < 4; v++) if (ratio_check && counts[v] >= 2) pairs[v] = out_pairs[v];
   }
-  c.mark("verify: decode launches enqueued");
-  // 3. random-linear-combination pairs for the power-ratio checks
-  uint8_t* d_pairs[4] = {nullptr, nullptr, nullptr, nullptr};
-  for (int v = 0; v < 4; v++) {
-    if (!d_aff[v]) continue;
-    int si = groups[v] == GROUP_G2 ? 1 : 0;
-    size_t usz = groups[v] == GROUP_G1 ? g1u : g2u;
-    if ((rc = c.alloc((void**)&d_pairs[v], 2 * usz, si))) return rc;
-    if ((rc = ops->msm_pairs(c, si, groups[v], d_aff[v], d_aff[v] + ops->aff_words[groups[v]], counts[v] - 1, rlc_seed32, d_pairs[v],
-                             err, errcap))) return rc;
-  }
-  c.mark("verify: msm launches enqueued");
-  // 3b. hash chain (host, overlapped with the GPU work above): the response must continue the challenge
-  uint8_t ch_hash[64];
-  blake2b_512(challenge, L.acc_size, ch_hash);
+  // 3. hash chain: the response must continue the challenge; the new challenge's hash slot chains the response
+  hasher.join();
+  if (ch_hash_out) memcpy(ch_hash_out, ch_hash, 64);
   if (memcmp(ch_hash, response, 64) != 0) { set_err(err, errcap, "hash chain broken: response does not continue the challenge"); return SSO_E_VERIFY; }
-  c.mark("verify: blake2b(challenge)");
-  // 4. proof-of-knowledge seeds while the GPU works: g2_s = hash_to_g2(Blake2b(pers || digest || g1_s || g1_s_x))
+  memcpy(new_challenge, resp_hash, 64);
+  c.mark("verify: blake2b(challenge), blake2b(response)");
+  // 4. the public key: nine points that must be non-zero, on their curves and in the subgroups (a zero or torsion point would
+  // make the proof-of-knowledge pairings vacuous); then g2_s = hash_to_g2(Blake2b(pers || digest || g1_s || g1_s_x))
   const uint8_t* pk = response + L.off_c[5];
+  {
+    uint8_t* d_pk;
+    uint32_t* d_status;
+    if ((rc = c.alloc((void**)&d_pk, L.pk_size))) return rc;
+    if ((rc = c.alloc((void**)&d_status, STATUS_BYTES))) return rc;
+    CUDA_TRY(cudaMemsetAsync(d_status, 0, STATUS_BYTES, c.s[0]));
+    CUDA_TRY(cudaMemcpyAsync(d_pk, pk, L.pk_size, cudaMemcpyHostToDevice, c.s[0]));
+    if ((rc = ops->reencode(c, 0, GROUP_G1, d_pk, 0, 6, nullptr, 0, CHECK_FULL, 1, nullptr, d_status, err, errcap))) return rc;
+    if ((rc = ops->reencode(c, 0, GROUP_G2, d_pk + 6 * g1u, 0, 3, nullptr, 0, CHECK_FULL, 1, nullptr, d_status, err, errcap))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c.s[0]));
+    if ((rc = check_status(c, d_status, "public key", err, errcap))) return rc == SSO_E_INPUT ? SSO_E_VERIFY : rc;
+  }
   std::vector<uint8_t> seeds2(3 * 32);
   for (uint32_t i = 0; i < 3; i++) {
     Blake2b h(64);
@@ -217,21 +322,9 @@ inline int verify_chunk_host(Ctx& c, const CurveOps* ops, const P1Layout& L, uin
   if ((rc = c.alloc((void**)&d_g2s, 3 * g2u))) return rc;
   CUDA_TRY(cudaMemcpyAsync(d_seeds2, seeds2.data(), 96, cudaMemcpyHostToDevice, c.s[0]));
   if ((rc = ops->hash_to_g2(c, 0, 3, d_seeds2, nullptr, d_g2s, nullptr, err, errcap))) return rc;
-  // the new challenge's hash slot chains the response
-  blake2b_512(response, L.contrib_size, new_challenge);
-  c.mark("verify: blake2b(response)");
-  if ((rc = sync_all(c, err, errcap))) return rc;
-  if ((rc = check_status(c, d_status, "response", err, errcap))) return rc == SSO_E_INPUT ? SSO_E_VERIFY : rc;
-  CUDA_TRY(cudaMemcpy(new_challenge + 64, d_new + 64, L.acc_size - 64, cudaMemcpyDeviceToHost));
   std::vector<uint8_t> g2s(3 * g2u);
-  CUDA_TRY(cudaMemcpy(g2s.data(), d_g2s, g2s.size(), cudaMemcpyDeviceToHost));
-  std::vector<uint8_t> pairs[4];
-  for (int v = 0; v < 4; v++) {
-    if (!d_pairs[v]) continue;
-    pairs[v].resize(2 * (groups[v] == GROUP_G1 ? g1u : g2u));
-    CUDA_TRY(cudaMemcpy(pairs[v].data(), d_pairs[v], pairs[v].size(), cudaMemcpyDeviceToHost));
-  }
-  c.mark("verify: results D2H");
+  CUDA_TRY(cudaMemcpyAsync(g2s.data(), d_g2s, g2s.size(), cudaMemcpyDeviceToHost, c.s[0]));
+  CUDA_TRY(cudaStreamSynchronize(c.s[0]));
   // 5. collect the same_ratio checks
   std::vector<RatioCheck> checks;
   const uint8_t* pk_g2 = pk + 6 * g1u;                       // tau_g2, alpha_g2, beta_g2 (= g2_s_x)
@@ -243,12 +336,7 @@ inline int verify_chunk_host(Ctx& c, const CurveOps* ops, const P1Layout& L, uin
   if (chunk_index == 0 && L.on >= 2) {
     // element 0 must still be the generator; element 1 / alpha / beta must have moved by the proven scalars
     std::vector<uint8_t> gen(g1u + g2u);
-    uint8_t* d_gen;
-    if ((rc = c.alloc((void**)&d_gen, g1u + g2u))) return rc;
-    if ((rc = ops->fill_generator(c, 0, GROUP_G1, 1, d_gen, 0, err, errcap))) return rc;
-    if ((rc = ops->fill_generator(c, 0, GROUP_G2, 1, d_gen + g1u, 0, err, errcap))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(gen.data(), d_gen, gen.size(), cudaMemcpyDeviceToHost, c.s[0]));
-    CUDA_TRY(cudaStreamSynchronize(c.s[0]));
+    if ((rc = generator_bytes(c, ops, L.cs, curve, gen.data(), err, errcap))) return rc;
     if (memcmp(after + L.off_u[0], gen.data(), g1u) != 0) { set_err(err, errcap, "tau_g1[0] is not the G1 generator"); return SSO_E_VERIFY; }
     if (memcmp(after + L.off_u[1], gen.data() + g1u, g2u) != 0) { set_err(err, errcap, "tau_g2[0] is not the G2 generator"); return SSO_E_VERIFY; }
     add_check(checks, "before/after: tau_g1[1] vs tau proof", challenge + L.off_u[0] + g1u, after + L.off_u[0] + g1u, g1u,
@@ -260,13 +348,15 @@ inline int verify_chunk_host(Ctx& c, const CurveOps* ops, const P1Layout& L, uin
     add_check(checks, "before/after: beta_g2 vs beta_g1[0]", challenge + L.off_u[3], after + L.off_u[3], g1u,
               challenge + L.off_u[4], after + L.off_u[4], g2u);
   }
-  if (ratio_check && d_pairs[1]) {
-    // consecutive powers inside the chunk share one ratio: compare the G1 combinations with the G2 one
+  if (ratio_check && !pairs[1].empty()) {
+    // consecutive powers inside the chunk share one ratio: compare the G1 combinations with the G2 one.  A chunk past
+    // 2^power holds tau_g1 only — no G2 element to compare with: its power ratios are checked on the combined accumulator
+    // by transform_ratios ([UP]: Phase1::aggregate_verification; reference src/bin/verify_transcript.rs:811-822).
     const uint8_t* g2p = pairs[1].data();
     if (chunk_index == 0) g2p = after + L.off_u[1];           // (tau_g2[0], tau_g2[1]) exactly, as upstream
-    if (d_pairs[0]) add_check(checks, "power ratio: tau_g1", pairs[0].data(), pairs[0].data() + g1u, g1u, g2p, g2p + g2u, g2u);
-    if (d_pairs[2]) add_check(checks, "power ratio: alpha_g1", pairs[2].data(), pairs[2].data() + g1u, g1u, g2p, g2p + g2u, g2u);
-    if (d_pairs[3]) add_check(checks, "power ratio: beta_g1", pairs[3].data(), pairs[3].data() + g1u, g1u, g2p, g2p + g2u, g2u);
+    if (!pairs[0].empty()) add_check(checks, "power ratio: tau_g1", pairs[0].data(), pairs[0].data() + g1u, g1u, g2p, g2p + g2u, g2u);
+    if (!pairs[2].empty()) add_check(checks, "power ratio: alpha_g1", pairs[2].data(), pairs[2].data() + g1u, g1u, g2p, g2p + g2u, g2u);
+    if (!pairs[3].empty()) add_check(checks, "power ratio: beta_g1", pairs[3].data(), pairs[3].data() + g1u, g1u, g2p, g2p + g2u, g2u);
     if (chunk_index == 0)
       add_check(checks, "power ratio: tau_g2", after + L.off_u[0], after + L.off_u[0] + g1u, g1u, pairs[1].data(), pairs[1].data() + g2u, g2u);
   }

@@ -167,6 +167,16 @@ struct Ctx {
     allocs.push_back(*p);
     return SSO_OK;
   }
+  // between the pieces of a streamed call: hand the scratch of the finished piece back to the pool (stream-ordered)
+  // and drop the host staging copies; the streams stay
+  int recycle() {
+    for (auto& st : s) if (st) CUDA_TRY(cudaStreamSynchronize(st));
+    resolve_timings();
+    for (void* p : allocs) cudaFreeAsync(p, s[0]);
+    allocs.clear();
+    staging.clear();
+    return SSO_OK;
+  }
   // make stream `to` wait for everything enqueued so far on stream `from`
   int fork(int from, int to) {
     cudaEvent_t ev;

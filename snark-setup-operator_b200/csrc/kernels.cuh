@@ -300,7 +300,9 @@ __device__ __forceinline__ void body_normalize_write(uint32_t tid, const VecBatc
 // ---------------------------------------------------------------------------------------------
 // K3 alone: re-encode points (compressed -> uncompressed and so on) with validation — the
 // decompression half of transform_pok_and_correctness / combine.
-//   subgroup != 0 : additionally require [r]P = O (SW::in_subgroup: endomorphism form where the curve has one)
+//   check         : CHECK_NO / CHECK_NONZERO (reject infinity) / CHECK_FULL (+ on the curve, for uncompressed input)
+//   subgroup != 0 : additionally require [r]P = O (SW::in_subgroup: endomorphism form where the curve has one; nothing to do
+//                   on the prime-order groups), independently of `check`
 // Optionally leaves the affine Montgomery coordinates in `aff_out` ([point][x|y] words, inf -> all-zero)
 // for the MSM that follows.
 // ---------------------------------------------------------------------------------------------
@@ -315,12 +317,14 @@ __device__ __forceinline__ void body_reencode(uint32_t tid, uint32_t n, const ui
   uint32_t st = in_compressed ? C::read_compressed(in + (size_t)tid * C::SIZE_C, p)
                               : C::read_uncompressed(in + (size_t)tid * C::SIZE_U, p);
   if (st != C::DESER_OK) { report(status, st, tid); p.inf = true; p.x = F::zero(); p.y = F::zero(); }
-  else if (check != CHECK_NO) {
-    if (p.inf) report(status, ST_ZERO_POINT, tid);
-    else if (check == CHECK_FULL) {
-      if (!in_compressed && !C::on_curve(p)) report(status, ST_NOT_ON_CURVE, tid);
-      else if (subgroup && !C::in_subgroup(p)) report(status, ST_NOT_IN_SUBGROUP, tid);
-    }
+  else if (p.inf) {
+    if (check != CHECK_NO) report(status, ST_ZERO_POINT, tid);
+  } else {
+    // CheckForCorrectness and SubgroupCheckMode are independent knobs of the reference (src/bin/contribute.rs:971-984):
+    // `check` decides non-zero / on-curve, `subgroup` decides the membership test.  A decompressed point is on the curve by
+    // construction; an uncompressed one is checked whenever the membership test (which assumes a curve point) follows.
+    if (!in_compressed && (check == CHECK_FULL || subgroup) && !C::on_curve(p)) report(status, ST_NOT_ON_CURVE, tid);
+    else if (subgroup && !C::in_subgroup(p)) report(status, ST_NOT_IN_SUBGROUP, tid);
   }
   if (out) {
     if (out_compressed) C::write_compressed(out + (size_t)tid * C::SIZE_C, p);

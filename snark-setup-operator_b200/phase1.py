@@ -327,3 +327,69 @@ def transform_pok_and_correctness(challenge_filename, challenge_hash_filename, c
     call("sso_p1_verify_chunk_file", ctypes.byref(parameters.c_struct()), challenge_filename.encode(), challenge_hash_filename.encode(),
          check_input, response_filename.encode(), response_hash_filename.encode(), check_output, new_challenge_filename.encode(),
          new_challenge_hash_filename.encode(), subgroup_check_mode, int(ratio_check), device)
+
+
+# ---- file-level calls on whole accumulators (verify_transcript / control / new_setup) ---------------------------------
+
+def _devices_arg(devices):
+    if not devices:
+        return None, 0
+    arr = (ctypes.c_int * len(devices))(*devices)
+    return arr, len(devices)
+
+
+def new_challenge(challenge_filename, challenge_hash_filename, parameters: Phase1Parameters, device=0):
+    """phase1_cli::new_challenge, argument for argument (reference src/bin/new_setup.rs:105-109)."""
+    call("sso_p1_new_challenge_file", challenge_filename.encode(), challenge_hash_filename.encode(), ctypes.byref(parameters.c_struct()),
+         device)
+
+
+def set_generators(curve, g1_uncompressed: bytes | None, g2_uncompressed: bytes | None, device=0):
+    """Hand the reference's G1 / G2 generators over (needed for MNT4-753 / MNT6-753 G2, see include/sso_b200.h); None, None resets."""
+    call("sso_p1_set_generators", curve_id(curve), g1_uncompressed, 0 if g1_uncompressed is None else len(g1_uncompressed),
+         g2_uncompressed, 0 if g2_uncompressed is None else len(g2_uncompressed), device)
+
+
+def combine(response_list_filename, combined_filename, parameters: Phase1Parameters, devices=None, device=0):
+    """phase1_cli::combine, argument for argument (reference src/bin/verify_transcript.rs:603-607); `parameters` = the chunk-0
+    parameters of the ceremony.  devices: GPUs of this process to decode on (default: `device`)."""
+    arr, n = _devices_arg(devices)
+    call("sso_p1_combine_file", response_list_filename.encode(), combined_filename.encode(), ctypes.byref(parameters.c_struct()), arr, n,
+         device)
+
+
+def transform_ratios(response_filename, check_input, parameters: Phase1Parameters, devices=None, device=0, rlc_seed32=None):
+    """phase1_cli::transform_ratios, argument for argument (reference src/bin/verify_transcript.rs:646-653, 811-822); raises
+    SsoError(code -4) on rejection.  The partial MSM results of the devices (or of the ranks of the process group set up with
+    dist_init) meet in one NCCL all-gather inside the library."""
+    arr, n = _devices_arg(devices)
+    call("sso_p1_verify_ratios_file", ctypes.byref(parameters.c_struct()), response_filename.encode(), check_input, arr, n, device,
+         rlc_seed32)
+
+
+def dist_init_from_torch(device: int):
+    """One process per GPU under torchrun: build the library's NCCL communicator for the cooperative calls.  Rank 0 draws
+    the NCCL id, torch.distributed (any backend) broadcasts it."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    box = [None]
+    if rank == 0:
+        buf = ctypes.create_string_buffer(128)
+        call("sso_dist_unique_id", buf)
+        box[0] = buf.raw
+    dist.broadcast_object_list(box, src=0)
+    call("sso_dist_init", rank, world, box[0], device)
+
+
+def dist_barrier():
+    call("sso_dist_barrier")
+
+
+def dist_finalize():
+    _lib.lib().sso_dist_finalize()
+
+
+def dist_stats() -> dict:
+    out = (ctypes.c_uint64 * 5)()
+    _lib.lib().sso_dist_stats(out)
+    return {"initialised": bool(out[0]), "rank": out[1], "world": out[2], "all_gathers": out[3], "nccl_version": out[4]}

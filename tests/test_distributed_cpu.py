@@ -1,6 +1,11 @@
-"""World-size-2 `gloo` test of the host-side sharding logic used by transform_ratios and the benchmark:
-the contiguous split with a one-element halo covers every pair index exactly once, and the all_gather of
-the per-rank partial results delivers every rank's bytes to every rank."""
+"""World-size-2 `gloo` test of the cooperative transform_ratios algebra, on CPU.
+
+The product's exchange step runs inside libsso_b200.so (csrc/stream.cuh: pieces dealt round-robin over the ranks, one
+partial pair per piece with its own Blake2b-derived ChaCha20 key, per-rank fold, ONE all-gather, point addition) and needs
+GPUs; here the same piece / owner / tweak logic is driven with the oracle standing in for the device arithmetic, over a real
+torch.distributed group: the gathered-and-folded pair must equal the pair computed piece by piece on a single rank, every
+rank must see the same gathered bytes, and the result must satisfy the power ratio.  The GPU-side NCCL branch is covered by
+tests/test_gpu_multi.py (needs two devices) and the kept hardware logs under profiles/."""
 import os
 
 import pytest
@@ -10,32 +15,67 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 
-def _worker(rank, world, port, n_pairs, ret):
+def _partial(c, G, pts, lo, cnt, seed, vec_id, rank_slot):
+    from oracle import phase1
+    rs = phase1.rlc_scalars(c, seed, cnt - 1, (phase1.TWEAK_P1_RATIOS | vec_id, 0, lo, rank_slot))
+    return phase1.power_pairs_with(G, pts[lo:lo + cnt], rs)
+
+
+def _worker(rank, world, port, n, piece, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from snark_setup_operator_b200.transcript import shard_range
-    lo, hi = shard_range(n_pairs, rank, world)
-    # stand-in for the partial pair: (sum of pair indices, count) — additive like the real partial points
-    mine = torch.tensor([sum(range(lo, hi)), hi - lo, lo, hi], dtype=torch.int64)
+    from oracle import serialize as ser, synth
+    from oracle.curves import get_curve
+    from snark_setup_operator_b200.transcript import owner, pieces
+    c = get_curve("bls12_377")
+    G = c.g1
+    s = synth.scalars_from_seed(c, synth.SEED_PREV)[0]
+    pts = synth._powers_points(G, G.gen, s, c.Fr.p, 0, n)
+    seed = bytes(range(32))
+    a = b = None
+    for i, (lo, cnt) in enumerate(pieces(n, piece, True)):
+        if owner(i, world) != rank:
+            continue
+        pa, pb = _partial(c, G, pts, lo, cnt, seed, 0, rank * 64)
+        a, b = G.add(a, pa), G.add(b, pb)
+    mine = torch.frombuffer(bytearray(ser.point_to_bytes(G, a, False) + ser.point_to_bytes(G, b, False)), dtype=torch.uint8)
     got = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(got, mine)
-    ret[rank] = [g.tolist() for g in got]
+    dist.all_gather(got, mine)                                  # the single collective of the path
+    ret[rank] = [bytes(g.numpy().tobytes()) for g in got]
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_pairs", [1, 2, 7, 1 << 16])
-def test_shards_cover_all_pairs_and_gather(n_pairs):
+@pytest.mark.parametrize("n,piece", [(2, 8), (9, 8), (37, 8), (64, 16)])
+def test_cooperative_power_pairs_over_gloo(n, piece):
+    from oracle import serialize as ser, synth
+    from oracle.curves import get_curve
+    from snark_setup_operator_b200.transcript import owner, pieces
     world = 2
     mgr = mp.Manager()
     ret = mgr.dict()
-    port = 29500 + (n_pairs % 97)
-    mp.spawn(_worker, args=(world, port, n_pairs, ret), nprocs=world, join=True)
+    port = 29500 + (n * 7 + piece) % 97
+    mp.spawn(_worker, args=(world, port, n, piece, ret), nprocs=world, join=True)
     assert ret[0] == ret[1]                                   # every rank sees the same gathered partials
-    parts = ret[0]
-    assert sum(p[1] for p in parts) == n_pairs
-    assert sum(p[0] for p in parts) == n_pairs * (n_pairs - 1) // 2
-    assert parts[0][2] == 0 and parts[-1][3] == n_pairs and parts[0][3] == parts[1][2]   # contiguous, no gap, no overlap
+    c = get_curve("bls12_377")
+    G = c.g1
+    usz = 2 * G.F.nbytes
+    a = b = None
+    for blob in ret[0]:
+        a = G.add(a, ser.point_from_bytes(G, blob[:usz], False))
+        b = G.add(b, ser.point_from_bytes(G, blob[usz:], False))
+    # single-rank reference: the same pieces with the keys their owners used
+    s = synth.scalars_from_seed(c, synth.SEED_PREV)[0]
+    pts = synth._powers_points(G, G.gen, s, c.Fr.p, 0, n)
+    ps = pieces(n, piece, True)
+    # the pieces cover every pair index exactly once, with one element of halo
+    assert ps[0][0] == 0 and all(ps[i][0] + ps[i][1] - 1 == ps[i + 1][0] for i in range(len(ps) - 1)) and ps[-1][0] + ps[-1][1] == n
+    wa = wb = None
+    for i, (lo, cnt) in enumerate(ps):
+        pa, pb = _partial(c, G, pts, lo, cnt, bytes(range(32)), 0, owner(i, world) * 64)
+        wa, wb = G.add(wa, pa), G.add(wb, pb)
+    assert G.eq(a, wa) and G.eq(b, wb)
+    assert G.eq(G.mul(a, s), b)                               # the combination keeps the power ratio
 
 
 def test_chunk_to_rank_assignment():

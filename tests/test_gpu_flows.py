@@ -184,25 +184,33 @@ def test_phase2_delta_update_and_check(name):
 
 def test_combine_and_transform_ratios(tmp_path):
     """A whole (tiny) ceremony round on the GPU: new_challenge per chunk, seeded contributions, combine, and the
-    full-accumulator ratio check (transform_ratios); a tampered element is rejected."""
+    full-accumulator ratio check (transform_ratios) — all through the file-level C ABI; a tampered element is rejected."""
     import numpy as np
-    from snark_setup_operator_b200 import transcript
     name, power, cs = "bls12_377", 3, 4
     full = sso.Phase1Parameters.new_full(name, power, cs)
-    nchunks = sso.Phase1Parameters.new_chunk(name, 0, cs, power, cs).sizes()["num_chunks"]
-    files, cps = [], []
+    p0 = sso.Phase1Parameters.new_chunk(name, 0, cs, power, cs)
+    nchunks = p0.sizes()["num_chunks"]
+    files, resps = [], []
     for k in range(nchunks):
         p = sso.Phase1Parameters.new_chunk(name, k, cs, power, cs)
-        d_ch = torch.empty(p.accumulator_size, dtype=torch.uint8, device="cuda")
-        sso.new_challenge_dev(p, d_ch)
-        resp = bytearray(p.contribution_size)
-        sso.contribute_seeded_buf(p, d_ch.cpu().numpy(), resp, synth.SEED_CONTRIB)
-        fn = str(tmp_path / ("response_%d" % k))
-        open(fn, "wb").write(resp)
-        files.append(fn); cps.append(p)
+        f = {n: str(tmp_path / ("%s_%d" % (n, k))) for n in ("challenge", "challenge.hash", "response", "response.hash", "challenge.hash2")}
+        sso.new_challenge(f["challenge"], f["challenge.hash"], p)
+        o = Phase1Params.new_chunk(name, k, cs, power, cs)
+        ch = open(f["challenge"], "rb").read()
+        assert ch == phase1.new_challenge(o)
+        assert open(f["challenge.hash"], "rb").read() == phase1.calculate_hash(ch)
+        sso.contribute(f["challenge"], f["challenge.hash2"], f["response"], f["response.hash"], sso.CHECK_NONZERO, 0, p, synth.SEED_CONTRIB)
+        files.append(f["response"])
+        resps.append(open(f["response"], "rb").read())
     combined = str(tmp_path / "combined")
-    transcript.combine(files, combined, cps, full)
-    assert os.path.getsize(combined) == full.accumulator_size
+    lst = str(tmp_path / "response_list")
+    open(lst, "w").write("\n".join(files) + "\n")
+    sso.combine(lst, combined, p0)
+    o0 = Phase1Params.new_chunk(name, 0, cs, power, cs)
+    assert open(combined, "rb").read() == phase1.combine(o0, resps)
+    with pytest.raises(sso.SsoError) as e:                      # outputs must not exist
+        sso.combine(lst, combined, p0)
+    assert e.value.code == -5
     # the combined vectors are the powers of the contributor's tau on the generators
     c = get_curve(name)
     key = phase1.PrivateKey(*synth.scalars_from_seed(c, synth.SEED_CONTRIB))
@@ -211,12 +219,16 @@ def test_combine_and_transform_ratios(tmp_path):
     r = c.Fr.p
     assert all(c.g1.eq(P, c.g1.mul(c.g1.gen, pow(key.tau, i, r))) for i, P in enumerate(v.tau_g1))
     assert all(c.g1.eq(P, c.g1.mul(c.g1.gen, key.beta * pow(key.tau, i, r) % r)) for i, P in enumerate(v.beta_g1))
-    assert transcript.transform_ratios(combined, sso.CHECK_FULL, full, rlc_seed32=bytes(range(32)), subgroup_check=True)
+    sso.transform_ratios(combined, sso.CHECK_FULL, full, rlc_seed32=bytes(range(32)))
+    sso.transform_ratios(combined, sso.CHECK_NO, full)          # fresh entropy
+    assert phase1.transform_ratios(o_full, open(combined, "rb").read(), phase1.CHECK_FULL, bytes(range(32)))
     # tamper with tau_g1[5]
     mm = np.memmap(combined, dtype=np.uint8, mode="r+")
     off = 64 + 5 * 96
     mm[off:off + 96] = np.frombuffer(ser.point_to_bytes(c.g1, c.g1.mul(c.g1.gen, 4242), False), dtype=np.uint8)
     mm.flush(); del mm
     with pytest.raises(sso.SsoError) as e:
-        transcript.transform_ratios(combined, sso.CHECK_NO, full)
+        sso.transform_ratios(combined, sso.CHECK_NO, full)
     assert e.value.code == -4 and "tau_g1" in e.value.message
+    with pytest.raises(phase1.VerificationError, match="tau_g1"):
+        phase1.transform_ratios(o_full, open(combined, "rb").read())
