@@ -185,7 +185,7 @@ def test_verify_verdicts_match_oracle_on_every_curve(name):
         both_reject(bad, "subgroup")
         # SubgroupCheckMode::No lets the membership test go; the ratio check still sees a wrong element
         with pytest.raises(sso.SsoError) as e:
-            sso.verify_chunk_buf(p, ch, bytes(bad), new_ch, rlc_seed32=seed, subgroup_check_mode=sso.phase1.SUBGROUP_NO)
+            sso.verify_chunk_buf(p, ch, bytes(bad), new_ch, rlc_seed32=seed, check_output=sso.CHECK_NONZERO, subgroup_check_mode=sso.phase1.SUBGROUP_NO)
         assert "subgroup" not in e.value.message
     bad = bytearray(resp); bad[oc[1] + s2: oc[1] + 2 * s2] = ser.point_to_bytes(c.g2, None, True)
     both_reject(bad, "infinity")
