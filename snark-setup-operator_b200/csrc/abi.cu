@@ -758,28 +758,6 @@ int32_t sso_dist_init(int32_t rank, int32_t world, const uint8_t id128[128], int
   return SSO_OK;
 }
 
-// all-reduce (sum) of one integer across the group: a barrier that also spreads a failure flag
-static int32_t dist_sum(int32_t mine, int32_t* total, char* err, size_t errcap) {
-  DistState& d = dist_state();
-  *total = mine;
-  if (!d.on || d.world == 1) return SSO_OK;
-  const NcclApi* api = nccl_api(err, errcap);
-  if (!api) return SSO_E_CUDA;
-  Ctx c(err, errcap);
-  int rc = c.init(d.device);
-  if (rc) return rc;
-  int32_t* d_v;
-  if ((rc = c.alloc((void**)&d_v, 4))) return rc;
-  CUDA_TRY(cudaMemcpyAsync(d_v, &mine, 4, cudaMemcpyHostToDevice, c.s[0]));
-  {
-    std::lock_guard<std::mutex> g(dist_mutex());
-    NCCL_TRY(api, api->AllReduce(d_v, d_v, 1, ncclInt32, ncclSum, d.comm, c.s[0]));
-  }
-  CUDA_TRY(cudaMemcpyAsync(total, d_v, 4, cudaMemcpyDeviceToHost, c.s[0]));
-  CUDA_TRY(cudaStreamSynchronize(c.s[0]));
-  return SSO_OK;
-}
-
 int32_t sso_dist_barrier(char* err, size_t errcap) {
   int32_t t;
   return dist_sum(0, &t, err, errcap);

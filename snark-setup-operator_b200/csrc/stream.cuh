@@ -171,6 +171,42 @@ inline int run_pieces(size_t n_pieces, const Participants& P, int workers_per_de
   return first_rc.load();
 }
 
+// all-reduce (sum) of one integer across the group: a barrier that also spreads a failure flag
+inline int32_t dist_sum(int32_t mine, int32_t* total, char* err, size_t errcap) {
+  DistState& d = dist_state();
+  *total = mine;
+  if (!d.on || d.world == 1) return SSO_OK;
+  const NcclApi* api = nccl_api(err, errcap);
+  if (!api) return SSO_E_CUDA;
+  Ctx c(err, errcap);
+  int rc = c.init(d.device);
+  if (rc) return rc;
+  int32_t* d_v;
+  if ((rc = c.alloc((void**)&d_v, 4))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(d_v, &mine, 4, cudaMemcpyHostToDevice, c.s[0]));
+  {
+    std::lock_guard<std::mutex> g(dist_mutex());
+    NCCL_TRY(api, api->AllReduce(d_v, d_v, 1, ncclInt32, ncclSum, d.comm, c.s[0]));
+  }
+  CUDA_TRY(cudaMemcpyAsync(total, d_v, 4, cudaMemcpyDeviceToHost, c.s[0]));
+  CUDA_TRY(cudaStreamSynchronize(c.s[0]));
+  return SSO_OK;
+}
+
+// Every rank of a cooperative call must take the same path through the collectives: after a phase that can fail on one
+// rank only (a bad element sits in ONE rank's piece), the failure flags are summed and every rank leaves together.
+inline int32_t agree(const Participants& P, int32_t rc, char* err, size_t errcap) {
+  if (!P.dist) return rc;
+  int32_t total = 0;
+  char e2[256];
+  e2[0] = 0;
+  int32_t rc2 = dist_sum(rc != SSO_OK ? 1 : 0, &total, e2, sizeof e2);
+  if (rc != SSO_OK) return rc;
+  if (rc2 != SSO_OK) { set_err(err, errcap, "%s", e2); return rc2; }
+  if (total != 0) { set_err(err, errcap, "another rank of the process group rejected its share of the call"); return SSO_E_VERIFY; }
+  return SSO_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Decode / check / re-encode vectors in pieces, with optional power_pairs partial sums
 // ---------------------------------------------------------------------------------------------
@@ -342,7 +378,7 @@ inline int stream_reencode(const CurveOps* ops, const CurveSizes& cs, const std:
     }
     return SSO_OK;
   });
-  if (rc) return rc;
+  if ((rc = agree(P, rc, err, errcap))) return rc;
   if (!pairs) return SSO_OK;
   if (!any_pairs) {
     pairs->assign(vecs.size(), {});
@@ -359,20 +395,25 @@ inline int stream_reencode(const CurveOps* ops, const CurveSizes& cs, const std:
   std::vector<size_t> voff(vecs.size()), vusz(vecs.size());
   for (size_t v = 0; v < vecs.size(); v++) { vusz[v] = point_size(cs, vecs[v].group, 0); voff[v] = blob; blob += 2 * vusz[v]; }
   std::vector<std::vector<uint8_t>> mine(nlocal, std::vector<uint8_t>(blob));
-  for (int s = 0; s < nlocal; s++) {
-    Ctx c(err, errcap);
-    if ((rc = c.init(P.devices[s]))) return rc;
-    for (size_t v = 0; v < vecs.size(); v++) {
-      const size_t usz = vusz[v], cnt = part[s][v].size() / (2 * usz);
-      std::vector<uint8_t> a(cnt * usz), b(cnt * usz);
-      for (size_t k = 0; k < cnt; k++) {
-        memcpy(a.data() + k * usz, part[s][v].data() + k * 2 * usz, usz);
-        memcpy(b.data() + k * usz, part[s][v].data() + k * 2 * usz + usz, usz);
+  auto fold = [&]() -> int {
+    int rc;
+    for (int s = 0; s < nlocal; s++) {
+      Ctx c(err, errcap);
+      if ((rc = c.init(P.devices[s]))) return rc;
+      for (size_t v = 0; v < vecs.size(); v++) {
+        const size_t usz = vusz[v], cnt = part[s][v].size() / (2 * usz);
+        std::vector<uint8_t> a(cnt * usz), b(cnt * usz);
+        for (size_t k = 0; k < cnt; k++) {
+          memcpy(a.data() + k * usz, part[s][v].data() + k * 2 * usz, usz);
+          memcpy(b.data() + k * usz, part[s][v].data() + k * 2 * usz + usz, usz);
+        }
+        if ((rc = sum_points_host(c, ops, vecs[v].group, usz, a.data(), cnt, mine[s].data() + voff[v], err, errcap))) return rc;
+        if ((rc = sum_points_host(c, ops, vecs[v].group, usz, b.data(), cnt, mine[s].data() + voff[v] + usz, err, errcap))) return rc;
       }
-      if ((rc = sum_points_host(c, ops, vecs[v].group, usz, a.data(), cnt, mine[s].data() + voff[v], err, errcap))) return rc;
-      if ((rc = sum_points_host(c, ops, vecs[v].group, usz, b.data(), cnt, mine[s].data() + voff[v] + usz, err, errcap))) return rc;
     }
-  }
+    return SSO_OK;
+  };
+  if ((rc = agree(P, fold(), err, errcap))) return rc;
   return exchange_and_sum(ops, cs, P, vecs, mine, *pairs, err, errcap);
 }
 
@@ -396,7 +437,7 @@ inline int stream_contribute(const CurveOps* ops, const P1Layout& L, const uint8
     int v = order[oi];
     for (uint64_t lo = 0; lo < counts[v]; lo += piece_elems) pieces.push_back({(uint32_t)v, lo, lo + piece_elems < counts[v] ? piece_elems : counts[v] - lo});
   }
-  return run_pieces(pieces.size(), P, 2, 1, err, errcap, [&](size_t i, int, Ctx& c, char* e, size_t ec) -> int {
+  int rc_all = run_pieces(pieces.size(), P, 2, 1, err, errcap, [&](size_t i, int, Ctx& c, char* e, size_t ec) -> int {
     char* err = e; size_t errcap = ec;
     const CPiece& pc = pieces[i];
     const uint32_t g = groups[pc.vec];
@@ -430,6 +471,7 @@ inline int stream_contribute(const CurveOps* ops, const P1Layout& L, const uint8
     }
     return SSO_OK;
   });
+  return agree(P, rc_all, err, errcap);
 }
 
 }  // namespace sso

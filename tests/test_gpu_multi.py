@@ -18,14 +18,19 @@ def _two_gpus():
 
 @pytest.mark.skipif(not _two_gpus(), reason="needs two GPUs")
 def test_transcript_over_two_devices_one_process(tmp_path):
-    from tests.test_gpu_transcript import _run_transcript
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_gpu_transcript import _run_transcript
     _run_transcript(tmp_path, "bls12_377", 10, 8, 64, devices=[0, 1])
 
 
 def _rank_main(rank, world, port, tmp):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import faulthandler
     import hashlib
+    import sys
     import torch.distributed as dist
+    faulthandler.dump_traceback_later(150, exit=True, file=sys.stderr)       # a hang must not hold the two GPUs
     from oracle import cport, phase1, synth
     from oracle.chacha import ChaChaRng
     from oracle.params import Phase1Params
@@ -82,6 +87,7 @@ def _rank_main(rank, world, port, tmp):
         assert e.code in (-3, -4)
     sso.dist_finalize()
     dist.destroy_process_group()
+    faulthandler.cancel_dump_traceback_later()
 
 
 @pytest.mark.skipif(not _two_gpus(), reason="needs two GPUs")
