@@ -43,7 +43,28 @@ GLV_KBITS = {"bls12_377": 129, "bw6_761": 191}
 # `ncu --set full` capture (profiles/r1_ncu_batch_exp_chunk_summary.csv): 3.64 GB read + 1.95 GB written.  The algorithmic
 # bytes are 31.5 MB in + 38 MB of Jacobian intermediates out; the rest is the per-thread stack (window tables, by-reference
 # point arguments, spills: 4.8 KB/thread x 37.9 k resident threads = 181 MB, more than the 126 MB L2).  207 GB/s: 3 % of HBM.
-NCU_DRAM_BYTES_PER_LAUNCH = {"bls12_377": 5.59e9}
+def ncu_dram_bytes_per_launch(curve: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, read from the committed summary of
+    the newest `ncu --set full` capture of this curve under profiles/ (r<N>_ncu_batch_exp_chunk_summary[_curve].csv);
+    None when no capture is committed.  -> (bytes, file name)"""
+    import glob
+    import re
+    best = None
+    for fn in glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_batch_exp_chunk_summary*.csv")):
+        m = re.match(r"r(\d+)_ncu_batch_exp_chunk_summary(?:_(\w+))?\.csv", os.path.basename(fn))
+        if not m or (m.group(2) or "bls12_377") != curve:
+            continue
+        if best is None or int(m.group(1)) > best[0]:
+            best = (int(m.group(1)), fn)
+    if best is None:
+        return None, None
+    tot = 0.0
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for line in open(best[1]):
+        parts = line.strip().split(",")
+        if len(parts) >= 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(parts[2]) * scale.get(parts[1], 1.0)
+    return (tot or None), os.path.relpath(best[1], ROOT)
 
 
 def declared_work_per_point(curve: str, group: int):
@@ -171,6 +192,272 @@ def cpu_reference_run(curve: str, power: int, chunk_log: int, steps: int, warmup
                       % (curve, clog, n, len(times))}, mean
 
 
+def run_phase2(args, rank, world, local_rank):
+    """--workload phase2 (BASELINE config 4): the delta^-1 scaling of a Groth16 H or L query of n G1 points
+    (phase2_cli::contribute -> batch_mul, reference src/bin/contribute.rs:827-838), synthetic vectors of the sizes the
+    Nimiq circuits have (2^19 .. 2^22, reference e2e/nimiq_e2e.sh:61-71).  value: device-resident points/s (sso_batch_mul_dev);
+    e2e: sso_p2_scale_queries_buf from pinned host buffers.  Every rank scales its own vector (no collective)."""
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    import torch
+    import snark_setup_operator_b200 as sso
+    from snark_setup_operator_b200 import phase2 as p2
+    from snark_setup_operator_b200.phase1 import curve_sizes
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product has no CPU path)")
+    torch.cuda.set_device(local_rank)
+    dev = local_rank
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    name = args.curve
+    es = curve_sizes(name)
+    limbs, bits = CURVE_BITS[name]
+    n = 1 << args.query_log
+    tau = int.from_bytes(bytes(range(1, 33)), "little") >> 8
+    delta_inv = int.from_bytes(bytes(range(7, 7 + 64)), "little") >> (512 - (bits - 1))
+    # a vector of distinct subgroup points: tau^i * G
+    d_gen = torch.frombuffer(bytearray(n * es["g1_u"]), dtype=torch.uint8).cuda()
+    pchunk = sso.Phase1Parameters.new_chunk(name, 0, 1, 1, 1)
+    d_one = torch.empty(pchunk.accumulator_size, dtype=torch.uint8, device="cuda")
+    sso.new_challenge_dev(pchunk, d_one, device=dev)
+    d_gen.view(n, es["g1_u"])[:] = d_one[64:64 + es["g1_u"]]
+    d_in = torch.empty(n * es["g1_u"], dtype=torch.uint8, device="cuda")
+    d_c = torch.empty(n * es["g1_c"], dtype=torch.uint8, device="cuda")
+    sso.batch_exp(name, 0, d_gen, n, 1 + rank, tau, None, d_c, device=dev)
+    sso.reencode(name, 0, d_c, n, d_in, check=sso.CHECK_NO, subgroup_check=False, device=dev)
+    del d_gen, d_c
+    d_out = torch.empty(n * es["g1_u"], dtype=torch.uint8, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    h_in = torch.empty(n * es["g1_u"], dtype=torch.uint8).pin_memory()
+    h_in.copy_(d_in)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run_steps(fn, k):
+        tot = 0.0
+        for _ in range(k):
+            flush.zero_()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); e1.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot
+
+    step = lambda: sso.batch_mul(name, 0, d_in, n, delta_inv, d_out, in_compressed=False, out_compressed=False, check=sso.CHECK_NO, device=dev)
+    run_steps(step, args.warmup)
+    sso.profile_reset()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    ms = run_steps(step, args.steps)
+    barrier()
+    launches = sum(v["launches"] for v in sso.profile_read().values()) // max(1, args.steps)
+    sso.profile_reset(); sso.profile_enable(2)
+    run_steps(step, args.steps)
+    sso.profile_enable(False)
+    prof = sso.profile_read()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    h_out = torch.empty(n * es["g1_u"], dtype=torch.uint8).pin_memory()
+    e2e_fn = lambda: p2.scale_queries(name, h_in, n, delta_inv, device=dev, out=h_out)
+    run_steps(e2e_fn, 1)
+    ms_e2e = run_steps(e2e_fn, args.steps)
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        peak = sso.imad_peak(0, dev)
+        k = prof["batch_exp_g1"]
+        macs = k["elems"] * declared_macs_per_point(name, 0)
+        achieved = macs / (k["ms"] * 1e-3) if k["ms"] > 0 else None
+        ms_step, ms_e2e_step = t[0].item() / args.steps, t[1].item() / args.steps
+        line = {"metric": "phase2_scale_points_per_s", "value": world * n / (ms_step * 1e-3), "unit": "points/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u32 limbs (Montgomery, integer pipe)", "data": "synthetic",
+                "config": {"workload": "phase-2 %s: delta^-1 scaling of a query vector of 2^%d G1 points (uncompressed in and out)" % (name, args.query_log),
+                           "curve": name, "points": n, "l2": "flushed between timed steps (256 MiB write)"},
+                "e2e": {"value": world * n / (ms_e2e_step * 1e-3), "unit": "points/s", "ms_per_step": ms_e2e_step,
+                        "h2d_bytes_per_step": n * es["g1_u"], "d2h_bytes_per_step": n * es["g1_u"], "call": "sso_p2_scale_queries_buf"},
+                "gpu_launches": launches,
+                "roofline": {"bound": "imad", "kernel": "k_batch_exp<G1> (one shared scalar)", "achieved": achieved / 1e12 if achieved else None,
+                             "peak": peak / 1e12, "unit": "TMAC/s", "frac": achieved / peak if achieved else None, "traffic": None,
+                             "fq_muls_per_point": round(declared_fq_muls_per_point(name, 0), 1),
+                             "kernels": {kk: {"launches": v["launches"], "ms_total": round(v["ms"], 3)} for kk, v in prof.items() if v["launches"]}},
+                "clocks": sampler.summary()}
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def run_verify_transcript(args, rank, world, local_rank):
+    """--workload verify_transcript: one pass of what the operator's verify_transcript binary drives through the crate
+    boundary for a phase-1 ceremony with one contribution per chunk (reference src/bin/verify_transcript.rs:293-569, 602-607,
+    675-696, 745-776, 811-822), on files in tmpfs:
+      chunk loop   per chunk: regenerate the round-0 challenge and compare its hash, transform_pok_and_correctness of the
+                   contribution — chunks dealt round-robin over the ranks, no collective
+      combine      cooperative: every rank decodes its share of the pieces into the shared combined file
+      beacon       phase1_cli::contribute on the combined accumulator, Full mode, cooperative (pieces of batch_size)
+      verify       transform_pok_and_correctness of the beacon contribution, Full mode, cooperative; the partial MSM results of
+                   the ranks meet in ONE NCCL all-gather
+      ratios       transform_ratios on the final accumulator, cooperative, ONE NCCL all-gather
+    value = seconds per pass (max over ranks); setup (new_challenge + the contributions being verified) is not timed."""
+    import hashlib
+    import shutil
+    import tempfile
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    import torch
+    import snark_setup_operator_b200 as sso
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product has no CPU path)")
+    torch.cuda.set_device(local_rank)
+    dev = local_rank
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        sso.dist_init_from_torch(dev)
+    name, power, cs, batch = args.curve, args.power, 1 << args.chunk_log, 1 << args.batch_log
+    base = [None]
+    if rank == 0:
+        root = "/dev/shm" if os.path.isdir("/dev/shm") else None
+        base[0] = tempfile.mkdtemp(prefix="sso_bench_", dir=root)
+    if dist is not None:
+        dist.broadcast_object_list(base, src=0)
+    base = base[0]
+    f = lambda n: os.path.join(base, n)
+    p0 = sso.Phase1Parameters.new_chunk(name, 0, cs, power, batch)
+    pf = sso.Phase1Parameters.new_full(name, power, batch)
+    sz0 = p0.sizes()
+    nchunks = sz0["num_chunks"]
+    full = pf.sizes()
+    npts = full["g1_count"] + 3 * full["other_count"] + 1
+    seed = bytes(range(32))
+    beacon = hashlib.blake2s(b"bench beacon").digest()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    def chunk_params(k):
+        return sso.Phase1Parameters.new_chunk(name, k, cs, power, batch)
+
+    # ---- setup: round 0 and one contribution per chunk (the transcript being verified)
+    t_setup = time.perf_counter()
+    for k in range(rank, nchunks, world):
+        sso.new_challenge(f("ch%d" % k), f("ch%d.hash" % k), chunk_params(k), device=dev)
+        sso.contribute(f("ch%d" % k), f("ch%d.h2" % k), f("resp%d" % k), f("resp%d.hash" % k), sso.CHECK_NONZERO, 0, chunk_params(k), seed, device=dev)
+    barrier()
+    if rank == 0:
+        open(f("list"), "w").write("\n".join(f("resp%d" % k) for k in range(nchunks)))
+    barrier()
+    t_setup = time.perf_counter() - t_setup
+    outputs = ["combined", "combined.hash", "beacon", "beacon.hash", "c.vhash", "b.vhash", "final", "final.hash"]
+
+    def clean():
+        for k in range(rank, nchunks, world):
+            for n in ("regen%d", "regen%d.hash", "ch%d.vhash", "resp%d.vhash", "new%d", "new%d.hash"):
+                if os.path.exists(f(n % k)):
+                    os.remove(f(n % k))
+        if rank == 0:
+            for n in outputs:
+                if os.path.exists(f(n)):
+                    os.remove(f(n))
+        barrier()
+
+    phases = ("chunks", "combine", "beacon", "verify", "ratios")
+
+    def one_pass():
+        t = {}
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(rank, nchunks, world):
+            pk = chunk_params(k)
+            sso.new_challenge(f("regen%d" % k), f("regen%d.hash" % k), pk, device=dev)                    # verify_transcript.rs:316-361
+            assert open(f("regen%d.hash" % k), "rb").read() == open(f("ch%d.hash" % k), "rb").read()
+            sso.transform_pok_and_correctness(f("ch%d" % k), f("ch%d.vhash" % k), sso.CHECK_NO, f("resp%d" % k), f("resp%d.vhash" % k),
+                                              sso.CHECK_NONZERO, f("new%d" % k), f("new%d.hash" % k), 0, True, pk, device=dev)
+        barrier()
+        t["chunks"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        sso.combine(f("list"), f("combined"), p0, device=dev)
+        barrier()
+        t["combine"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        sso.contribute(f("combined"), f("combined.hash"), f("beacon"), f("beacon.hash"), sso.CHECK_NONZERO, 0, pf, beacon, device=dev)
+        barrier()
+        t["beacon"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        sso.transform_pok_and_correctness(f("combined"), f("c.vhash"), sso.CHECK_NO, f("beacon"), f("b.vhash"), sso.CHECK_NONZERO, f("final"),
+                                          f("final.hash"), 0, True, pf, device=dev)
+        barrier()
+        t["verify"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        sso.transform_ratios(f("final"), sso.CHECK_NO, pf, device=dev)
+        barrier()
+        t["ratios"] = time.perf_counter() - t0
+        return t
+
+    sampler = ClockSampler(local_rank)
+    try:
+        for _ in range(max(1, args.warmup)):
+            clean()
+            one_pass()
+        sampler.start()
+        totals = {k: 0.0 for k in phases}
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev_ms = 0.0
+        for _ in range(args.steps):
+            clean()
+            e0.record()
+            t = one_pass()
+            e1.record()
+            e1.synchronize()
+            ev_ms += e0.elapsed_time(e1)
+            for k in phases:
+                totals[k] += t[k]
+        sampler.stop_flag = True
+        if sampler.is_alive():
+            sampler.join(timeout=2)
+        vals = torch.tensor([totals[k] for k in phases] + [ev_ms / 1e3], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        stats = sso.dist_stats()
+        final_hash = open(f("final.hash"), "rb").read().hex() if rank == 0 else None
+    finally:
+        barrier()
+        if rank == 0:
+            shutil.rmtree(base, ignore_errors=True)
+    if rank == 0:
+        per = {k: vals[i].item() / args.steps for i, k in enumerate(phases)}
+        total_s = vals[len(phases)].item() / args.steps
+        es = sso.phase1.curve_sizes(name)
+        line = {"metric": "verify_transcript_s", "value": total_s, "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": max(1, args.warmup),
+                "ms_per_step": total_s * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+                "dtype": "u32 limbs (Montgomery, integer pipe)", "data": "synthetic",
+                "config": {"workload": "verify_transcript of a phase-1 %s 2^%d-power ceremony, %d chunks of 2^%d, one contribution per chunk, beacon "
+                                       "applied, batch_size 2^%d; files in tmpfs" % (name, power, nchunks, args.chunk_log, args.batch_log),
+                           "curve": name, "power": power, "chunk_size": cs, "batch_size": batch, "points": npts,
+                           "accumulator_bytes": full["accumulator_size"],
+                           "sharding": "chunks round-robin over ranks; Full-mode calls cooperative in batch_size pieces; partial MSM results: one "
+                                       "NCCL all-gather per Full-mode verification and per transform_ratios"},
+                "phases_s": per, "points_per_s": npts / total_s, "setup_s": t_setup,
+                "nccl": {"ranks": stats["world"] if stats["initialised"] else 1, "all_gathers_total": stats["all_gathers"], "version": stats["nccl_version"]},
+                "final_hash": final_hash, "clocks": sampler.summary(), "point_bytes": es}
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    if dist is not None:
+        sso.dist_finalize()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -181,7 +468,12 @@ def main():
     ap.add_argument("--power", type=int, default=20)
     ap.add_argument("--chunk-log", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="contribute", choices=["contribute", "verify_transcript", "phase2"])
+    ap.add_argument("--query-log", type=int, default=20, help="phase2 workload: log2 of the query length")
+    ap.add_argument("--batch-log", type=int, default=None, help="log2 of Phase1Parameters::batch_size (default: the chunk size)")
     args = ap.parse_args()
+    if args.batch_log is None:
+        args.batch_log = args.chunk_log
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
@@ -191,6 +483,10 @@ def main():
     config = {"workload": workload, "curve": args.curve, "power": args.power, "chunk_size": 1 << args.chunk_log,
               "sharding": "one chunk per rank, no data-path collective", "l2": "flushed between timed steps (256 MiB write)"}
 
+    if args.workload == "verify_transcript" and args.impl == "ours":
+        return run_verify_transcript(args, rank, world, local_rank)
+    if args.workload == "phase2" and args.impl == "ours":
+        return run_phase2(args, rank, world, local_rank)
     if args.impl == "reference":
         if rank != 0:
             return
@@ -371,6 +667,46 @@ def main():
         e1.synchronize()
         ms_e2e_seeded_many_total = e0.elapsed_time(e1)
         barrier()
+    # (c) the call the operator makes: phase1_cli::contribute on FILES (tmpfs), one call per process-lane slot
+    # (--max-in-process-lane threads, reference src/bin/contribute.rs:118-123, 809-823): mmap of the challenge, key generation,
+    # proofs of knowledge, computation, Blake2b of challenge and response, response + 2 hash files written and renamed
+    file_call = None
+    if not quick:
+        import shutil
+        import tempfile
+        from concurrent.futures import ThreadPoolExecutor
+        tdir = tempfile.mkdtemp(prefix="sso_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        try:
+            ch_fn = os.path.join(tdir, "challenge")
+            with open(ch_fn, "wb") as fh:
+                fh.write(h_ch.numpy().tobytes())
+
+            def one_file(i):
+                out = [os.path.join(tdir, "%s_%d" % (n, i)) for n in ("challenge.hash", "response", "response.hash")]
+                for o in out:
+                    if os.path.exists(o):
+                        os.remove(o)
+                sso.contribute(ch_fn, out[0], out[1], out[2], sso.CHECK_NONZERO, 0, p, bytes(range(32)), device=dev)
+
+            one_file(0)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(args.steps):
+                one_file(0)
+            t_single = (time.perf_counter() - t0) / args.steps
+            lanes = 4
+            with ThreadPoolExecutor(lanes) as ex:
+                list(ex.map(one_file, range(lanes)))
+                n_calls = max(lanes, 2 * args.steps)
+                t0 = time.perf_counter()
+                list(ex.map(one_file, [i % lanes for i in range(n_calls)]))
+                t_lanes = (time.perf_counter() - t0) / n_calls
+            file_call = {"single_call": {"value": npts / t_single, "ms_per_step": t_single * 1e3},
+                         "lanes": {"value": npts / t_lanes, "ms_per_step": t_lanes * 1e3, "process_lanes": lanes},
+                         "unit": "points/s (this rank)",
+                         "call": "sso_p1_contribute_file on tmpfs: everything phase1_cli::contribute does, files in and out"}
+        finally:
+            shutil.rmtree(tdir, ignore_errors=True)
     sampler.stop_flag = True
     if sampler.is_alive():
         sampler.join(timeout=2)
@@ -458,14 +794,16 @@ def main():
                                 "call": "sso_p1_contribute_seeded_buf, one chunk per call: key generation from the seed, proofs of "
                                         "knowledge (hash_to_g2), computation — all of phase1_cli::contribute but the file I/O"},
                 "seeded_in_flight": {"value": world * npts / (ms_e2e_seeded_many * 1e-3), "ms_per_step": ms_e2e_seeded_many,
-                                     "call": "sso_p1_contribute_seeded_many_buf: the full call with K chunks in flight, 6 host workers"}},
+                                     "call": "sso_p1_contribute_seeded_many_buf: the full call with K chunks in flight, 6 host workers"},
+                "file_call": file_call},
         "gpu_launches": launches,
         "roofline": {"bound": "imad",
                      "kernel": dom["kernel"], "achieved": dom["achieved_tmacs"], "peak": peak / 1e12, "unit": "TMAC/s",
-                     "frac": dom["frac"], "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(args.curve),
+                     "frac": dom["frac"], "traffic": ncu_dram_bytes_per_launch(args.curve)[0],
                      "peak_source": "measured live: mad.wide.u32 probe kernel (sso_imad_peak variant 0)",
                      "peak_carry_chain": peak_chain / 1e12, "frac_of_carry_chain_peak": (dom["frac"] * peak / peak_chain) if dom["frac"] else None,
-                     "traffic_source": "profiles/r1_ncu_batch_exp_chunk_summary.csv (dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
+                     "traffic_source": "%s (dram__bytes_read.sum + dram__bytes_write.sum, one launch)" % ncu_dram_bytes_per_launch(args.curve)[1],
+                     "algorithmic_bytes": acc + contrib - 64 - sz["public_key_size"],
                      "macs_per_fq_mul": mac, "macs_per_fq_sqr": macs_per_fq_sqr(limbs), "kernels": kernels},
         "clocks": sampler.summary(),
         "points_per_step": npts,

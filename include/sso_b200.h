@@ -110,8 +110,8 @@ int32_t sso_reencode_dev(uint32_t curve, uint32_t group, const void* d_in, uint3
 /* setup_utils::power_pairs (K3 + K5): decode and check n points, draw scalars r_i, return the pair
  * (sum r_i v_i, sum r_i v_{i+1}) over i < n-1 as two uncompressed points in out_pair (host).  The reference
  * draws r_i from thread_rng, so only the verdict downstream is comparable; seed32 == NULL uses fresh host
- * entropy, a 32-byte seed makes the scalars reproducible (tests): r_i = first bits(r)-1 bits of the
- * ChaCha20(seed32) keystream blocks 2i, 2i+1.  TEST-ONLY: two MSMs run with the same seed share their r_i, which
+ * entropy, a 32-byte seed makes the scalars reproducible (tests): r_i = first 128 bits of the ChaCha20(seed32)
+ * keystream block 2i (uniform 128-bit scalars: soundness error 2^-128, a third to a sixth of the work of full-size ones).  TEST-ONLY: two MSMs run with the same seed share their r_i, which
  * makes a G1-vs-G2 comparison of their results vacuous; the verification flows (sso_p1_verify_chunk_*, sso_p1_verify_ratios_file,
  * sso_p2_verify_queries_buf) derive a distinct ChaCha20 key per MSM, Blake2b-256(seed || vector id || chunk || piece || rank). */
 int32_t sso_power_pairs_dev(uint32_t curve, uint32_t group, const void* d_in, uint32_t in_compressed, uint64_t n,

@@ -60,7 +60,7 @@ def lib() -> ctypes.CDLL:
         L.sso_p1_verify_chunk_buf.argtypes = [pp, vp, sz, vp, sz, vp, sz, u32, u32, u32, u32, u8p, i32, cp, sz]
         L.sso_p1_verify_chunk_file.argtypes = [pp, cp, cp, u32, cp, cp, u32, cp, cp, u32, u32, i32, cp, sz]
         L.sso_points_sum.argtypes = [u32, u32, u8p, u64, cp, sz, i32, cp, sz]
-        L.sso_p2_scale_queries_buf.argtypes = [u32, u8p, sz, cp, sz, u64, u8p, u32, u32, u32, i32, cp, sz]
+        L.sso_p2_scale_queries_buf.argtypes = [u32, vp, sz, vp, sz, u64, u8p, u32, u32, u32, i32, cp, sz]
         L.sso_p2_verify_queries_buf.argtypes = [u32, u8p, sz, u8p, sz, u64, u32, u32, u8p, u8p, u32, u32, u8p, i32, cp, sz]
         L.sso_p1_new_challenge_dev.argtypes = [ctypes.POINTER(P1Params), vp, i32, cp, sz]
         L.sso_p1_contribute_many_buf.argtypes = [pp, sz, ctypes.POINTER(vp), ctypes.POINTER(sz), ctypes.POINTER(vp), ctypes.POINTER(sz),

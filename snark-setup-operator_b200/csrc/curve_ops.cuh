@@ -249,11 +249,11 @@ inline int run_fill_generator(Ctx& c, int si, uint64_t n, uint8_t* d_out, uint32
 struct Key32 { uint32_t w[8]; };
 template <class G>
 __global__ void k_random_scalars(uint32_t n, const __grid_constant__ Key32 key, uint32_t* scalars) {
-  body_random_scalars<G::Fr::L, G::Fr::P::BITS - 1>(blockIdx.x * blockDim.x + threadIdx.x, n, key.w, scalars);
+  body_random_scalars<RLC_WORDS, RLC_BITS>(blockIdx.x * blockDim.x + threadIdx.x, n, key.w, scalars);
 }
 template <class G>
 __global__ void k_msm_keys(uint32_t n, uint32_t nwin, uint32_t c, const uint32_t* scalars, uint32_t* keys, uint32_t* vals) {
-  body_msm_keys<G::Fr::L>(blockIdx.x * blockDim.x + threadIdx.x, n, nwin, c, scalars, keys, vals);
+  body_msm_keys<RLC_WORDS>(blockIdx.x * blockDim.x + threadIdx.x, n, nwin, c, scalars, keys, vals);
 }
 template <class G>
 __global__ void __launch_bounds__(128) k_msm_buckets(uint32_t n, uint32_t nwin, uint32_t c, const uint32_t* keys, const uint32_t* vals,
@@ -368,8 +368,9 @@ inline int run_msm_pairs(Ctx& c, int si, const uint32_t* d_aff_a, const uint32_t
                          const uint64_t* tweak, uint8_t* d_out, char* err, size_t errcap) {
   using F = typename G::F;
   using Fr = typename G::Fr;
-  constexpr int KL = Fr::L;
-  constexpr int SBITS = Fr::P::BITS - 1;
+  constexpr int KL = RLC_WORDS;
+  constexpr int SBITS = RLC_BITS;
+  static_assert(RLC_BITS < Fr::P::BITS, "the random scalars must stay below the group order");
   if (n == 0 || n > (1ull << 26)) { set_err(err, errcap, "msm length out of range"); return SSO_E_ARG; }
   cudaStream_t st = c.s[si];
   uint32_t wb = msm_window_bits(n, SBITS), nwin = (SBITS + wb - 1) / wb, nb = 1u << wb;

@@ -64,7 +64,8 @@ struct Bw6_761_G1 {
   static constexpr bool AFFINE_TABLE = true;
   static constexpr bool HAS_GLV = true;
   using Glv = GLV_bw6_761_g1;
-  static constexpr int ENDO_SUBGROUP_TEST = 0;
+  static constexpr int ENDO_SUBGROUP_TEST = 3;          // [x + 1]P + [x^3 - x^2 + 1]phi(P) = O  (ec.cuh::in_subgroup)
+  using Endo = ENDO_bw6_761;
   static constexpr bool HAS_GLS4 = false;
   static constexpr uint32_t GROUP = 0;
   SSO_GROUP_COMMON(bw6_761_g1, Fq761, Fq377)

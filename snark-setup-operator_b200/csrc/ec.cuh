@@ -463,6 +463,21 @@ template <class Cfg> struct SW {
     return acc;
   }
 
+  // [x]J for the sparse 64-bit curve parameter x (constant memory, 2 words) and a Jacobian base: 63 doublings and one full
+  // addition per set bit below the top one
+  __device__ __noinline__ static Jac mul_x_jac(const Jac& base, const uint32_t* x) {
+    if (is_identity(base)) return base;
+    Jac acc = base;
+    bool started = false;
+    for (int i = 63; i >= 0; i--) {
+      bool bit = ((x[i >> 5] >> (i & 31)) & 1) != 0;
+      if (!started) { started = bit; continue; }
+      acc = dbl(acc);
+      if (bit) acc = add(acc, base);
+    }
+    return acc;
+  }
+
   // q == t for a Jacobian q and an affine t != O
   __device__ __forceinline__ static bool jac_eq_affine(const Jac& q, const Affine& t) {
     if (is_identity(q)) return false;
@@ -489,6 +504,21 @@ template <class Cfg> struct SW {
       Jac q = mul_const(p, E::x(), 2);
       Affine t{F::mul_base(F::conj(p.x), B::from_const(E::psi_cx())), F::mul_base(F::conj(p.y), B::from_const(E::psi_cy())), false};
       return jac_eq_affine(q, t);
+    } else if constexpr (Cfg::ENDO_SUBGROUP_TEST == 3) {
+      // BW6-761 G1: [x + 1]P + [x^3 - x^2 + 1]phi(P) = O, phi(X, Y) = (beta X, Y) — equivalent to [r]P = O
+      // (tools/gen_constants.py::bw6_endo_block); chains of multiplications by the sparse x: 256 doublings, ~30 additions
+      using E = typename Cfg::Endo;
+      Affine phip{F::mul(p.x, F::from_const(E::beta_g1())), p.y, false};
+      Affine nphip{phip.x, F::neg(phip.y), false};
+      Jac res = mul_const(phip, E::x(), 2);          // x phi(P)
+      res = madd(res, nphip);                         // (x - 1) phi(P)
+      res = mul_x_jac(res, E::x());                   // (x^2 - x) phi(P)
+      res = mul_x_jac(res, E::x());                   // (x^3 - x^2) phi(P)
+      res = madd(res, phip);                          // (x^3 - x^2 + 1) phi(P)
+      Jac t = mul_const(p, E::x(), 2);                // x P
+      t = madd(t, p);                                 // (x + 1) P
+      t = add(t, res);
+      return is_identity(t);
     } else {
       Jac q = mul_const(p, Cfg::order(), (Cfg::Fr::P::BITS + 31) / 32);
       return is_identity(q);

@@ -207,10 +207,55 @@ inline int verify_chunk_host(Ctx& c, const CurveOps* ops, const P1Layout& L, uin
   static const char* vnames[5] = {"response tau_g1", "response tau_g2", "response alpha_g1", "response beta_g1", "response beta_g2"};
   static const char* inames[5] = {"challenge tau_g1", "challenge tau_g2", "challenge alpha_g1", "challenge beta_g1", "challenge beta_g2"};
   const uint32_t elem_check = verify_elem_check(check_output), subgroup = verify_subgroup(check_output, subgroup_mode);
-  // the two sequential Blake2b passes (challenge, response) run on a host thread beside the GPU work
-  uint8_t ch_hash[64], resp_hash[64];
-  std::thread hasher([&] { blake2b_512(challenge, L.acc_size, ch_hash); blake2b_512(response, L.contrib_size, resp_hash); });
-  struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{hasher};
+  // Beside the main GPU work, on a host thread with its own high-priority stream: Blake2b(challenge) (sequential, the longest
+  // host step), then — the digest known — the public-key validation and g2_s = hash_to_g2(Blake2b(pers || digest || g1_s ||
+  // g1_s_x)) of the three proofs (single-thread chains of tens of milliseconds that would otherwise run after everything
+  // else), and Blake2b(response) while those kernels run.
+  struct Side { int rc = SSO_OK; char err[256]; uint8_t ch_hash[64], resp_hash[64]; std::vector<uint8_t> g2s; } side;
+  side.err[0] = 0;
+  const uint8_t* pk = response + L.off_c[5];
+  const int side_device = c.dev;
+  std::thread side_thread([&] {
+    char* err = side.err; size_t errcap = sizeof side.err;
+    side.rc = [&]() -> int {
+      int rc;
+      blake2b_512(challenge, L.acc_size, side.ch_hash);
+      Ctx c2(err, errcap);
+      if ((rc = c2.init(side_device, 3))) return rc;
+      const int si = c2.aliased ? 0 : 2;
+      // the public key: nine points that must be non-zero, on their curves and in the subgroups (a zero or torsion point
+      // would make the proof-of-knowledge pairings vacuous)
+      uint8_t *d_pk, *d_g2s;
+      uint32_t *d_status, *d_seeds2;
+      if ((rc = c2.alloc((void**)&d_pk, L.pk_size, si))) return rc;
+      if ((rc = c2.alloc((void**)&d_status, STATUS_BYTES, si))) return rc;
+      if ((rc = c2.alloc((void**)&d_seeds2, 96, si))) return rc;
+      if ((rc = c2.alloc((void**)&d_g2s, 3 * g2u, si))) return rc;
+      CUDA_TRY(cudaMemsetAsync(d_status, 0, STATUS_BYTES, c2.s[si]));
+      CUDA_TRY(cudaMemcpyAsync(d_pk, pk, L.pk_size, cudaMemcpyHostToDevice, c2.s[si]));
+      if ((rc = ops->reencode(c2, si, GROUP_G1, d_pk, 0, 6, nullptr, 0, CHECK_FULL, 1, nullptr, d_status, err, errcap))) return rc;
+      if ((rc = ops->reencode(c2, si, GROUP_G2, d_pk + 6 * g1u, 0, 3, nullptr, 0, CHECK_FULL, 1, nullptr, d_status, err, errcap))) return rc;
+      std::vector<uint8_t> seeds2(3 * 32);
+      for (uint32_t i = 0; i < 3; i++) {
+        Blake2b h(64);
+        uint8_t pers = (uint8_t)i, full[64];
+        h.update(&pers, 1);
+        h.update(side.ch_hash, 64);
+        h.update(pk + (size_t)2 * i * g1u, 2 * g1u);
+        h.final(full, 64);
+        memcpy(seeds2.data() + 32 * i, full, 32);
+      }
+      CUDA_TRY(cudaMemcpyAsync(d_seeds2, seeds2.data(), 96, cudaMemcpyHostToDevice, c2.s[si]));
+      if ((rc = ops->hash_to_g2(c2, si, 3, d_seeds2, nullptr, d_g2s, nullptr, err, errcap))) return rc;
+      side.g2s.resize(3 * g2u);
+      CUDA_TRY(cudaMemcpyAsync(side.g2s.data(), d_g2s, side.g2s.size(), cudaMemcpyDeviceToHost, c2.s[si]));
+      blake2b_512(response, L.contrib_size, side.resp_hash);
+      CUDA_TRY(cudaStreamSynchronize(c2.s[si]));
+      if ((rc = check_status(c2, d_status, "public key", err, errcap))) return rc == SSO_E_INPUT ? SSO_E_VERIFY : rc;
+      return SSO_OK;
+    }();
+  });
+  struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{side_thread};
   std::vector<uint8_t> pairs[4];
   if (!P) {
     // 1. decode + check the response vectors on the device, producing the new challenge image
@@ -285,46 +330,15 @@ inline int verify_chunk_host(Ctx& c, const CurveOps* ops, const P1Layout& L, uin
     if ((rc = stream_reencode(ops, L.cs, vecs, piece_elems, rlc_seed32, chunk_index, *P, &out_pairs, err, errcap))) return rc == SSO_E_INPUT ? SSO_E_VERIFY : rc;
     for (int v = 0; v < 4; v++) if (ratio_check && counts[v] >= 2) pairs[v] = out_pairs[v];
   }
-  // 3. hash chain: the response must continue the challenge; the new challenge's hash slot chains the response
-  hasher.join();
-  if (ch_hash_out) memcpy(ch_hash_out, ch_hash, 64);
-  if (memcmp(ch_hash, response, 64) != 0) { set_err(err, errcap, "hash chain broken: response does not continue the challenge"); return SSO_E_VERIFY; }
-  memcpy(new_challenge, resp_hash, 64);
-  c.mark("verify: blake2b(challenge), blake2b(response)");
-  // 4. the public key: nine points that must be non-zero, on their curves and in the subgroups (a zero or torsion point would
-  // make the proof-of-knowledge pairings vacuous); then g2_s = hash_to_g2(Blake2b(pers || digest || g1_s || g1_s_x))
-  const uint8_t* pk = response + L.off_c[5];
-  {
-    uint8_t* d_pk;
-    uint32_t* d_status;
-    if ((rc = c.alloc((void**)&d_pk, L.pk_size))) return rc;
-    if ((rc = c.alloc((void**)&d_status, STATUS_BYTES))) return rc;
-    CUDA_TRY(cudaMemsetAsync(d_status, 0, STATUS_BYTES, c.s[0]));
-    CUDA_TRY(cudaMemcpyAsync(d_pk, pk, L.pk_size, cudaMemcpyHostToDevice, c.s[0]));
-    if ((rc = ops->reencode(c, 0, GROUP_G1, d_pk, 0, 6, nullptr, 0, CHECK_FULL, 1, nullptr, d_status, err, errcap))) return rc;
-    if ((rc = ops->reencode(c, 0, GROUP_G2, d_pk + 6 * g1u, 0, 3, nullptr, 0, CHECK_FULL, 1, nullptr, d_status, err, errcap))) return rc;
-    CUDA_TRY(cudaStreamSynchronize(c.s[0]));
-    if ((rc = check_status(c, d_status, "public key", err, errcap))) return rc == SSO_E_INPUT ? SSO_E_VERIFY : rc;
-  }
-  std::vector<uint8_t> seeds2(3 * 32);
-  for (uint32_t i = 0; i < 3; i++) {
-    Blake2b h(64);
-    uint8_t pers = (uint8_t)i, full[64];
-    h.update(&pers, 1);
-    h.update(ch_hash, 64);
-    h.update(pk + (size_t)2 * i * g1u, 2 * g1u);
-    h.final(full, 64);
-    memcpy(seeds2.data() + 32 * i, full, 32);
-  }
-  uint32_t* d_seeds2;
-  uint8_t* d_g2s;
-  if ((rc = c.alloc((void**)&d_seeds2, 96))) return rc;
-  if ((rc = c.alloc((void**)&d_g2s, 3 * g2u))) return rc;
-  CUDA_TRY(cudaMemcpyAsync(d_seeds2, seeds2.data(), 96, cudaMemcpyHostToDevice, c.s[0]));
-  if ((rc = ops->hash_to_g2(c, 0, 3, d_seeds2, nullptr, d_g2s, nullptr, err, errcap))) return rc;
-  std::vector<uint8_t> g2s(3 * g2u);
-  CUDA_TRY(cudaMemcpyAsync(g2s.data(), d_g2s, g2s.size(), cudaMemcpyDeviceToHost, c.s[0]));
-  CUDA_TRY(cudaStreamSynchronize(c.s[0]));
+  // 3. the side thread's results: hash chain (the response must continue the challenge; the new challenge's hash slot chains
+  // the response), the validated public key and the g2_s points of the proofs
+  side_thread.join();
+  if (ch_hash_out) memcpy(ch_hash_out, side.ch_hash, 64);
+  if (memcmp(side.ch_hash, response, 64) != 0) { set_err(err, errcap, "hash chain broken: response does not continue the challenge"); return SSO_E_VERIFY; }
+  if (side.rc != SSO_OK) { set_err(err, errcap, "%s", side.err); return side.rc; }
+  memcpy(new_challenge, side.resp_hash, 64);
+  const std::vector<uint8_t>& g2s = side.g2s;
+  c.mark("verify: hashes, public key, hash_to_g2");
   // 5. collect the same_ratio checks
   std::vector<RatioCheck> checks;
   const uint8_t* pk_g2 = pk + 6 * g1u;                       // tau_g2, alpha_g2, beta_g2 (= g2_s_x)

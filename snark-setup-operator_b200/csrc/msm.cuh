@@ -38,8 +38,16 @@ __device__ __forceinline__ void chacha20_block(const uint32_t* key, uint64_t cou
   for (int i = 0; i < 16; i++) out[i] = x[i] + s[i];
 }
 
+// Width of the random-linear-combination scalars.  The reference draws full-size Fr::rand scalars from thread_rng; what
+// the same-ratio test needs from them is unpredictability — a contribution with a wrong element passes with probability
+// 2^-128 when the r_i are uniform 128-bit integers, the bound batch verification commonly works with — so this core draws
+// 128-bit scalars: half (BLS12-377), a third (BW6-761) or a sixth (MNT4/6-753) of the windows, bucket additions and
+// final doublings of an MSM with full-size scalars.  Verdicts, not scalars, are what is comparable with the reference.
+static constexpr int RLC_BITS = 128;
+static constexpr int RLC_WORDS = 4;
+
 // scalar i = first SBITS bits of the ChaCha20 keystream blocks (2i, 2i+1): uniform in [0, 2^SBITS)
-// with SBITS = bits(r) - 1, hence < r.  Words: [i][KL].
+// with SBITS = RLC_BITS < bits(r).  Words: [i][KL].
 template <int KL, int SBITS>
 __device__ __forceinline__ void body_random_scalars(uint32_t tid, uint32_t n, const uint32_t* key, uint32_t* scalars) {
   if (tid >= n) return;

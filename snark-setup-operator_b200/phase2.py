@@ -10,14 +10,20 @@ from ._lib import call
 from .phase1 import CHECK_NO, curve_id, curve_sizes, scalar_bytes
 
 
-def scale_queries(curve, queries: bytes, n: int, delta_inv: int, in_compressed=False, out_compressed=False, check=CHECK_NO,
-                  device=0) -> bytes:
-    """h_query / l_query (n serialized G1 points) -> the same vector multiplied by delta^-1."""
+def scale_queries(curve, queries, n: int, delta_inv: int, in_compressed=False, out_compressed=False, check=CHECK_NO,
+                  device=0, out=None):
+    """h_query / l_query (n serialized G1 points: bytes, numpy or a pinned torch tensor) -> the same vector multiplied by
+    delta^-1; returns bytes, or fills the writable buffer `out` when given."""
+    from .phase1 import _host_ptr
     s = curve_sizes(curve)
-    out = ctypes.create_string_buffer(n * (s["g1_c"] if out_compressed else s["g1_u"]))
-    call("sso_p2_scale_queries_buf", curve_id(curve), queries, len(queries), out, len(out), n, scalar_bytes(curve, delta_inv),
+    in_ptr, in_len, k1 = _host_ptr(queries)
+    out_len = n * (s["g1_c"] if out_compressed else s["g1_u"])
+    buf = ctypes.create_string_buffer(out_len) if out is None else None
+    out_ptr, out_len2, k2 = (ctypes.addressof(buf), out_len, buf) if out is None else _host_ptr(out)
+    call("sso_p2_scale_queries_buf", curve_id(curve), in_ptr, in_len, out_ptr, out_len2, n, scalar_bytes(curve, delta_inv),
          int(in_compressed), int(out_compressed), check, device)
-    return out.raw
+    del k1, k2
+    return buf.raw if out is None else out
 
 
 def verify_queries(curve, before: bytes, after: bytes, n: int, delta_g2_before: bytes, delta_g2_after: bytes,

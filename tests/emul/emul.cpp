@@ -162,8 +162,8 @@ extern "C" int emul_power_pairs(uint32_t curve, uint32_t group, const uint8_t* i
     using G = decltype(g);
     using F = typename G::F;
     using Fr = typename G::Fr;
-    constexpr int KL = Fr::L;
-    constexpr int SBITS = Fr::P::BITS - 1;
+    constexpr int KL = RLC_WORDS;
+    constexpr int SBITS = RLC_BITS;
     std::vector<uint32_t> aff((size_t)n * 2 * F::WORDS);
     for (uint32_t t = 0; t < n; t++) body_reencode<G>(t, n, in, in_compressed, nullptr, 0, 0, 0, aff.data(), status);
     uint32_t m = n - 1;

@@ -132,12 +132,13 @@ def test_bls12_g2_four_way_decomposition_edge_scalars(emul):
         assert out.raw == want, hex(k)
 
 
-@pytest.mark.parametrize("gi", [0, 1])
-def test_endomorphism_subgroup_tests_agree_with_order_check(emul, gi):
-    """BLS12-377 membership is tested on the device as phi(P) = [-x^2]P (G1) / psi(P) = [x]P (G2); the verdict must be
-    the reference's [r]P == O on every kind of on-curve point: random curve points, pure cofactor-torsion points
-    [r]P, and subgroup points plus a cofactor-torsion component."""
-    c = get_curve("bls12_377")
+@pytest.mark.parametrize("name,gi", [("bls12_377", 0), ("bls12_377", 1), ("bw6_761", 0), ("bw6_761", 1)])
+def test_endomorphism_subgroup_tests_agree_with_order_check(emul, name, gi):
+    """Membership is tested on the device in endomorphism form where the curve has one — BLS12-377: phi(P) = [-x^2]P (G1) /
+    psi(P) = [x]P (G2); BW6-761 G1: [x + 1]P + [x^3 - x^2 + 1]phi(P) = O (G2 keeps [r]P) —; the verdict must be the
+    reference's [r]P == O on every kind of on-curve point: random curve points, pure cofactor-torsion points [r]P, points of
+    tiny order, and subgroup points plus a cofactor-torsion component."""
+    c = get_curve(name)
     G = c.g1 if gi == 0 else c.g2
     from oracle.curves import _some_point
     rogue = [_some_point(G, s) for s in (11, 12, 13)]
@@ -154,7 +155,7 @@ def test_endomorphism_subgroup_tests_agree_with_order_check(emul, gi):
             continue
         assert G.on_curve(P) and G.in_subgroup(P) == want_ok
         emul.emul_reencode(c.cid, gi, ser.point_to_bytes(G, P, False), 0, 1, out, 0, 2, 1, st)
-        assert (st[0] == 0) == want_ok, (gi, want_ok, st[0])
+        assert (st[0] == 0) == want_ok, (name, gi, want_ok, st[0])
         if not want_ok:
             assert st[0] == 5
 
