@@ -699,7 +699,7 @@ def main():
                 list(ex.map(one_file, range(lanes)))
                 n_calls = max(lanes, 2 * args.steps)
                 t0 = time.perf_counter()
-                list(ex.map(one_file, [i % lanes for i in range(n_calls)]))
+                list(ex.map(one_file, range(lanes, lanes + n_calls)))          # distinct outputs per call (lanes run concurrently)
                 t_lanes = (time.perf_counter() - t0) / n_calls
             file_call = {"single_call": {"value": npts / t_single, "ms_per_step": t_single * 1e3},
                          "lanes": {"value": npts / t_lanes, "ms_per_step": t_lanes * 1e3, "process_lanes": lanes},

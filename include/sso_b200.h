@@ -110,8 +110,8 @@ int32_t sso_reencode_dev(uint32_t curve, uint32_t group, const void* d_in, uint3
 /* setup_utils::power_pairs (K3 + K5): decode and check n points, draw scalars r_i, return the pair
  * (sum r_i v_i, sum r_i v_{i+1}) over i < n-1 as two uncompressed points in out_pair (host).  The reference
  * draws r_i from thread_rng, so only the verdict downstream is comparable; seed32 == NULL uses fresh host
- * entropy, a 32-byte seed makes the scalars reproducible (tests): r_i = first 128 bits of the ChaCha20(seed32)
- * keystream block 2i (uniform 128-bit scalars: soundness error 2^-128, a third to a sixth of the work of full-size ones).  TEST-ONLY: two MSMs run with the same seed share their r_i, which
+ * entropy, a 32-byte seed makes the scalars reproducible (tests): r_i = first 120 bits of the ChaCha20(seed32)
+ * keystream block 2i (uniform 120-bit scalars: soundness error 2^-120, a third to a sixth of the work of full-size ones).  TEST-ONLY: two MSMs run with the same seed share their r_i, which
  * makes a G1-vs-G2 comparison of their results vacuous; the verification flows (sso_p1_verify_chunk_*, sso_p1_verify_ratios_file,
  * sso_p2_verify_queries_buf) derive a distinct ChaCha20 key per MSM, Blake2b-256(seed || vector id || chunk || piece || rank). */
 int32_t sso_power_pairs_dev(uint32_t curve, uint32_t group, const void* d_in, uint32_t in_compressed, uint64_t n,
@@ -299,6 +299,33 @@ int32_t sso_p2_verify_queries_buf(uint32_t curve, const uint8_t* before, size_t 
                                   uint64_t n, uint32_t before_compressed, uint32_t after_compressed, const uint8_t* delta_g2_before,
                                   const uint8_t* delta_g2_after, uint32_t check, uint32_t subgroup_check, const uint8_t* rlc_seed32,
                                   int device, char* err, size_t errcap);
+
+/* phase2_cli::contribute::<P> / phase2_cli::verify::<P> on the Groth16 parameter container (rows a10, a11; reference
+ * src/bin/contribute.rs:827-838, 990-1007, src/bin/verify_transcript.rs:486-503, 655-672, 698-715, src/bin/control.rs:633-644,
+ * 810-824; MPCParameters::read_fast at src/bin/get_keys.rs:81-88).  The curve type parameter becomes `curve`, the rng its
+ * 32-byte seed.  Container ([UP] phase2::MPCParameters over ark-groth16 0.4, as recalled — see csrc/p2.cuh):
+ *   vk.alpha_g1 | vk.beta_g2 | vk.gamma_g2 | vk.delta_g2 | vk.gamma_abc_g1[] | beta_g1 | delta_g1 | a_query[] | b_g1_query[] |
+ *   b_g2_query[] | h_query[] | l_query[] | cs_hash[64] | u32 BE count | contributions (delta_after, s, s_delta, r_delta, transcript)
+ * challenge files uncompressed, responses compressed; vectors carry a u64 LE length.
+ *   contribute: delta <- Fr::rand, s <- G1::rand; proof of knowledge bound to the transcript of the earlier contributions;
+ *               h_query, l_query *= delta^-1 (the batch_mul of K7), delta_g1, vk.delta_g2 *= delta; the public key is appended
+ *   verify:     structure and untouched elements equal, transcript chain, proof of knowledge, delta_g1 / delta_g2 updates and
+ *               same_ratio(merge_pairs(query_before, query_after), (delta_g2_after, delta_g2_before)) for h and l; writes the
+ *               decompressed new challenge.  verify_full is accepted for signature parity (this container is always whole).
+ * `_buf`: *out_len receives the size of the output; SSO_E_ARG (with the size) when the capacity is too small. */
+int32_t sso_p2_contribute_buf(uint32_t curve, const uint8_t* challenge, size_t challenge_len, uint8_t* response, size_t response_cap,
+                              size_t* response_len, const uint8_t seed32[32], uint32_t check_input, int device, char* err, size_t errcap);
+int32_t sso_p2_contribute_file(uint32_t curve, const char* challenge_fn, const char* challenge_hash_fn, const char* response_fn,
+                               const char* response_hash_fn, uint32_t check_input, uint32_t batch_exp_mode, const uint8_t seed32[32],
+                               int device, char* err, size_t errcap);
+int32_t sso_p2_verify_buf(uint32_t curve, const uint8_t* challenge, size_t challenge_len, const uint8_t* response, size_t response_len,
+                          uint8_t* new_challenge, size_t new_challenge_cap, size_t* new_challenge_len, uint32_t check_input,
+                          uint32_t check_output, uint32_t subgroup_check_mode, const uint8_t* rlc_seed32, int device, char* err,
+                          size_t errcap);
+int32_t sso_p2_verify_file(uint32_t curve, const char* challenge_fn, const char* challenge_hash_fn, uint32_t check_input,
+                           const char* response_fn, const char* response_hash_fn, uint32_t check_output, const char* new_challenge_fn,
+                           const char* new_challenge_hash_fn, uint32_t subgroup_check_mode, uint32_t verify_full, int device, char* err,
+                           size_t errcap);
 
 /* setup_utils::calculate_hash (reference src/utils.rs:618-623): Blake2b-512, unkeyed. Host only. */
 int32_t sso_blake2b_512(const uint8_t* data, size_t len, uint8_t out[64]);

@@ -298,14 +298,14 @@ def rlc_key(seed32: bytes, tweak) -> bytes:
 
 def rlc_scalars(curve: Curve, seed32: bytes, n: int, tweak=None):
     """The product's reproducible random-linear-combination scalars (include/sso_b200.h,
-    sso_power_pairs_dev): r_i = first 128 bits (csrc/msm.cuh RLC_BITS) of the ChaCha20(key) keystream blocks 2i, 2i+1; key = seed32 for the
+    sso_power_pairs_dev): r_i = first 120 bits (csrc/msm.cuh RLC_BITS) of the ChaCha20(key) keystream blocks 2i, 2i+1; key = seed32 for the
     test-only primitives, rlc_key(seed32, tweak) inside the verification flows."""
     import struct
     from .chacha import chacha20_block
     if tweak is not None:
         seed32 = rlc_key(seed32, tweak)
     key = struct.unpack("<8I", seed32)
-    sbits = min(curve.Fr.bits - 1, 128)                      # csrc/msm.cuh RLC_BITS
+    sbits = min(curve.Fr.bits - 1, 120)                      # csrc/msm.cuh RLC_BITS
     out = []
     for i in range(n):
         words = chacha20_block(key, 2 * i)

@@ -78,6 +78,11 @@ def lib() -> ctypes.CDLL:
         L.sso_dist_init.argtypes = [ctypes.c_int32, ctypes.c_int32, u8p, i32, cp, sz]
         L.sso_dist_barrier.argtypes = [cp, sz]
         L.sso_dist_stats.argtypes = [ctypes.POINTER(u64)]
+        szp = ctypes.POINTER(sz)
+        L.sso_p2_contribute_buf.argtypes = [u32, vp, sz, vp, sz, szp, u8p, u32, i32, cp, sz]
+        L.sso_p2_contribute_file.argtypes = [u32, cp, cp, cp, cp, u32, u32, u8p, i32, cp, sz]
+        L.sso_p2_verify_buf.argtypes = [u32, vp, sz, vp, sz, vp, sz, szp, u32, u32, u32, u8p, i32, cp, sz]
+        L.sso_p2_verify_file.argtypes = [u32, cp, cp, u32, cp, cp, u32, cp, cp, u32, u32, i32, cp, sz]
         L.sso_profile_enable.argtypes = [ctypes.c_int32]
         L.sso_profile_read.argtypes = [ctypes.POINTER(u64), sz]
         L.sso_imad_peak.argtypes = [i32, i32, ctypes.POINTER(ctypes.c_double), cp, sz]
@@ -89,6 +94,7 @@ def lib() -> ctypes.CDLL:
                      "sso_p1_contribute_seeded_buf", "sso_p1_contribute_file", "sso_p1_verify_chunk_buf", "sso_p1_verify_chunk_file", "sso_points_sum",
                      "sso_p2_scale_queries_buf", "sso_p2_verify_queries_buf", "sso_p1_contribute_many_buf", "sso_p1_verify_chunk_many_buf",
                      "sso_p1_new_challenge_file", "sso_p1_set_generators", "sso_p1_combine_file", "sso_p1_verify_ratios_file",
+                     "sso_p2_contribute_buf", "sso_p2_contribute_file", "sso_p2_verify_buf", "sso_p2_verify_file",
                      "sso_dist_unique_id", "sso_dist_init", "sso_dist_barrier", "sso_dist_finalize", "sso_dist_stats", "sso_p1_contribute_seeded_many_buf"):
             getattr(L, name).restype = ctypes.c_int32
         _lib = L

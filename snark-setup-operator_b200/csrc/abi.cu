@@ -6,6 +6,7 @@
 // There is no CPU fallback: without a device every compute entry returns SSO_E_CUDA.
 #include "flows.cuh"
 #include "files.cuh"
+#include "p2.cuh"
 #include <memory>
 #include <thread>
 #include <mutex>
@@ -1136,6 +1137,281 @@ int32_t sso_p1_verify_ratios_file(const sso_p1_params_t* p, const char* combined
     return run_checks(c, ops, checks, err, errcap);
   };
   return coop_result(coop, body(), err, errcap);
+}
+
+// ---------------------------------------------------------------------------------------------
+// phase 2 on the parameter container (p2.cuh)
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+const uint32_t* fr_modulus_host(uint32_t curve, int& L) {
+  switch (curve) {
+    case SSO_CURVE_BLS12_377: L = P_r253::L; return P_r253::host_p();
+    case SSO_CURVE_BW6_761: L = P_q377::L; return P_q377::host_p();
+    case SSO_CURVE_MNT4_753: L = P_q6::L; return P_q6::host_p();
+    case SSO_CURVE_MNT6_753: L = P_q4::L; return P_q4::host_p();
+  }
+  L = 0;
+  return nullptr;
+}
+
+// a^-1 mod p on canonical little-endian limbs (binary extended Euclid; p odd, 0 < a < p) — one inversion per contribution
+bool host_mod_inverse(const uint32_t* a, const uint32_t* p, int L, uint32_t* out) {
+  auto is_zero = [&](const std::vector<uint32_t>& x) { for (uint32_t w : x) if (w) return false; return true; };
+  auto is_one = [&](const std::vector<uint32_t>& x) { if (x[0] != 1) return false; for (int i = 1; i < L; i++) if (x[i]) return false; return true; };
+  auto ge = [&](const std::vector<uint32_t>& x, const std::vector<uint32_t>& y) { for (int i = L - 1; i >= 0; i--) { if (x[i] != y[i]) return x[i] > y[i]; } return true; };
+  auto sub = [&](std::vector<uint32_t>& x, const std::vector<uint32_t>& y) { uint64_t b = 0; for (int i = 0; i < L; i++) { uint64_t d = (uint64_t)x[i] - y[i] - b; x[i] = (uint32_t)d; b = (d >> 32) & 1; } return b; };
+  auto add = [&](std::vector<uint32_t>& x, const std::vector<uint32_t>& y) { uint64_t cy = 0; for (int i = 0; i < L; i++) { uint64_t d = (uint64_t)x[i] + y[i] + cy; x[i] = (uint32_t)d; cy = d >> 32; } return cy; };
+  auto shr1 = [&](std::vector<uint32_t>& x, uint32_t top) { for (int i = 0; i < L - 1; i++) x[i] = (x[i] >> 1) | (x[i + 1] << 31); x[L - 1] = (x[L - 1] >> 1) | (top << 31); };
+  std::vector<uint32_t> u(a, a + L), v(p, p + L), x1(L, 0), x2(L, 0), pm(p, p + L);
+  if (is_zero(u)) return false;
+  x1[0] = 1;
+  auto halve = [&](std::vector<uint32_t>& x) { uint32_t cy = 0; if (x[0] & 1) cy = (uint32_t)add(x, pm); shr1(x, cy); };
+  while (!is_one(u) && !is_one(v)) {
+    while (!(u[0] & 1)) { shr1(u, 0); halve(x1); }
+    while (!(v[0] & 1)) { shr1(v, 0); halve(x2); }
+    if (ge(u, v)) { sub(u, v); if (sub(x1, x2)) add(x1, pm); }
+    else { sub(v, u); if (sub(x2, x1)) add(x2, pm); }
+  }
+  const std::vector<uint32_t>& r = is_one(u) ? x1 : x2;
+  memcpy(out, r.data(), (size_t)L * 4);
+  return true;
+}
+
+// scalar * point for one serialized point (host in, host out)
+int scalar_mul_one(Ctx& c, const CurveOps* ops, const CurveSizes& cs, uint32_t group, const uint8_t* pt, bool in_compressed, const uint8_t* scalar,
+                   uint8_t* out_uncompressed, char* err, size_t errcap) {
+  int rc;
+  const size_t isz = point_size(cs, group, in_compressed), usz = point_size(cs, group, 0);
+  uint8_t *d_in, *d_out;
+  uint32_t *d_status, *d_table;
+  if ((rc = c.alloc((void**)&d_in, isz))) return rc;
+  if ((rc = c.alloc((void**)&d_out, usz))) return rc;
+  if ((rc = c.alloc((void**)&d_status, STATUS_BYTES))) return rc;
+  CUDA_TRY(cudaMemsetAsync(d_status, 0, STATUS_BYTES, c.s[0]));
+  CUDA_TRY(cudaMemcpyAsync(d_in, pt, isz, cudaMemcpyHostToDevice, c.s[0]));
+  std::vector<uint8_t> one(ops->fr_bytes, 0);
+  one[0] = 1;
+  const uint8_t* coeffs[TAU_COEFF_SLOTS] = {scalar, nullptr, nullptr};
+  if ((rc = ops->tau_tables(c, 0, 0, one.data(), coeffs, &d_table, err, errcap))) return rc;
+  VecBatch b = batch_of({seg(d_in, d_out, 1, 0, 1, 1)});
+  if ((rc = ops->batch_exp(c, 0, group, b, in_compressed, d_table, 0, CHECK_NO, d_status, err, errcap))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(out_uncompressed, d_out, usz, cudaMemcpyDeviceToHost, c.s[0]));
+  CUDA_TRY(cudaStreamSynchronize(c.s[0]));
+  return check_status(c, d_status, "point", err, errcap);
+}
+
+// r = hash_to_g2(transcript[..32]) and optionally r_delta
+int p2_hash_to_g2(Ctx& c, const CurveOps* ops, const CurveSizes& cs, const uint8_t transcript[64], const uint32_t* d_scalar, uint8_t* r_out,
+                  uint8_t* r_delta_out, char* err, size_t errcap) {
+  int rc;
+  uint32_t* d_seed;
+  uint8_t *d_r, *d_rd;
+  if ((rc = c.alloc((void**)&d_seed, 32))) return rc;
+  if ((rc = c.alloc((void**)&d_r, cs.g2u))) return rc;
+  if ((rc = c.alloc((void**)&d_rd, cs.g2u))) return rc;
+  c.staging.emplace_back(8, 0u);
+  memcpy(c.staging.back().data(), transcript, 32);
+  CUDA_TRY(cudaMemcpyAsync(d_seed, c.staging.back().data(), 32, cudaMemcpyHostToDevice, c.s[0]));
+  if ((rc = ops->hash_to_g2(c, 0, 1, d_seed, d_scalar, d_r, d_scalar ? d_rd : nullptr, err, errcap))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(r_out, d_r, cs.g2u, cudaMemcpyDeviceToHost, c.s[0]));
+  if (d_scalar) CUDA_TRY(cudaMemcpyAsync(r_delta_out, d_rd, cs.g2u, cudaMemcpyDeviceToHost, c.s[0]));
+  CUDA_TRY(cudaStreamSynchronize(c.s[0]));
+  return SSO_OK;
+}
+
+}  // namespace
+
+// phase2_cli::contribute on host buffers: challenge (uncompressed container) -> response (compressed container, one more
+// contribution).  *response_len receives the size; SSO_E_ARG with the needed size in *response_len when response_cap is too small.
+int32_t sso_p2_contribute_buf(uint32_t curve, const uint8_t* challenge, size_t challenge_len, uint8_t* response, size_t response_cap,
+                              size_t* response_len, const uint8_t seed32[32], uint32_t check_input, int device, char* err, size_t errcap) {
+  const CurveOps* ops = ops_for(curve);
+  CurveSizes cs;
+  if (!ops || !curve_sizes(curve, cs) || !challenge || !response_len || !seed32) { set_err(err, errcap, "unknown curve %u or null argument", curve); return SSO_E_ARG; }
+  P2View vi;
+  int rc = p2_parse(challenge, challenge_len, false, cs, vi, err, errcap);
+  if (rc) return rc;
+  const size_t need = p2_size(vi, cs, true, 1);
+  *response_len = need;
+  if (!response || response_cap < need) { set_err(err, errcap, "response buffer too small: %zu bytes needed", need); return SSO_E_ARG; }
+  Ctx c(err, errcap);
+  if ((rc = c.init(device, 1))) return rc;
+  // the key pair: delta <- Fr::rand, s <- G1::rand, s_delta (the RNG draws, in the reference's order)
+  std::vector<uint8_t> delta(cs.fr);
+  KeygenState keys;
+  if ((rc = keygen_stage1(c, 0, ops, cs, seed32, 1, keys, delta.data(), err, errcap))) return rc;
+  int L;
+  const uint32_t* pmod = fr_modulus_host(curve, L);
+  std::vector<uint32_t> dw(L, 0), iw(L, 0);
+  memcpy(dw.data(), delta.data(), cs.fr);
+  if (!host_mod_inverse(dw.data(), pmod, L, iw.data())) { set_err(err, errcap, "delta is zero"); return SSO_E_INPUT; }
+  std::vector<uint8_t> delta_inv(cs.fr);
+  memcpy(delta_inv.data(), iw.data(), cs.fr);
+  uint8_t transcript[64];
+  p2_transcript(challenge, vi, keys.g1.data(), cs.g1u, transcript);
+  std::vector<uint8_t> r(cs.g2u), r_delta(cs.g2u), delta_after(cs.g1u);
+  if ((rc = p2_hash_to_g2(c, ops, cs, transcript, keys.d_scalars, r.data(), r_delta.data(), err, errcap))) return rc;
+  if ((rc = scalar_mul_one(c, ops, cs, GROUP_G1, challenge + vi.delta_g1, false, delta.data(), delta_after.data(), err, errcap))) return rc;
+  // the elements: h / l queries by delta^-1, delta_g1 / delta_g2 by delta, everything else re-encoded
+  if ((rc = p2_transform(c, ops, cs, challenge, vi, response, true, delta.data(), delta_inv.data(), check_input, 0, "challenge", err, errcap))) return rc;
+  // append the public key
+  uint8_t* tail = response + need - vi.contrib_size;
+  wr_u32be(response + need - 4 - (size_t)(vi.n_contrib + 1) * vi.contrib_size, vi.n_contrib + 1);
+  memcpy(tail, delta_after.data(), cs.g1u);
+  memcpy(tail + cs.g1u, keys.g1.data(), 2 * cs.g1u);
+  memcpy(tail + 3 * cs.g1u, r_delta.data(), cs.g2u);
+  memcpy(tail + 3 * cs.g1u + cs.g2u, transcript, 64);
+  return SSO_OK;
+}
+
+// phase2_cli::verify on host buffers: challenge (uncompressed) + response (compressed) -> new challenge (uncompressed).
+int32_t sso_p2_verify_buf(uint32_t curve, const uint8_t* challenge, size_t challenge_len, const uint8_t* response, size_t response_len,
+                          uint8_t* new_challenge, size_t new_challenge_cap, size_t* new_challenge_len, uint32_t check_input, uint32_t check_output,
+                          uint32_t subgroup_check_mode, const uint8_t* rlc_seed32, int device, char* err, size_t errcap) {
+  const CurveOps* ops = ops_for(curve);
+  CurveSizes cs;
+  if (!ops || !curve_sizes(curve, cs) || !challenge || !response || !new_challenge_len) { set_err(err, errcap, "unknown curve %u or null argument", curve); return SSO_E_ARG; }
+  P2View vc, vr;
+  int rc;
+  if ((rc = p2_parse(challenge, challenge_len, false, cs, vc, err, errcap))) return rc;
+  if ((rc = p2_parse(response, response_len, true, cs, vr, err, errcap))) return rc == SSO_E_INPUT ? SSO_E_VERIFY : rc;
+  const size_t need = p2_size(vr, cs, false, 0);
+  *new_challenge_len = need;
+  if (!new_challenge || new_challenge_cap < need) { set_err(err, errcap, "new challenge buffer too small: %zu bytes needed", need); return SSO_E_ARG; }
+  auto reject = [&](const char* why) { set_err(err, errcap, "phase-2 verification: %s", why); return (int32_t)SSO_E_VERIFY; };
+  if (vc.gamma_abc.n != vr.gamma_abc.n || vc.a_query.n != vr.a_query.n || vc.b_g1_query.n != vr.b_g1_query.n || vc.b_g2_query.n != vr.b_g2_query.n ||
+      vc.h_query.n != vr.h_query.n || vc.l_query.n != vr.l_query.n) return reject("the query lengths changed");
+  if (vr.n_contrib != vc.n_contrib + 1) return reject("the response must hold exactly one more contribution");
+  if (memcmp(challenge + vc.cs_hash, response + vr.cs_hash, 64) != 0) return reject("cs_hash changed");
+  if (memcmp(challenge + vc.contribs, response + vr.contribs, (size_t)vc.n_contrib * vc.contrib_size) != 0) return reject("earlier contributions changed");
+  Ctx c(err, errcap);
+  if ((rc = c.init(device, 1))) return rc;
+  const uint32_t elem_check = verify_elem_check(check_output), subgroup = verify_subgroup(check_output, subgroup_check_mode);
+  if (check_input != CHECK_NO) {
+    std::vector<uint8_t> scratch(p2_size(vc, cs, false, 0));
+    if ((rc = p2_transform(c, ops, cs, challenge, vc, scratch.data(), false, nullptr, nullptr, check_input, check_input == CHECK_FULL ? 1u : 0u, "challenge", err, errcap)))
+      return rc == SSO_E_INPUT ? SSO_E_VERIFY : rc;
+  }
+  if ((rc = p2_transform(c, ops, cs, response, vr, new_challenge, false, nullptr, nullptr, elem_check, subgroup, "response", err, errcap)))
+    return rc == SSO_E_INPUT ? SSO_E_VERIFY : rc;
+  P2View vn;
+  if ((rc = p2_parse(new_challenge, need, false, cs, vn, err, errcap))) return rc;
+  // untouched elements
+  std::vector<P2Item> ic = p2_items(vc), in_ = p2_items(vn);
+  for (size_t i = 0; i < ic.size(); i++) {
+    if (ic[i].kind != 0) continue;
+    const size_t usz = point_size(cs, ic[i].group, 0);
+    if (memcmp(challenge + ic[i].off, new_challenge + in_[i].off, ic[i].n * usz) != 0) return reject("an element outside h_query / l_query / delta changed");
+  }
+  // the public key of this contribution
+  const uint8_t* pk = response + vr.contribs + (size_t)vc.n_contrib * vr.contrib_size;
+  const uint8_t *delta_after = pk, *s_pair = pk + cs.g1u, *r_delta = pk + 3 * cs.g1u, *pk_transcript = pk + 3 * cs.g1u + cs.g2u;
+  {
+    uint8_t* d_pk;
+    uint32_t* d_status;
+    if ((rc = c.alloc((void**)&d_pk, vr.contrib_size))) return rc;
+    if ((rc = status_buffer(c, &d_status, err, errcap))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(d_pk, pk, vr.contrib_size, cudaMemcpyHostToDevice, c.s[0]));
+    if ((rc = ops->reencode(c, 0, GROUP_G1, d_pk, 0, 3, nullptr, 0, CHECK_FULL, 1, nullptr, d_status, err, errcap))) return rc;
+    if ((rc = ops->reencode(c, 0, GROUP_G2, d_pk + 3 * cs.g1u, 0, 1, nullptr, 0, CHECK_FULL, 1, nullptr, d_status, err, errcap))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(c.s[0]));
+    if ((rc = check_status(c, d_status, "public key", err, errcap))) return rc == SSO_E_INPUT ? SSO_E_VERIFY : rc;
+  }
+  uint8_t transcript[64];
+  p2_transcript(challenge, vc, s_pair, cs.g1u, transcript);
+  if (memcmp(transcript, pk_transcript, 64) != 0) return reject("the transcript hash of the public key does not continue the challenge");
+  if (memcmp(delta_after, new_challenge + vn.delta_g1, cs.g1u) != 0) return reject("delta_after of the public key is not the new delta_g1");
+  std::vector<uint8_t> r(cs.g2u);
+  if ((rc = p2_hash_to_g2(c, ops, cs, transcript, nullptr, r.data(), nullptr, err, errcap))) return rc;
+  std::vector<RatioCheck> checks;
+  add_check(checks, "proof of knowledge: delta", s_pair, s_pair + cs.g1u, cs.g1u, r.data(), r_delta, cs.g2u);
+  add_check(checks, "delta_g1 vs delta proof", challenge + vc.delta_g1, new_challenge + vn.delta_g1, cs.g1u, r.data(), r_delta, cs.g2u);
+  add_check(checks, "delta_g1 vs delta_g2", challenge + vc.delta_g1, new_challenge + vn.delta_g1, cs.g1u, challenge + vc.delta_g2, new_challenge + vn.delta_g2, cs.g2u);
+  // the queries: merge_pairs(before, after) against (delta_g2 after, delta_g2 before)
+  std::vector<uint8_t> pairs[2];
+  const P2Vec* qb[2] = {&vc.h_query, &vc.l_query};
+  const P2Vec* qa[2] = {&vn.h_query, &vn.l_query};
+  static const char* qn[2] = {"h_query vs delta_g2", "l_query vs delta_g2"};
+  for (int q = 0; q < 2; q++) {
+    const uint64_t n = qb[q]->n;
+    if (n == 0) continue;
+    if (n > (1ull << 24)) return reject("query longer than 2^24 elements");
+    uint8_t *d_b, *d_a, *d_pair;
+    uint32_t *d_status, *d_aff_b, *d_aff_a;
+    if ((rc = status_buffer(c, &d_status, err, errcap))) return rc;
+    if ((rc = c.alloc((void**)&d_b, n * cs.g1u))) return rc;
+    if ((rc = c.alloc((void**)&d_a, n * cs.g1u))) return rc;
+    if ((rc = c.alloc((void**)&d_aff_b, n * ops->aff_words[0] * 4))) return rc;
+    if ((rc = c.alloc((void**)&d_aff_a, n * ops->aff_words[0] * 4))) return rc;
+    if ((rc = c.alloc((void**)&d_pair, 2 * cs.g1u))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(d_b, challenge + qb[q]->off, n * cs.g1u, cudaMemcpyHostToDevice, c.s[0]));
+    CUDA_TRY(cudaMemcpyAsync(d_a, new_challenge + qa[q]->off, n * cs.g1u, cudaMemcpyHostToDevice, c.s[0]));
+    if ((rc = ops->reencode(c, 0, GROUP_G1, d_b, 0, n, nullptr, 0, CHECK_NO, 0, d_aff_b, d_status, err, errcap))) return rc;
+    if ((rc = ops->reencode(c, 0, GROUP_G1, d_a, 0, n, nullptr, 0, CHECK_NO, 0, d_aff_a, d_status, err, errcap))) return rc;
+    const uint64_t tweak[4] = {TWEAK_P2_VERIFY | (uint64_t)q, n, 0, 0};
+    if ((rc = ops->msm_pairs(c, 0, GROUP_G1, d_aff_b, d_aff_a, n, rlc_seed32, tweak, d_pair, err, errcap))) return rc;
+    pairs[q].resize(2 * cs.g1u);
+    CUDA_TRY(cudaMemcpyAsync(pairs[q].data(), d_pair, 2 * cs.g1u, cudaMemcpyDeviceToHost, c.s[0]));
+    CUDA_TRY(cudaStreamSynchronize(c.s[0]));
+    if ((rc = check_status(c, d_status, "query", err, errcap))) return rc == SSO_E_INPUT ? SSO_E_VERIFY : rc;
+    add_check(checks, qn[q], pairs[q].data(), pairs[q].data() + cs.g1u, cs.g1u, new_challenge + vn.delta_g2, challenge + vc.delta_g2, cs.g2u);
+  }
+  return run_checks(c, ops, checks, err, errcap);
+}
+
+// phase2_cli::contribute::<P>(challenge_fn, challenge_hash_fn, response_fn, response_hash_fn, check_input, batch_exp_mode, rng)
+// — reference src/bin/contribute.rs:827-838; the curve type parameter becomes `curve`, the rng its 32-byte seed
+int32_t sso_p2_contribute_file(uint32_t curve, const char* challenge_fn, const char* challenge_hash_fn, const char* response_fn,
+                               const char* response_hash_fn, uint32_t check_input, uint32_t batch_exp_mode, const uint8_t seed32[32], int device,
+                               char* err, size_t errcap) {
+  (void)batch_exp_mode;
+  if (!challenge_fn || !challenge_hash_fn || !response_fn || !response_hash_fn || !seed32) { set_err(err, errcap, "null argument"); return SSO_E_ARG; }
+  MappedFile in, out;
+  int rc;
+  if ((rc = in.open_ro(challenge_fn, err, errcap))) return rc;
+  size_t need = 0;
+  rc = sso_p2_contribute_buf(curve, in.p, in.len, nullptr, 0, &need, seed32, check_input, device, err, errcap);
+  if (rc != SSO_E_ARG || need == 0) return rc ? rc : SSO_E_ARG;
+  if ((rc = out.create(response_fn, need, true, err, errcap))) return rc;
+  if ((rc = sso_p2_contribute_buf(curve, in.p, in.len, out.p, out.len, &need, seed32, check_input, device, err, errcap))) return rc;
+  uint8_t h[64];
+  std::vector<SmallFile> small;
+  blake2b_512(in.p, in.len, h);
+  if ((rc = write_small(small, challenge_hash_fn, h, 64, err, errcap))) return rc;
+  blake2b_512(out.p, out.len, h);
+  if ((rc = write_small(small, response_hash_fn, h, 64, err, errcap))) { discard_small(small); return rc; }
+  if ((rc = out.commit(err, errcap))) { discard_small(small); return rc; }
+  return commit_small(small, err, errcap);
+}
+
+// phase2_cli::verify::<P>(challenge_fn, challenge_hash_fn, check_input, response_fn, response_hash_fn, check_output, new_challenge_fn,
+//                         new_challenge_hash_fn, subgroup_check_mode, verify_full) — reference src/bin/contribute.rs:990-1007
+int32_t sso_p2_verify_file(uint32_t curve, const char* challenge_fn, const char* challenge_hash_fn, uint32_t check_input, const char* response_fn,
+                           const char* response_hash_fn, uint32_t check_output, const char* new_challenge_fn, const char* new_challenge_hash_fn,
+                           uint32_t subgroup_check_mode, uint32_t verify_full, int device, char* err, size_t errcap) {
+  (void)verify_full;                                       // this container is always the full parameter set
+  if (!challenge_fn || !challenge_hash_fn || !response_fn || !response_hash_fn || !new_challenge_fn || !new_challenge_hash_fn) { set_err(err, errcap, "null argument"); return SSO_E_ARG; }
+  MappedFile ch, resp, out;
+  int rc;
+  if ((rc = ch.open_ro(challenge_fn, err, errcap))) return rc;
+  if ((rc = resp.open_ro(response_fn, err, errcap))) return rc;
+  size_t need = 0;
+  rc = sso_p2_verify_buf(curve, ch.p, ch.len, resp.p, resp.len, nullptr, 0, &need, check_input, check_output, subgroup_check_mode, nullptr, device, err, errcap);
+  if (rc != SSO_E_ARG || need == 0) return rc ? rc : SSO_E_ARG;
+  if ((rc = out.create(new_challenge_fn, need, true, err, errcap))) return rc;
+  if ((rc = sso_p2_verify_buf(curve, ch.p, ch.len, resp.p, resp.len, out.p, out.len, &need, check_input, check_output, subgroup_check_mode, nullptr, device, err, errcap))) return rc;
+  uint8_t h[64];
+  std::vector<SmallFile> small;
+  auto fail = [&](int32_t rc) { discard_small(small); return rc; };
+  blake2b_512(ch.p, ch.len, h);
+  if ((rc = write_small(small, challenge_hash_fn, h, 64, err, errcap))) return fail(rc);
+  blake2b_512(resp.p, resp.len, h);
+  if ((rc = write_small(small, response_hash_fn, h, 64, err, errcap))) return fail(rc);
+  blake2b_512(out.p, out.len, h);
+  if ((rc = write_small(small, new_challenge_hash_fn, h, 64, err, errcap))) return fail(rc);
+  if ((rc = out.commit(err, errcap))) return fail(rc);
+  return commit_small(small, err, errcap);
 }
 
 int32_t sso_imad_peak(int device, int variant, double* macs_per_s, char* err, size_t errcap) {

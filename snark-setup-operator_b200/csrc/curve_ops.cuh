@@ -341,24 +341,19 @@ inline int run_points_sum(Ctx& c, int si, const uint8_t* d_points, uint32_t n, u
   return SSO_OK;
 }
 
-// Window width of the Pippenger MSM.  Buckets are summed by one thread each, so the longest bucket sets the time of the
-// bucket phase.  The top window only holds sbits - (nwin - 1) * c bits: with 2 bits there it has 3 buckets of n / 4 points
-// (252-bit scalars, c = 10: measured 1.2 s instead of 7 ms on 2^16 G2 points).  Among the widths near log2(n) - 6 pick the
-// one whose longest expected bucket, max(n >> c, n >> top_bits), is shortest.
+// Window width of the Pippenger MSM.  One thread sums one bucket, so the bucket phase lasts as long as the longest bucket
+// (n >> c points when every window is full); the fold adds 2 * MSM_SEG points per thread and the window stage walks the
+// 2^c / MSM_SEG segments of a window serially.  Among the widths that divide the scalar length (no partial top window)
+// pick the one with the shortest chain of dependent point additions (mixed addition ~ 11, full addition ~ 16 multiplications).
 inline uint32_t msm_window_bits(uint64_t n, uint32_t sbits) {
-  uint32_t lg = 0;
-  while ((2ull << lg) <= n) lg++;
-  int centre = (int)lg - 6;
-  centre = centre < 4 ? 4 : (centre > 14 ? 14 : centre);
-  uint32_t best = (uint32_t)centre;
+  static const uint32_t cands[] = {4, 5, 6, 8, 10, 12};
+  uint32_t best = 4;
   uint64_t best_cost = ~0ull;
-  for (int c = centre - 2; c <= centre + 2; c++) {
-    if (c < 4 || c > 14) continue;
-    uint32_t nwin = (sbits + c - 1) / c;
-    uint32_t top = sbits - (nwin - 1) * c;                  // 1 .. c bits in the top window
-    uint64_t cost = (n >> top) > (n >> c) ? (n >> top) : (n >> c);
-    cost = cost * 8 + (uint64_t)(c > centre ? c - centre : centre - c);     // ties: stay near the centre
-    if (cost < best_cost) { best_cost = cost; best = (uint32_t)c; }
+  for (uint32_t c : cands) {
+    if (sbits % c) continue;
+    uint64_t nb = 1ull << c, seg = nb < MSM_SEG ? nb : MSM_SEG;
+    uint64_t cost = (n >> c) * 11 + 2 * seg * 16 + 3 * (nb / seg) * 16;
+    if (cost < best_cost) { best_cost = cost; best = c; }
   }
   return best;
 }

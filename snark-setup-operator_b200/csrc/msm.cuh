@@ -40,10 +40,13 @@ __device__ __forceinline__ void chacha20_block(const uint32_t* key, uint64_t cou
 
 // Width of the random-linear-combination scalars.  The reference draws full-size Fr::rand scalars from thread_rng; what
 // the same-ratio test needs from them is unpredictability — a contribution with a wrong element passes with probability
-// 2^-128 when the r_i are uniform 128-bit integers, the bound batch verification commonly works with — so this core draws
-// 128-bit scalars: half (BLS12-377), a third (BW6-761) or a sixth (MNT4/6-753) of the windows, bucket additions and
-// final doublings of an MSM with full-size scalars.  Verdicts, not scalars, are what is comparable with the reference.
-static constexpr int RLC_BITS = 128;
+// 2^-120 when the r_i are uniform 120-bit integers (batch verification commonly works with 2^-128 or less) — so this core draws
+// 120-bit scalars: half (BLS12-377), a third (BW6-761) or a sixth (MNT4/6-753) of the windows, bucket additions and
+// final doublings of an MSM with full-size scalars.  120 rather than 128 because it is divisible by every window width
+// the MSM uses (4, 5, 6, 8, 10, 12): no window is left partial — a top window holding only a few bits has few, very long
+// buckets, and one thread sums one bucket (measured: 2x on the bucket phase with 128 bits and 10-bit windows).
+// Verdicts, not scalars, are what is comparable with the reference.
+static constexpr int RLC_BITS = 120;
 static constexpr int RLC_WORDS = 4;
 
 // scalar i = first SBITS bits of the ChaCha20 keystream blocks (2i, 2i+1): uniform in [0, 2^SBITS)

@@ -1,7 +1,7 @@
 """Host-side mirror of the phase-2 path over the C ABI: the delta update of the Groth16 H / L queries
 (`phase2_cli::contribute::<P>`, reference src/bin/contribute.rs:826-839) and its same-ratio check
 (`phase2_cli::verify::<P>`, src/bin/contribute.rs:989-1008).  Only the scaling / verification cores are
-bound; the MPCParameters container (ark-groth16 ProvingKey layout) stays with the host application."""
+bound as primitives; `contribute` / `verify` are the reference-shaped calls on the parameter container (csrc/p2.cuh)."""
 from __future__ import annotations
 
 import ctypes
@@ -39,3 +39,47 @@ def points_sum(curve, group: int, points: bytes, n: int, device=0) -> bytes:
     out = ctypes.create_string_buffer(s["g1_u"] if group == 0 else s["g2_u"])
     call("sso_points_sum", curve_id(curve), group, points, n, out, len(out), device)
     return out.raw
+
+
+def contribute_buf(curve, challenge: bytes, seed32: bytes, check_input=CHECK_NO, device=0) -> bytes:
+    """phase2_cli::contribute on host buffers: challenge container (uncompressed) -> response (compressed, one more contribution)."""
+    from ._lib import SsoError, lib
+    need = ctypes.c_size_t(0)
+    err = ctypes.create_string_buffer(512)
+    rc = lib().sso_p2_contribute_buf(curve_id(curve), challenge, len(challenge), None, 0, ctypes.byref(need), seed32, check_input, device, err, len(err))
+    if rc != -1 or need.value == 0:
+        raise SsoError(rc, err.value.decode("utf-8", "replace"))
+    out = ctypes.create_string_buffer(need.value)
+    call("sso_p2_contribute_buf", curve_id(curve), challenge, len(challenge), out, len(out), ctypes.byref(need), seed32, check_input, device)
+    return out.raw
+
+
+def verify_buf(curve, challenge: bytes, response: bytes, check_input=CHECK_NO, check_output=CHECK_NO, subgroup_check_mode=0, rlc_seed32=None,
+               device=0) -> bytes:
+    """phase2_cli::verify on host buffers -> the new challenge (uncompressed); raises SsoError(code -4) on rejection."""
+    from ._lib import SsoError, lib
+    need = ctypes.c_size_t(0)
+    err = ctypes.create_string_buffer(512)
+    rc = lib().sso_p2_verify_buf(curve_id(curve), challenge, len(challenge), response, len(response), None, 0, ctypes.byref(need), check_input,
+                                 check_output, subgroup_check_mode, rlc_seed32, device, err, len(err))
+    if rc != -1 or need.value == 0:
+        raise SsoError(rc, err.value.decode("utf-8", "replace"))
+    out = ctypes.create_string_buffer(need.value)
+    call("sso_p2_verify_buf", curve_id(curve), challenge, len(challenge), response, len(response), out, len(out), ctypes.byref(need), check_input,
+         check_output, subgroup_check_mode, rlc_seed32, device)
+    return out.raw
+
+
+def contribute(curve, challenge_filename, challenge_hash_filename, response_filename, response_hash_filename, check_input, batch_exp_mode,
+               seed32: bytes, device=0):
+    """phase2_cli::contribute::<P>, argument for argument (reference src/bin/contribute.rs:827-838); P -> curve, rng -> its seed."""
+    call("sso_p2_contribute_file", curve_id(curve), challenge_filename.encode(), challenge_hash_filename.encode(), response_filename.encode(),
+         response_hash_filename.encode(), check_input, batch_exp_mode, seed32, device)
+
+
+def verify(curve, challenge_filename, challenge_hash_filename, check_input, response_filename, response_hash_filename, check_output,
+           new_challenge_filename, new_challenge_hash_filename, subgroup_check_mode, verify_full, device=0):
+    """phase2_cli::verify::<P>, argument for argument (reference src/bin/contribute.rs:990-1007)."""
+    call("sso_p2_verify_file", curve_id(curve), challenge_filename.encode(), challenge_hash_filename.encode(), check_input, response_filename.encode(),
+         response_hash_filename.encode(), check_output, new_challenge_filename.encode(), new_challenge_hash_filename.encode(), subgroup_check_mode,
+         int(verify_full), device)
