@@ -1241,6 +1241,7 @@ int32_t sso_p2_contribute_buf(uint32_t curve, const uint8_t* challenge, size_t c
   std::vector<uint8_t> delta(cs.fr);
   KeygenState keys;
   if ((rc = keygen_stage1(c, 0, ops, cs, seed32, 1, keys, delta.data(), err, errcap))) return rc;
+  if ((rc = keygen_collect_g1(c, 0, cs, keys, err, errcap))) return rc;
   int L;
   const uint32_t* pmod = fr_modulus_host(curve, L);
   std::vector<uint32_t> dw(L, 0), iw(L, 0);
@@ -1287,7 +1288,8 @@ int32_t sso_p2_verify_buf(uint32_t curve, const uint8_t* challenge, size_t chall
   if (memcmp(challenge + vc.contribs, response + vr.contribs, (size_t)vc.n_contrib * vc.contrib_size) != 0) return reject("earlier contributions changed");
   Ctx c(err, errcap);
   if ((rc = c.init(device, 1))) return rc;
-  const uint32_t elem_check = verify_elem_check(check_output), subgroup = verify_subgroup(check_output, subgroup_check_mode);
+  // Groth16 queries may hold the point at infinity (unused variables): the zero test follows check_output here
+  const uint32_t elem_check = check_output, subgroup = verify_subgroup(check_output, subgroup_check_mode);
   if (check_input != CHECK_NO) {
     std::vector<uint8_t> scratch(p2_size(vc, cs, false, 0));
     if ((rc = p2_transform(c, ops, cs, challenge, vc, scratch.data(), false, nullptr, nullptr, check_input, check_input == CHECK_FULL ? 1u : 0u, "challenge", err, errcap)))

@@ -40,6 +40,9 @@ struct CurveOps {
   // a3: key generation pieces.  keygen_g1: nscalars Fr::rand draws then, per scalar, g1_s <- G1::rand and
   // g1_s_x; d_scalars: nscalars * Fr words (canonical), d_g1: 2 * nscalars uncompressed G1 points.
   int (*keygen_g1)(Ctx& c, int si, const uint32_t* d_seed, uint32_t nscalars, uint32_t* d_scalars, uint8_t* d_g1, char* err, size_t errcap);
+  // the private scalars alone (the first nscalars Fr::rand draws): microseconds, so that the main kernels of a contribution
+  // can start while keygen_g1 (the single-thread point sampling and the proofs' G1 halves) runs beside them
+  int (*keygen_scalars)(Ctx& c, int si, const uint32_t* d_seed, uint32_t nscalars, uint32_t* d_scalars, char* err, size_t errcap);
   // hash_to_g2 for n seeds (8 words each); d_scalars / d_g2_sx may be null (verification only needs g2_s)
   int (*hash_to_g2)(Ctx& c, int si, uint32_t n, const uint32_t* d_seeds, const uint32_t* d_scalars, uint8_t* d_g2_s, uint8_t* d_g2_sx,
                     char* err, size_t errcap);
@@ -312,6 +315,17 @@ __global__ void k_keygen_g1(const uint32_t* seed, uint32_t nscalars, uint32_t* s
   uint32_t i = threadIdx.x >> 5;
   if ((threadIdx.x & 31) == 0 && i < nscalars) keygen_g1_finish<G1>(i, raw[i], scalars_out, g1_out);
 }
+template <class G1>
+__global__ void k_keygen_scalars(const uint32_t* seed, uint32_t nscalars, uint32_t* scalars_out) {
+  using Fr = typename G1::Fr;
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  ChaChaStream rng;
+  rng.init(seed);
+  for (uint32_t i = 0; i < nscalars; i++) {
+    typename Fr::T c = Fr::from_mont(fp_rand<Fr>(rng));
+    for (int w = 0; w < Fr::L; w++) scalars_out[i * Fr::L + w] = c.v[w];
+  }
+}
 template <class G2>
 __global__ void k_hash_to_g2(uint32_t n, const uint32_t* seeds, const uint32_t* scalars, uint8_t* g2_s, uint8_t* g2_sx) {
   // one point per block so that the long single-thread chains land on different SMs
@@ -468,6 +482,14 @@ template <class G1, class G2, class PP> struct CurveImpl {
     CUDA_TRY(cudaGetLastError());
     return SSO_OK;
   }
+  static int keygen_scalars(Ctx& c, int si, const uint32_t* d_seed, uint32_t nscalars, uint32_t* d_scalars, char* err, size_t errcap) {
+    if (nscalars < 1 || nscalars > 3) { set_err(err, errcap, "keygen: 1..3 scalars"); return SSO_E_ARG; }
+    c.begin(PK_OTHER, si, nscalars);
+    k_keygen_scalars<G1><<<1, 32, 0, c.s[si]>>>(d_seed, nscalars, d_scalars);
+    c.end(si);
+    CUDA_TRY(cudaGetLastError());
+    return SSO_OK;
+  }
   static int hash_to_g2(Ctx& c, int si, uint32_t n, const uint32_t* d_seeds, const uint32_t* d_scalars, uint8_t* d_g2_s, uint8_t* d_g2_sx,
                         char* err, size_t errcap) {
     if (n == 0) return SSO_OK;
@@ -490,7 +512,7 @@ template <class G1, class G2, class PP> struct CurveImpl {
     return SSO_E_ARG;
   }
   static const CurveOps* ops() {
-    static const CurveOps o = {&tau_tables, &batch_exp, &batch_exp_chunk, &reencode, &msm_pairs, &same_ratio, (uint32_t)Pairing<G1, G2, PP>::CHECK_BYTES, &keygen_g1, &hash_to_g2, (uint32_t)G1::Fr::L, &points_sum, &fill_generator, (uint32_t)G1::Fr::NBYTES, {2u * G1::F::WORDS, 2u * G2::F::WORDS}};
+    static const CurveOps o = {&tau_tables, &batch_exp, &batch_exp_chunk, &reencode, &msm_pairs, &same_ratio, (uint32_t)Pairing<G1, G2, PP>::CHECK_BYTES, &keygen_g1, &keygen_scalars, &hash_to_g2, (uint32_t)G1::Fr::L, &points_sum, &fill_generator, (uint32_t)G1::Fr::NBYTES, {2u * G1::F::WORDS, 2u * G2::F::WORDS}};
     return &o;
   }
 };

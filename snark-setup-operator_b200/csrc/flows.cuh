@@ -55,7 +55,7 @@ inline int write_new_file(const char* path, const uint8_t* data, size_t len, cha
 struct KeygenState {
   uint32_t nscalars = 0;
   uint32_t *d_scalars = nullptr, *d_seeds2 = nullptr;
-  uint8_t *d_g2s = nullptr, *d_g2sx = nullptr;
+  uint8_t *d_g2s = nullptr, *d_g2sx = nullptr, *d_g1 = nullptr;
   std::vector<uint8_t> g1, seeds2;
   std::vector<uint32_t> sc;
 };
@@ -73,14 +73,26 @@ inline int keygen_stage1(Ctx& c, int si, const CurveOps* ops, const CurveSizes& 
   if ((rc = c.alloc((void**)&k.d_g2s, nscalars * g2u, si))) return rc;
   if ((rc = c.alloc((void**)&k.d_g2sx, nscalars * g2u, si))) return rc;
   CUDA_TRY(cudaMemcpyAsync(d_seed, seed32, 32, cudaMemcpyHostToDevice, c.s[si]));
-  if ((rc = ops->keygen_g1(c, si, d_seed, nscalars, k.d_scalars, d_g1, err, errcap))) return rc;
-  k.g1.resize(2 * nscalars * g1u);
+  // the scalars first (microseconds): the caller starts its main kernels with them; the point sampling and the G1 halves of
+  // the proofs (a single-thread kernel of ~20 ms) stay enqueued on this stream and are collected by stage 2
+  uint32_t* d_sc_only;
+  if ((rc = c.alloc((void**)&d_sc_only, (size_t)nscalars * ops->fr_words * 4, si))) return rc;
+  if ((rc = ops->keygen_scalars(c, si, d_seed, nscalars, d_sc_only, err, errcap))) return rc;
   k.sc.resize((size_t)nscalars * ops->fr_words);
-  CUDA_TRY(cudaMemcpyAsync(k.g1.data(), d_g1, k.g1.size(), cudaMemcpyDeviceToHost, c.s[si]));
-  CUDA_TRY(cudaMemcpyAsync(k.sc.data(), k.d_scalars, k.sc.size() * 4, cudaMemcpyDeviceToHost, c.s[si]));
+  CUDA_TRY(cudaMemcpyAsync(k.sc.data(), d_sc_only, k.sc.size() * 4, cudaMemcpyDeviceToHost, c.s[si]));
   CUDA_TRY(cudaStreamSynchronize(c.s[si]));
   for (uint32_t i = 0; i < nscalars; i++)
     memcpy(scalars_out + (size_t)i * ops->fr_bytes, k.sc.data() + (size_t)i * ops->fr_words, ops->fr_bytes);
+  if ((rc = ops->keygen_g1(c, si, d_seed, nscalars, k.d_scalars, d_g1, err, errcap))) return rc;
+  k.d_g1 = d_g1;
+  return SSO_OK;
+}
+// waits for the G1 halves of the proofs left running by stage 1: k.g1 = g1_s(x) | g1_s_x(x) per scalar, uncompressed
+inline int keygen_collect_g1(Ctx& c, int si, const CurveSizes& cs, KeygenState& k, char* err, size_t errcap) {
+  if (!k.g1.empty()) return SSO_OK;
+  k.g1.resize(2 * k.nscalars * cs.g1u);
+  CUDA_TRY(cudaMemcpyAsync(k.g1.data(), k.d_g1, k.g1.size(), cudaMemcpyDeviceToHost, c.s[si]));
+  CUDA_TRY(cudaStreamSynchronize(c.s[si]));
   return SSO_OK;
 }
 // enqueues on stream si (the stream stage 1 ran on); pubkey_out is complete once si drained
@@ -88,6 +100,7 @@ inline int keygen_stage2(Ctx& c, int si, const CurveOps* ops, const CurveSizes& 
                          uint8_t* pubkey_out, char* err, size_t errcap) {
   int rc;
   const size_t g1u = cs.g1u, g2u = cs.g2u;
+  if ((rc = keygen_collect_g1(c, si, cs, k, err, errcap))) return rc;
   // compute_g2_s: Blake2b(personalization || digest || g1_s || g1_s_x)[..32] seeds hash_to_g2
   k.seeds2.resize((size_t)k.nscalars * 32);
   for (uint32_t i = 0; i < k.nscalars; i++) {
