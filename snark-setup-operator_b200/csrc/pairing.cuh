@@ -205,8 +205,60 @@ template <class G1, class G2, class PP> struct Pairing {
     }
   }
 
-  // ws.f <- ws.f ^ ((q^k - 1) / r): (q^(k/2) - 1) by conjugation and one inversion, then (q^(k/2) + 1) / r
+  // Frobenius on Fq[w]/(w^K - nu): coefficient l is multiplied by c^l, c = nu^((q-1)/K) (PP::frob(), BLS12 only)
+  __device__ __forceinline__ static void kfrob(int lane, FT* out, const FT* a) {
+    coop(lane, out, [&](int l) { return Fq::mul(a[l], Fq::from_const(PP::frob() + (size_t)l * Fq::L)); });
+  }
+  // out = a^x for the 64-bit curve parameter x (square-and-multiply, x sparse); out must not alias a; tmp is scratch
+  __device__ __noinline__ static void kexp_x(int lane, Ws& ws, FT* out, const FT* a) {
+    constexpr unsigned long long X = PP::X;
+    kcopy(lane, out, a);
+    bool started = false;
+    for (int i = 63; i >= 0; i--) {
+      bool bit = ((X >> i) & 1ull) != 0;
+      if (!started) { started = bit; continue; }
+      kmul(lane, ws, out, out, out);
+      if (bit) kmul(lane, ws, out, out, a);
+    }
+  }
+  // BLS12: is f^((q^12 - 1) / r) == 1 ?  Easy part g = f^((q^6 - 1)(q^2 + 1)); then, with
+  //   3 (q^4 - q^2 + 1) / r = (x - 1)^2 (x + q) (x^2 + q^2 - 1) + 3      (asserted in tools/gen_constants.py)
+  // and 3 not dividing r, the test is g^((x-1)^2 (x+q) (x^2+q^2-1)) g^3 == 1: five exponentiations by the 64-bit x (about 350
+  // Fq12 multiplications) instead of square-and-multiply over the 2009-bit (q^6 + 1) / r (about 3000).  After the easy part g
+  // is unitary: its inverse is the conjugate.  Leaves the value in ws.f.
+  __device__ __noinline__ static void final_exp_bls12(int lane, Ws& ws) {
+    kinv(lane, ws, ws.g, ws.f);                           // g = f^-1
+    kconj(lane, ws.u, ws.f, 1);                           // u = f^(q^6)
+    kmul(lane, ws, ws.g, ws.g, ws.u);                     // g = f^(q^6 - 1)
+    kfrob(lane, ws.u, ws.g);
+    kfrob(lane, ws.u, ws.u);                              // g^(q^2)
+    kmul(lane, ws, ws.g, ws.g, ws.u);                     // g = f^((q^6 - 1)(q^2 + 1))
+    FT* t0 = ws.xq; FT* t1 = ws.yq; FT* t2 = ws.ln;
+    kexp_x(lane, ws, t0, ws.g);
+    kconj(lane, ws.u, ws.g, 1);
+    kmul(lane, ws, t0, t0, ws.u);                         // t0 = g^(x - 1)
+    kexp_x(lane, ws, t1, t0);
+    kconj(lane, ws.u, t0, 1);
+    kmul(lane, ws, t1, t1, ws.u);                         // t1 = g^((x - 1)^2)
+    kexp_x(lane, ws, t2, t1);
+    kfrob(lane, ws.u, t1);
+    kmul(lane, ws, t2, t2, ws.u);                         // t2 = t1^(x + q)
+    kexp_x(lane, ws, t0, t2);
+    kexp_x(lane, ws, t1, t0);                             // t1 = t2^(x^2)
+    kfrob(lane, ws.u, t2);
+    kfrob(lane, ws.u, ws.u);                              // t2^(q^2)
+    kmul(lane, ws, t1, t1, ws.u);
+    kconj(lane, ws.u, t2, 1);
+    kmul(lane, ws, t1, t1, ws.u);                         // t1 = t2^(x^2 + q^2 - 1)
+    kmul(lane, ws, ws.f, ws.g, ws.g);
+    kmul(lane, ws, ws.f, ws.f, ws.g);                     // g^3
+    kmul(lane, ws, ws.f, ws.f, t1);
+  }
+
+  // ws.f <- ws.f ^ ((q^k - 1) / r): (q^(k/2) - 1) by conjugation and one inversion, then (q^(k/2) + 1) / r.
+  // (BLS12: a value that is 1 exactly when that power is 1 — final_exp_bls12.)
   __device__ __noinline__ static void final_exp(int lane, Ws& ws) {
+    if constexpr (PP::BLS12_FINAL_EXP) { final_exp_bls12(lane, ws); return; }
     kinv(lane, ws, ws.g, ws.f);                       // g = f^-1
     kconj(lane, ws.u, ws.f, 1);                       // u = f^(q^(k/2))
     kmul(lane, ws, ws.g, ws.g, ws.u);                     // g = f^(q^(k/2) - 1)
