@@ -932,6 +932,22 @@ int32_t sso_p1_contribute_file(const sso_p1_params_t* p, const char* challenge_f
   if (rc) return rc;
   if (!challenge_fn || !challenge_hash_fn || !response_fn || !response_hash_fn || !seed32) { set_err(err, errcap, "null argument"); return SSO_E_ARG; }
   const bool coop = is_coop(p), lead = !coop || dist_state().rank == 0;
+  if (!needs_streaming(p, L)) {
+    // chunk-sized call: page-locked staging in and out (files.cuh), outputs written whole and renamed
+    PinnedLease in(L.acc_size), out(L.contrib_size);
+    if (!in.b.p || !out.b.p) { set_err(err, errcap, "cannot allocate page-locked staging buffers"); return SSO_E_CUDA; }
+    struct stat st;
+    if (stat(response_fn, &st) == 0) { set_err(err, errcap, "cannot create %s (outputs must not exist)", response_fn); return SSO_E_IO; }
+    if ((rc = read_file_into(challenge_fn, in.b.p, L.acc_size, err, errcap))) return rc;
+    if ((rc = contribute_buf_core(p, in.b.p, L.acc_size, out.b.p, L.contrib_size, nullptr, nullptr, nullptr, nullptr, 0, seed32, check_input, device, err, errcap))) return rc;
+    uint8_t h[64];
+    blake2b_512(out.b.p, L.contrib_size, h);
+    std::vector<SmallFile> small;
+    if ((rc = write_small(small, response_fn, out.b.p, L.contrib_size, err, errcap))) return rc;
+    if ((rc = write_small(small, challenge_hash_fn, out.b.p, 64, err, errcap))) { discard_small(small); return rc; }     // response[0..64) = hash(challenge)
+    if ((rc = write_small(small, response_hash_fn, h, 64, err, errcap))) { discard_small(small); return rc; }
+    return commit_small(small, err, errcap);
+  }
   MappedFile in, out;
   std::vector<SmallFile> small;
   auto body = [&]() -> int32_t {
@@ -977,6 +993,24 @@ int32_t sso_p1_verify_chunk_file(const sso_p1_params_t* p, const char* challenge
   if (rc) return rc;
   if (!challenge_fn || !challenge_hash_fn || !response_fn || !response_hash_fn || !new_challenge_fn || !new_challenge_hash_fn) { set_err(err, errcap, "null argument"); return SSO_E_ARG; }
   const bool coop = is_coop(p), lead = !coop || dist_state().rank == 0;
+  if (!needs_streaming(p, L)) {
+    PinnedLease chb(L.acc_size), respb(L.contrib_size), outb(L.acc_size);
+    if (!chb.b.p || !respb.b.p || !outb.b.p) { set_err(err, errcap, "cannot allocate page-locked staging buffers"); return SSO_E_CUDA; }
+    struct stat st;
+    if (stat(new_challenge_fn, &st) == 0) { set_err(err, errcap, "cannot create %s (outputs must not exist)", new_challenge_fn); return SSO_E_IO; }
+    if ((rc = read_file_into(challenge_fn, chb.b.p, L.acc_size, err, errcap))) return rc;
+    if ((rc = read_file_into(response_fn, respb.b.p, L.contrib_size, err, errcap))) return rc;
+    uint8_t ch_hash[64], h[64];
+    if ((rc = verify_chunk_core(p, chb.b.p, L.acc_size, respb.b.p, L.contrib_size, outb.b.p, L.acc_size, check_input, check_output, subgroup_check_mode,
+                                ratio_check, nullptr, device, ch_hash, err, errcap))) return rc;
+    blake2b_512(outb.b.p, L.acc_size, h);
+    std::vector<SmallFile> small;
+    if ((rc = write_small(small, new_challenge_fn, outb.b.p, L.acc_size, err, errcap))) return rc;
+    if ((rc = write_small(small, challenge_hash_fn, ch_hash, 64, err, errcap))) { discard_small(small); return rc; }
+    if ((rc = write_small(small, response_hash_fn, outb.b.p, 64, err, errcap))) { discard_small(small); return rc; }        // new_challenge[0..64) = hash(response)
+    if ((rc = write_small(small, new_challenge_hash_fn, h, 64, err, errcap))) { discard_small(small); return rc; }
+    return commit_small(small, err, errcap);
+  }
   MappedFile ch, resp, out;
   std::vector<SmallFile> small;
   uint8_t ch_hash[64];

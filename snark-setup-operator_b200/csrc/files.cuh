@@ -8,6 +8,8 @@
 #include <fcntl.h>
 #include <unistd.h>
 #include <string>
+#include <mutex>
+#include <vector>
 
 namespace sso {
 
@@ -77,6 +79,56 @@ struct MappedFile {
     if (output && owner && !committed) unlink(tmp.c_str());
   }
 };
+
+// Page-locked staging buffers for the chunk-sized file calls, cached across calls (cudaHostAlloc of 31 MB costs milliseconds;
+// a pageable source makes cudaMemcpyAsync stage synchronously through the driver's own bounce buffers and serialises the
+// lanes).  A lane takes a buffer, read()s the file into it — the H2D copy then runs at link speed beside the Blake2b of the same
+// bytes —, and hands it back.
+struct PinnedBuf { uint8_t* p = nullptr; size_t cap = 0; };
+struct PinnedPool {
+  std::mutex mu;
+  std::vector<PinnedBuf> free_list;
+  static PinnedPool& get() { static PinnedPool pool; return pool; }
+  PinnedBuf take(size_t bytes) {
+    {
+      std::lock_guard<std::mutex> g(mu);
+      for (size_t i = 0; i < free_list.size(); i++)
+        if (free_list[i].cap >= bytes && free_list[i].cap <= 2 * bytes + (1u << 20)) { PinnedBuf b = free_list[i]; free_list.erase(free_list.begin() + i); return b; }
+    }
+    PinnedBuf b;
+    if (cudaHostAlloc((void**)&b.p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); b.p = nullptr; return b; }
+    b.cap = bytes;
+    return b;
+  }
+  void give(PinnedBuf b) {
+    if (!b.p) return;
+    std::lock_guard<std::mutex> g(mu);
+    if (free_list.size() >= 24) { cudaFreeHost(b.p); return; }
+    free_list.push_back(b);
+  }
+};
+struct PinnedLease {
+  PinnedBuf b;
+  explicit PinnedLease(size_t bytes) : b(PinnedPool::get().take(bytes)) {}
+  ~PinnedLease() { PinnedPool::get().give(b); }
+  PinnedLease(const PinnedLease&) = delete;
+  PinnedLease& operator=(const PinnedLease&) = delete;
+};
+inline int read_file_into(const char* path, uint8_t* dst, size_t expect, char* err, size_t errcap) {
+  int fd = ::open(path, O_RDONLY);
+  if (fd < 0) { set_err(err, errcap, "cannot open %s", path); return SSO_E_IO; }
+  struct stat st;
+  if (fstat(fd, &st) != 0) { ::close(fd); set_err(err, errcap, "cannot stat %s", path); return SSO_E_IO; }
+  if ((size_t)st.st_size != expect) { ::close(fd); set_err(err, errcap, "The size of %s should be correct: %zu != %zu", path, (size_t)st.st_size, expect); return SSO_E_ARG; }
+  size_t got = 0;
+  while (got < expect) {
+    ssize_t r = read(fd, dst + got, expect - got);
+    if (r <= 0) { ::close(fd); set_err(err, errcap, "short read on %s", path); return SSO_E_IO; }
+    got += (size_t)r;
+  }
+  ::close(fd);
+  return SSO_OK;
+}
 
 // small outputs (the 64-byte hash files): written whole under a temporary name, renamed by commit_small_files
 struct SmallFile { std::string path, tmp; };

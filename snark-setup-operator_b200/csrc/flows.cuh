@@ -228,6 +228,10 @@ inline int verify_chunk_host(Ctx& c, const CurveOps* ops, const P1Layout& L, uin
   side.err[0] = 0;
   const uint8_t* pk = response + L.off_c[5];
   const int side_device = c.dev;
+  // the response hash has its own thread: at accumulator scale (a gigabyte and more) the two sequential Blake2b passes are
+  // the critical path of the call (~1 GB/s each)
+  std::thread resp_hasher([&] { blake2b_512(response, L.contrib_size, side.resp_hash); });
+  struct Joiner0 { std::thread& t; ~Joiner0() { if (t.joinable()) t.join(); } } joiner0{resp_hasher};
   std::thread side_thread([&] {
     char* err = side.err; size_t errcap = sizeof side.err;
     side.rc = [&]() -> int {
@@ -262,7 +266,6 @@ inline int verify_chunk_host(Ctx& c, const CurveOps* ops, const P1Layout& L, uin
       if ((rc = ops->hash_to_g2(c2, si, 3, d_seeds2, nullptr, d_g2s, nullptr, err, errcap))) return rc;
       side.g2s.resize(3 * g2u);
       CUDA_TRY(cudaMemcpyAsync(side.g2s.data(), d_g2s, side.g2s.size(), cudaMemcpyDeviceToHost, c2.s[si]));
-      blake2b_512(response, L.contrib_size, side.resp_hash);
       CUDA_TRY(cudaStreamSynchronize(c2.s[si]));
       if ((rc = check_status(c2, d_status, "public key", err, errcap))) return rc == SSO_E_INPUT ? SSO_E_VERIFY : rc;
       return SSO_OK;
@@ -346,6 +349,7 @@ inline int verify_chunk_host(Ctx& c, const CurveOps* ops, const P1Layout& L, uin
   // 3. the side thread's results: hash chain (the response must continue the challenge; the new challenge's hash slot chains
   // the response), the validated public key and the g2_s points of the proofs
   side_thread.join();
+  resp_hasher.join();
   if (ch_hash_out) memcpy(ch_hash_out, side.ch_hash, 64);
   if (memcmp(side.ch_hash, response, 64) != 0) { set_err(err, errcap, "hash chain broken: response does not continue the challenge"); return SSO_E_VERIFY; }
   if (side.rc != SSO_OK) { set_err(err, errcap, "%s", side.err); return side.rc; }
