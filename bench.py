@@ -700,7 +700,7 @@ def main():
             for i in range(args.steps):
                 one_file(0)
             t_single = (time.perf_counter() - t0) / args.steps
-            lanes = 6
+            lanes = 8
             with ThreadPoolExecutor(lanes) as ex:
                 list(ex.map(one_file, range(lanes)))
                 n_calls = max(lanes, 2 * args.steps)
