@@ -99,7 +99,8 @@ struct Mnt4_753_G1 {
 struct Mnt4_753_G2 {
   static constexpr bool AFFINE_TABLE = true;
   static constexpr bool HAS_GLV = false;
-  static constexpr int ENDO_SUBGROUP_TEST = 0;
+  static constexpr int ENDO_SUBGROUP_TEST = 4;          // psi(P) = [t - 1]P  (ec.cuh::in_subgroup)
+  using Endo = ENDO_mnt4_753;
   static constexpr bool HAS_GLS4 = false;
   static constexpr uint32_t GROUP = 1;                                         // a' = (26, 0)
   SSO_GROUP_COMMON(mnt4_753_g2, Fq4x2, Fq6)
@@ -121,7 +122,8 @@ struct Mnt6_753_G1 {
 struct Mnt6_753_G2 {
   static constexpr bool AFFINE_TABLE = false;   // measured: the 72 KB Fq3 inversion tree costs more than mixed additions save
   static constexpr bool HAS_GLV = false;
-  static constexpr int ENDO_SUBGROUP_TEST = 0;
+  static constexpr int ENDO_SUBGROUP_TEST = 4;          // psi(P) = [t - 1]P  (ec.cuh::in_subgroup)
+  using Endo = ENDO_mnt6_753;
   static constexpr bool HAS_GLS4 = false;
   static constexpr uint32_t GROUP = 1;                                         // a' = (0, 0, 11) = 11 u^2, u^3 = 11
   SSO_GROUP_COMMON(mnt6_753_g2, Fq6x3, Fq4)

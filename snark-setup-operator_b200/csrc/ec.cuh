@@ -519,6 +519,22 @@ template <class Cfg> struct SW {
       t = madd(t, p);                                 // (x + 1) P
       t = add(t, res);
       return is_identity(t);
+    } else if constexpr (Cfg::ENDO_SUBGROUP_TEST == 4) {
+      // MNT4-753 / MNT6-753 G2: psi(P) = [t - 1]P with psi(X, Y) = (cx frob(X), cy frob(Y)) the Frobenius endomorphism of the
+      // twist and t the 377-bit trace — equivalent to [r]P = O (tools/gen_constants.py::mnt_endo_block), half the ladder
+      using E = typename Cfg::Endo;
+      using B = typename F::Base;
+      Jac q = mul_const(p, E::tm1(), E::TM1_WORDS);
+      FT fx, fy;
+      if constexpr (F::DEG == 2) { fx = F::conj(p.x); fy = F::conj(p.y); }
+      else {
+        typename B::T w1 = B::from_const(E::w1()), w2 = B::from_const(E::w2());
+        fx = FT{p.x.c0, B::mul(p.x.c1, w1), B::mul(p.x.c2, w2)};
+        fy = FT{p.y.c0, B::mul(p.y.c1, w1), B::mul(p.y.c2, w2)};
+      }
+      Affine t{F::mul_base(fx, B::from_const(E::cx())), F::mul_base(fy, B::from_const(E::cy())), false};
+      if (E::TM1_NEG) t.y = F::neg(t.y);                // the ladder ran over |t - 1|
+      return jac_eq_affine(q, t);
     } else {
       Jac q = mul_const(p, Cfg::order(), (Cfg::Fr::P::BITS + 31) / 32);
       return is_identity(q);

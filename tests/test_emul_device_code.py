@@ -132,10 +132,10 @@ def test_bls12_g2_four_way_decomposition_edge_scalars(emul):
         assert out.raw == want, hex(k)
 
 
-@pytest.mark.parametrize("name,gi", [("bls12_377", 0), ("bls12_377", 1), ("bw6_761", 0), ("bw6_761", 1)])
+@pytest.mark.parametrize("name,gi", [("bls12_377", 0), ("bls12_377", 1), ("bw6_761", 0), ("bw6_761", 1), ("mnt4_753", 1), ("mnt6_753", 1)])
 def test_endomorphism_subgroup_tests_agree_with_order_check(emul, name, gi):
     """Membership is tested on the device in endomorphism form where the curve has one — BLS12-377: phi(P) = [-x^2]P (G1) /
-    psi(P) = [x]P (G2); BW6-761 G1: [x + 1]P + [x^3 - x^2 + 1]phi(P) = O (G2 keeps [r]P) —; the verdict must be the
+    psi(P) = [x]P (G2); BW6-761 G1: [x + 1]P + [x^3 - x^2 + 1]phi(P) = O (G2 keeps [r]P); MNT4/6-753 G2: psi(P) = [t - 1]P —; the verdict must be the
     reference's [r]P == O on every kind of on-curve point: random curve points, pure cofactor-torsion points [r]P, points of
     tiny order, and subgroup points plus a cofactor-torsion component."""
     c = get_curve(name)
