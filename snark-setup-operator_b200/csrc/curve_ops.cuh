@@ -138,8 +138,8 @@ inline int run_batch_exp_chunk(Ctx& c, int si, const VecBatch& b1, const VecBatc
   if ((rc = c.alloc((void**)&d_jac1, (size_t)n1 * 3 * G1::F::WORDS * 4, si))) return rc;
   if ((rc = c.alloc((void**)&d_jac2, (size_t)n2 * 3 * G2::F::WORDS * 4, si))) return rc;
   uint32_t nb2 = div_up(n2, EXP_BLOCK), nb1 = div_up(n1, EXP_BLOCK);
-  constexpr size_t TREE_BYTES = 2 * EXP_BLOCK * (sizeof(typename G1::F::T) > sizeof(typename G2::F::T) ? sizeof(typename G1::F::T)
-                                                                                                        : sizeof(typename G2::F::T));
+  constexpr size_t TREE_BYTES = 16 + 2 * EXP_BLOCK * (sizeof(typename G1::F::T) > sizeof(typename G2::F::T) ? sizeof(typename G1::F::T)
+                                                                                                             : sizeof(typename G2::F::T));
   // per device and cheap: set on every call (a process-wide "done" flag would leave the other GPUs of the box unset)
   if (TREE_BYTES > 48 * 1024)
     CUDA_TRY(cudaFuncSetAttribute(k_batch_exp_chunk<G1, G2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TREE_BYTES));
@@ -147,7 +147,7 @@ inline int run_batch_exp_chunk(Ctx& c, int si, const VecBatch& b1, const VecBatc
   {
     // G2 (the longer blocks) on the call's stream, G1 beside it on the second stream; both drain before the normalisation
     const int sj = (c.s[1] && !c.aliased) ? 1 : si;
-    constexpr size_t TREE1 = 2 * EXP_BLOCK * sizeof(typename G1::F::T), TREE2 = 2 * EXP_BLOCK * sizeof(typename G2::F::T);
+    constexpr size_t TREE1 = 16 + 2 * EXP_BLOCK * sizeof(typename G1::F::T), TREE2 = 16 + 2 * EXP_BLOCK * sizeof(typename G2::F::T);
     if (TREE1 > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_batch_exp<G1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TREE1));
     if (TREE2 > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_batch_exp<G2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TREE2));
     if (sj != si && (rc = c.fork(si, sj))) return rc;
@@ -213,7 +213,7 @@ inline int run_batch_exp(Ctx& c, int si, const VecBatch& batch, uint32_t in_comp
   int rc;
   if ((rc = c.alloc((void**)&d_jac, (size_t)n * 3 * F::WORDS * 4, si))) return rc;
   constexpr bool IS_G1 = G::GROUP == 0;
-  constexpr size_t TREE_BYTES = 2 * EXP_BLOCK * sizeof(typename F::T);
+  constexpr size_t TREE_BYTES = 16 + 2 * EXP_BLOCK * sizeof(typename F::T);
   if (TREE_BYTES > 48 * 1024)
     CUDA_TRY(cudaFuncSetAttribute(k_batch_exp<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TREE_BYTES));
   c.begin(IS_G1 ? PK_BATCH_EXP_G1 : PK_BATCH_EXP_G2, si, n);

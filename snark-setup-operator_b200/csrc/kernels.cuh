@@ -142,7 +142,7 @@ template <class F> inline void block_batch_inverse_all(typename F::T* tree) {
 
 // ---------------------------------------------------------------------------------------------
 // K3 + K2: read one point, validate, multiply by its scalar, leave the Jacobian result in HBM.
-//   jac_out : total * 3 * F::WORDS words, [flat point index][X|Y|Z][limb]
+//   jac_out : total * 3 * F::WORDS words, SoA [X|Y|Z][limb][flat point index]
 //   status  : [0] first failure code, [1] element index inside its vector, [2] vector (segment) index
 // Three stages around the per-block inversion (ec.cuh "staged scalar multiplication"):
 //   exp_stage_a  per thread : decode + checks, scalar from the tau tables, recoding, Jacobian window table
@@ -160,9 +160,11 @@ template <class G> struct ExpTypes {
   using State = std::conditional_t<GLS4, typename C::template Staged4<NW>, typename C::template Staged<GLV, KW, NW>>;
 };
 
+// staged_src: the thread's serialized input point in shared memory (block_stage_input), or null = read it from global memory
 template <class G>
 __device__ __forceinline__ typename G::F::T exp_stage_a(uint32_t tid, const VecBatch& b, uint32_t in_compressed, const uint32_t* table,
-                                                        uint32_t check, uint32_t* status, typename ExpTypes<G>::State& st) {
+                                                        uint32_t check, uint32_t* status, typename ExpTypes<G>::State& st,
+                                                        const uint8_t* staged_src = nullptr) {
   using C = SW<G>;
   using F = typename G::F;
   using Fr = typename G::Fr;
@@ -173,8 +175,8 @@ __device__ __forceinline__ typename G::F::T exp_stage_a(uint32_t tid, const VecB
   if (!locate(b, tid, sidx, j)) return F::one();
   const VecSeg& sg = b.seg[sidx];
   typename C::Affine p;
-  uint32_t dst = in_compressed ? C::read_compressed(sg.in + (size_t)j * C::SIZE_C, p)
-                               : C::read_uncompressed(sg.in + (size_t)j * C::SIZE_U, p);
+  const uint8_t* src = staged_src ? staged_src : sg.in + (size_t)j * (in_compressed ? C::SIZE_C : C::SIZE_U);
+  uint32_t dst = in_compressed ? C::read_compressed(src, p) : C::read_uncompressed(src, p);
   if (dst != C::DESER_OK) { report(status, dst, j, sidx); p.inf = true; }
   if (check != CHECK_NO && dst == C::DESER_OK) {
     if (p.inf) report(status, ST_ZERO_POINT, j, sidx);
@@ -219,20 +221,56 @@ __device__ __forceinline__ void exp_stage_c(uint32_t tid, const VecBatch& b, typ
     if constexpr (ExpTypes<G>::GLV) beta = G::Glv::beta();
     r = C::staged_loop(st, beta);
   }
-  uint32_t* o = jac_out + (size_t)tid * 3 * F::WORDS;
-  F::store(o, 1, r.X);
-  F::store(o + F::WORDS, 1, r.Y);
-  F::store(o + 2 * F::WORDS, 1, r.Z);
+  // SoA: word w of coordinate c of point i sits at jac_out[(c * WORDS + w) * total + i] — a warp's stores of one word are one
+  // contiguous 128-byte line (the AoS records of round 1 made every store a separate sector)
+  const size_t total = b.total;
+  uint32_t* o = jac_out + tid;
+  F::store(o, total, r.X);
+  F::store(o + (size_t)F::WORDS * total, total, r.Y);
+  F::store(o + (size_t)2 * F::WORDS * total, total, r.Z);
 }
 
 #ifndef SSO_HOST_EMUL
-// whole block: `tree` is shared memory for 2 * EXP_BLOCK field elements
+// The serialized input points of a block (EXP_BLOCK consecutive points of one vector: a contiguous byte range of the file
+// image) are brought into shared memory with coalesced 128-bit loads by the whole block; every thread then parses its own
+// point from shared memory (point sizes of 95 / 190 / 285 bytes leave the per-thread records unaligned and 32 threads reading
+// their records byte by byte from global memory touch 32 different lines per instruction).  The buffer is the inversion tree's
+// (used later), plus 16 bytes for the alignment offset.  Returns the thread's record, or null when the block straddles two
+// vectors (at most three blocks per launch: they read global memory directly).
+template <class G>
+__device__ __forceinline__ const uint8_t* block_stage_input(uint32_t block, const VecBatch& b, uint32_t in_compressed, uint8_t* smem) {
+  using C = SW<G>;
+  const uint32_t sz = in_compressed ? C::SIZE_C : C::SIZE_U;
+  const uint32_t f0 = block * EXP_BLOCK;
+  if (f0 >= b.total) return nullptr;
+  const uint32_t f1 = f0 + EXP_BLOCK - 1 < b.total ? f0 + EXP_BLOCK - 1 : b.total - 1;
+  uint32_t s0, j0, s1, j1;
+  locate(b, f0, s0, j0);
+  locate(b, f1, s1, j1);
+  if (s0 != s1) return nullptr;                                        // uniform over the block: no divergence at the barrier below
+  const uint8_t* g0 = b.seg[s0].in + (size_t)j0 * sz;
+  const uint32_t nbytes = (j1 - j0 + 1) * sz;
+  const uint32_t head = (uint32_t)(reinterpret_cast<uintptr_t>(g0) & 15u);
+  const uint8_t* ga = g0 - head;                                       // 16-byte aligned, inside the allocation (bases are 256-byte aligned)
+  const uint32_t span = head + nbytes, full = span >> 4;
+  const uint4* gv = reinterpret_cast<const uint4*>(ga);
+  uint4* sv = reinterpret_cast<uint4*>(smem);
+  for (uint32_t k = threadIdx.x; k < full; k += EXP_BLOCK) sv[k] = gv[k];
+  for (uint32_t k = (full << 4) + threadIdx.x; k < span; k += EXP_BLOCK) smem[k] = ga[k];      // tail: never past the vector
+  __syncthreads();
+  const uint32_t tid = f0 + threadIdx.x;
+  return tid <= f1 ? smem + head + (tid - f0) * sz : nullptr;
+}
+
+// whole block: `tree` is shared memory for 2 * EXP_BLOCK field elements (+ 16 bytes, see block_stage_input)
 template <class G>
 __device__ __forceinline__ void block_batch_exp(uint32_t block, const VecBatch& b, uint32_t in_compressed, const uint32_t* table,
                                                 uint32_t check, uint32_t* jac_out, uint32_t* status, typename G::F::T* tree) {
   typename ExpTypes<G>::State st;
   uint32_t tid = block * EXP_BLOCK + threadIdx.x;
-  typename G::F::T leaf = exp_stage_a<G>(tid, b, in_compressed, table, check, status, st);
+  const uint8_t* staged = block_stage_input<G>(block, b, in_compressed, reinterpret_cast<uint8_t*>(tree));
+  typename G::F::T leaf = exp_stage_a<G>(tid, b, in_compressed, table, check, status, st, staged);
+  __syncthreads();                                                    // the staged bytes are dead: the tree may take the buffer
   if constexpr (G::AFFINE_TABLE) {
     tree[EXP_BLOCK + threadIdx.x] = leaf;
     block_batch_inverse<typename G::F>(tree, threadIdx.x);
@@ -266,21 +304,28 @@ __device__ __forceinline__ void body_normalize_write(uint32_t tid, const VecBatc
   using C = SW<G>;
   using F = typename G::F;
   using FT = typename F::T;
-  uint32_t n = b.total;
-  uint32_t first = tid * NORM_BATCH;
-  if (first >= n) return;
-  uint32_t cnt = n - first < (uint32_t)NORM_BATCH ? n - first : (uint32_t)NORM_BATCH;
+  const uint32_t n = b.total;
+  // thread tid takes the points tid, tid + T, tid + 2T, ... (T = number of threads with work): with the SoA layout the
+  // threads of a warp load consecutive words
+  const uint32_t T = (n + NORM_BATCH - 1) / NORM_BATCH;
+  if (tid >= T) return;
+  const size_t total = n;
+  auto zptr = [&](uint32_t idx) { return jac + (size_t)2 * F::WORDS * total + idx; };
+  uint32_t cnt = 0;
   FT prefix[NORM_BATCH];
   FT acc = F::one();
-  for (uint32_t i = 0; i < cnt; i++) {
-    FT z = F::load(jac + ((size_t)(first + i) * 3 + 2) * F::WORDS, 1);
+  for (uint32_t i = 0; i < (uint32_t)NORM_BATCH; i++) {
+    uint32_t idx = tid + i * T;
+    if (idx >= n) break;
+    cnt = i + 1;
+    FT z = F::load(zptr(idx), total);
     prefix[i] = acc;
     if (!F::is_zero(z)) acc = F::mul(acc, z);
   }
   FT inv = F::inv(acc);
   for (int i = (int)cnt - 1; i >= 0; i--) {
-    const uint32_t* pj = jac + (size_t)(first + i) * 3 * F::WORDS;
-    typename C::Jac p{F::load(pj, 1), F::load(pj + F::WORDS, 1), F::load(pj + 2 * F::WORDS, 1)};
+    uint32_t idx = tid + (uint32_t)i * T;
+    typename C::Jac p{F::load(jac + idx, total), F::load(jac + (size_t)F::WORDS * total + idx, total), F::load(zptr(idx), total)};
     typename C::Affine a;
     if (F::is_zero(p.Z)) {
       a.inf = true; a.x = F::zero(); a.y = F::zero();
@@ -290,7 +335,7 @@ __device__ __forceinline__ void body_normalize_write(uint32_t tid, const VecBatc
       a = C::to_affine_with(p, zinv);
     }
     uint32_t sidx, j;
-    locate(b, first + i, sidx, j);
+    locate(b, idx, sidx, j);
     uint8_t* out = b.seg[sidx].out;
     if (out_compressed) C::write_compressed(out + (size_t)j * C::SIZE_C, a);
     else C::write_uncompressed(out + (size_t)j * C::SIZE_U, a);
