@@ -187,6 +187,9 @@ def cpu_reference_run(curve: str, power: int, chunk_log: int, steps: int, warmup
             times.append(t)
     mean = sum(times) / len(times)
     return {"value": n / mean, "unit": "points/s", "cores": threads, "kind": "port",
+            "caveats": "a C++ restatement of the reference algorithm, not the Rust binary (no toolchain in the image): unsigned __int128 limbs "
+                       "without the x86 assembly of ark-ff-asm, per-point double-and-add without the BatchInversion mode of batch_exp; "
+                       "a stated baseline, not the target",
             "sample": "%s chunk of 2^%d elements per vector (%d points) per step, %d steps; C++ restatement of "
                       "per-index pow + double-and-add + batch normalisation (oracle/c/oracle.cpp), std::thread over points"
                       % (curve, clog, n, len(times))}, mean

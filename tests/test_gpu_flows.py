@@ -152,6 +152,44 @@ def test_file_entry_points(tmp_path):
     assert e.value.code == -1 and "size" in e.value.message
 
 
+def test_failed_file_call_leaves_nothing_behind(tmp_path):
+    """no half-written outputs — a call that fails after it created its outputs (here: an off-subgroup point in
+    the challenge under CheckForCorrectness::Full, a response that fails verification) removes them, also the hash files."""
+    from oracle.curves import _some_point
+    name = "bls12_377"
+    o = Phase1Params.new_chunk(name, 1, 4, 3, 4)
+    p = sso.Phase1Parameters.new_chunk(name, 1, 4, 3, 4)
+    c = o.curve
+    ch = bytearray(synth.synthetic_challenge(o))
+    ou = o.offsets(False)
+    ch[ou[0] + 96: ou[0] + 192] = ser.point_to_bytes(c.g1, _some_point(c.g1, 11), False)
+    f = {k: str(tmp_path / k) for k in ("challenge", "challenge.hash", "response", "response.hash", "new", "new.hash", "c.vhash", "r.vhash")}
+    open(f["challenge"], "wb").write(ch)
+    with pytest.raises(sso.SsoError):
+        sso.contribute(f["challenge"], f["challenge.hash"], f["response"], f["response.hash"], sso.CHECK_FULL, 0, p, synth.SEED_CONTRIB)
+    assert sorted(os.listdir(tmp_path)) == ["challenge"]
+    # the same for a Full-mode (streamed, memory-mapped) call and for a rejected verification
+    pf = sso.Phase1Parameters.new_full(name, 3, 4)
+    of = Phase1Params.new_full(name, 3, 4)
+    chf = bytearray(phase1.new_challenge(of))
+    ouf = of.offsets(False)
+    chf[ouf[2] + 96: ouf[2] + 192] = ser.point_to_bytes(c.g1, _some_point(c.g1, 11), False)
+    open(f["challenge"], "wb").write(chf)
+    with pytest.raises(sso.SsoError):
+        sso.contribute(f["challenge"], f["challenge.hash"], f["response"], f["response.hash"], sso.CHECK_FULL, 0, pf, synth.SEED_CONTRIB)
+    assert sorted(os.listdir(tmp_path)) == ["challenge"]
+    open(f["challenge"], "wb").write(phase1.new_challenge(of))
+    sso.contribute(f["challenge"], f["challenge.hash"], f["response"], f["response.hash"], sso.CHECK_NONZERO, 0, pf, synth.SEED_CONTRIB)
+    resp = bytearray(open(f["response"], "rb").read())
+    resp[-1] ^= 1                                               # public key tampered: verification fails at the end of the call
+    open(f["response"], "wb").write(resp)
+    with pytest.raises(sso.SsoError) as e:
+        sso.transform_pok_and_correctness(f["challenge"], f["c.vhash"], sso.CHECK_NO, f["response"], f["r.vhash"], sso.CHECK_NONZERO, f["new"],
+                                          f["new.hash"], 0, True, pf)
+    assert e.value.code in (-3, -4)
+    assert sorted(os.listdir(tmp_path)) == ["challenge", "challenge.hash", "response", "response.hash"]
+
+
 @pytest.mark.parametrize("name", ["mnt4_753", "mnt6_753", "bls12_377"])
 def test_phase2_delta_update_and_check(name):
     """Config 4: H / L query scaling by delta^-1 is bit-exact with the oracle and passes the same-ratio check

@@ -104,3 +104,38 @@ def test_phase2_file_calls(tmp_path):
     with pytest.raises(sso.SsoError) as e:                      # outputs must not exist
         p2.contribute(name, f["challenge"], str(tmp_path / "x.hash"), f["response"], str(tmp_path / "y.hash"), sso.CHECK_NO, 0, SEED1)
     assert e.value.code == -5
+
+
+def test_config4_query_of_2_19_points_spot_checked():
+    """BASELINE config 4 at a Nimiq circuit size (2^19 G1 points, reference e2e/nimiq_e2e.sh:61-71): the delta^-1 scaling of the
+    whole vector on the GPU, sampled elements recomputed one by one by the C++ oracle leg (plain double-and-add), and the
+    same-ratio check of the whole vector against (delta_g2_after, delta_g2_before)."""
+    from oracle import cport, synth
+    name = "mnt4_753"
+    c = get_curve(name)
+    n = 1 << 19
+    es = sso.phase1.curve_sizes(name)
+    usz = es["g1_u"]
+    s = synth.scalars_from_seed(c, synth.SEED_PREV)[0]
+    delta = synth.scalars_from_seed(c, synth.SEED_CONTRIB, 4)[3]
+    dinv = pow(delta, -1, c.Fr.p)
+    gen = ser.point_to_bytes(c.g1, c.g1.gen, False)
+    d_gen = torch.frombuffer(bytearray(gen * n), dtype=torch.uint8).cuda()
+    d_c = torch.empty(n * es["g1_c"], dtype=torch.uint8, device="cuda")
+    sso.batch_exp(name, 0, d_gen, n, 1, s, None, d_c)                       # h_i = s^(1+i) G
+    d_u = torch.empty(n * usz, dtype=torch.uint8, device="cuda")
+    sso.reencode(name, 0, d_c, n, d_u, check=sso.CHECK_NO, subgroup_check=False)
+    before = d_u.cpu().numpy().tobytes()
+    after = p2.scale_queries(name, before, n, dinv)
+    rnd = random.Random(3)
+    for j in [0, 1, n - 1] + [rnd.randrange(n) for _ in range(5)]:
+        want = cport.batch_exp(c, 0, before[j * usz:(j + 1) * usz], 1, 0, 1, dinv, mode=1, out_compressed=False, threads=1)
+        assert after[j * usz:(j + 1) * usz] == want, j
+    d2b = c.g2.mul(c.g2.gen, 31337)
+    d2a = c.g2.mul(d2b, delta)
+    p2.verify_queries(name, before, after, n, ser.point_to_bytes(c.g2, d2b, False), ser.point_to_bytes(c.g2, d2a, False))
+    bad = bytearray(after)
+    bad[12345 * usz:12346 * usz] = before[12345 * usz:12346 * usz]
+    with pytest.raises(sso.SsoError) as e:
+        p2.verify_queries(name, before, bytes(bad), n, ser.point_to_bytes(c.g2, d2b, False), ser.point_to_bytes(c.g2, d2a, False))
+    assert e.value.code == -4
