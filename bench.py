@@ -76,6 +76,7 @@ def declared_work_per_point(curve: str, group: int):
       window loop, signed 4-bit digits               4 (NW - 1) dbl + additions on 15/16 of the windows:
          plain ladder (MNT4/6)   NW = ceil((bits+2)/4)   one addition per window
          GLV (BLS12-377 G1, BW6) NW = ceil((KBITS+2)/4)  two additions per window + one multiplication by beta (deg Fq-muls)
+         2-way psi (MNT4/6 G2)   NW = 95                 two additions per window + the psi-image of the table entry
          4-way psi decomposition (BLS12-377 G2)  NW = 17  four additions per window + (4 + 2 + 2) Fq-muls for psi, psi^2, psi^3
       additions are mixed (madd) with the affine table, full Jacobian additions otherwise.
     Base-field cost of an extension operation: Fq2 mul = 3 M, Fq2 sqr = 2 M (complex squaring); Fq3 mul = sqr = 6 M;
@@ -104,6 +105,11 @@ def declared_work_per_point(curve: str, group: int):
     elif curve in GLV_KBITS:
         nw = (GLV_KBITS[curve] + 2 + 3) // 4
         terms += [(4 * (nw - 1), dbl), (2 * nw * 15.0 / 16.0, step), (nw * (15.0 / 16.0) * deg, base)]
+    elif curve in ("mnt4_753", "mnt6_753") and group == 1:
+        # 2-way psi decomposition (k = k0 + k1 |t - 1|, 378-bit halves): two additions per window, the second on the psi-image of
+        # the table entry: Fq2 (affine table) 2 mul_base = 4 Fq-muls; Fq3 (Jacobian table) Frobenius of X, Y, Z (2 each) + 2 mul_base (3 each) = 12
+        nw = (378 + 2 + 3) // 4
+        terms += [(4 * (nw - 1), dbl), (2 * nw * 15.0 / 16.0, step), (nw * (15.0 / 16.0) * (4 if deg == 2 else 12), base)]
     else:
         nw = (bits + 2 + 3) // 4
         terms += [(4 * (nw - 1), dbl), (nw * 15.0 / 16.0, step)]

@@ -40,6 +40,7 @@ struct Bls12_377_G1 {
   using Glv = GLV_bls12_377_g1;
   static constexpr int ENDO_SUBGROUP_TEST = 1;          // phi(P) = [-x^2]P  (ec.cuh::in_subgroup)
   static constexpr bool HAS_GLS4 = false;
+  static constexpr bool HAS_GLS2 = false;
   using Endo = ENDO_bls12_377;
   static constexpr uint32_t GROUP = 0;
   SSO_GROUP_COMMON(bls12_377_g1, Fq377, Fr253)
@@ -53,6 +54,7 @@ struct Bls12_377_G2 {
   using Glv = GLV_bls12_377_g2;
   static constexpr int ENDO_SUBGROUP_TEST = 2;          // psi(P) = [x]P
   static constexpr bool HAS_GLS4 = true;                // batch_exp: k = k0 + k1 x + k2 x^2 + k3 x^3 with psi (ec.cuh)
+  static constexpr bool HAS_GLS2 = false;
   using Endo = ENDO_bls12_377;
   static constexpr uint32_t GROUP = 1;
   SSO_GROUP_COMMON(bls12_377_g2, Fq377x2, Fr253)
@@ -67,6 +69,7 @@ struct Bw6_761_G1 {
   static constexpr int ENDO_SUBGROUP_TEST = 3;          // [x + 1]P + [x^3 - x^2 + 1]phi(P) = O  (ec.cuh::in_subgroup)
   using Endo = ENDO_bw6_761;
   static constexpr bool HAS_GLS4 = false;
+  static constexpr bool HAS_GLS2 = false;
   static constexpr uint32_t GROUP = 0;
   SSO_GROUP_COMMON(bw6_761_g1, Fq761, Fq377)
   static constexpr bool A_IS_ZERO = true;
@@ -79,6 +82,7 @@ struct Bw6_761_G2 {
   using Glv = GLV_bw6_761_g2;
   static constexpr int ENDO_SUBGROUP_TEST = 0;
   static constexpr bool HAS_GLS4 = false;
+  static constexpr bool HAS_GLS2 = false;
   static constexpr uint32_t GROUP = 1;
   SSO_GROUP_COMMON(bw6_761_g2, Fq761, Fq377)
   static constexpr bool A_IS_ZERO = true;
@@ -90,6 +94,7 @@ struct Mnt4_753_G1 {
   static constexpr bool HAS_GLV = false;
   static constexpr int ENDO_SUBGROUP_TEST = 0;
   static constexpr bool HAS_GLS4 = false;
+  static constexpr bool HAS_GLS2 = false;
   static constexpr uint32_t GROUP = 0;                                         // a = 2
   SSO_GROUP_COMMON(mnt4_753_g1, Fq4, Fq6)
   static constexpr bool A_IS_ZERO = false;
@@ -102,6 +107,7 @@ struct Mnt4_753_G2 {
   static constexpr int ENDO_SUBGROUP_TEST = 4;          // psi(P) = [t - 1]P  (ec.cuh::in_subgroup)
   using Endo = ENDO_mnt4_753;
   static constexpr bool HAS_GLS4 = false;
+  static constexpr bool HAS_GLS2 = true;                 // batch_exp: k = k0 + k1 |t - 1| with the Frobenius endomorphism psi (ec.cuh)
   static constexpr uint32_t GROUP = 1;                                         // a' = (26, 0)
   SSO_GROUP_COMMON(mnt4_753_g2, Fq4x2, Fq6)
   static constexpr bool A_IS_ZERO = false;
@@ -113,6 +119,7 @@ struct Mnt6_753_G1 {
   static constexpr bool HAS_GLV = false;
   static constexpr int ENDO_SUBGROUP_TEST = 0;
   static constexpr bool HAS_GLS4 = false;
+  static constexpr bool HAS_GLS2 = false;
   static constexpr uint32_t GROUP = 0;                                         // a = 11
   SSO_GROUP_COMMON(mnt6_753_g1, Fq6, Fq4)
   static constexpr bool A_IS_ZERO = false;
@@ -125,6 +132,7 @@ struct Mnt6_753_G2 {
   static constexpr int ENDO_SUBGROUP_TEST = 4;          // psi(P) = [t - 1]P  (ec.cuh::in_subgroup)
   using Endo = ENDO_mnt6_753;
   static constexpr bool HAS_GLS4 = false;
+  static constexpr bool HAS_GLS2 = true;                 // batch_exp: k = k0 + k1 |t - 1| with the Frobenius endomorphism psi (ec.cuh)
   static constexpr uint32_t GROUP = 1;                                         // a' = (0, 0, 11) = 11 u^2, u^3 = 11
   SSO_GROUP_COMMON(mnt6_753_g2, Fq6x3, Fq4)
   static constexpr bool A_IS_ZERO = false;

@@ -356,6 +356,58 @@ template <class Cfg> struct SW {
     if (flip) q.Y = F::neg(q.Y);
     return add(acc, q);
   }
+  // ---- 2-way decomposition on the G2 groups of the MNT curves: psi = untwist^-1 . Frobenius . untwist acts on G2 as multiplication
+  // by t - 1 (t the 377-bit trace), so with mu = |t - 1| and k = k0 + k1 mu:  [k]P = [k0]P +- [k1]psi(P)  — half the doublings of
+  // the 753-bit ladder (constants and the numerical checks: tools/gen_constants.py::mnt_endo_block)
+  __device__ __forceinline__ static FT endo_frob(const FT& a) {
+    using E = typename Cfg::Endo;
+    using B = typename F::Base;
+    if constexpr (F::DEG == 2) { return F::conj(a); }
+    else { return FT{a.c0, B::mul(a.c1, B::from_const(E::w1())), B::mul(a.c2, B::from_const(E::w2()))}; }
+  }
+  template <int KL>
+  __device__ __forceinline__ static void gls2_split(const uint32_t* k, uint32_t* k0, uint32_t* k1) {
+    using E = typename Cfg::Endo;
+    constexpr int KW = E::GLS_KW, GW = E::GLS_GW;
+    static_assert(KL == 24 && KW <= 12, "768-bit Barrett shift");
+    uint32_t prod[KL + GW];
+    mul_low<KL, GW, KL + GW>(k, E::recip(), prod);
+    uint32_t q[KW + 1];
+#pragma unroll
+    for (int i = 0; i <= KW; i++) q[i] = KL + i < KL + GW ? prod[KL + i] : 0u;               // floor(k recip / 2^768)
+    uint32_t t[KL], rem[KL];
+    mul_low<KW, KW, KL>(q, E::tm1(), t);
+    limbs_sub<KL>(rem, k, t);                                                             // k - q mu in [0, 3 mu)
+    uint32_t mu[KL], one[KW + 1];
+#pragma unroll
+    for (int i = 0; i < KL; i++) mu[i] = i < KW ? E::tm1()[i] : 0u;
+#pragma unroll
+    for (int i = 0; i <= KW; i++) one[i] = i == 0 ? 1u : 0u;
+    for (int it = 0; it < 2; it++) {
+      uint32_t d[KL];
+      if (limbs_sub<KL>(d, rem, mu) == 0) {                                               // rem >= mu
+#pragma unroll
+        for (int i = 0; i < KL; i++) rem[i] = d[i];
+        limbs_add<KW + 1>(q, q, one);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < KW; i++) { k0[i] = rem[i]; k1[i] = q[i]; }
+  }
+  // acc + sign * psi(table entry)
+  template <class ST>
+  __device__ __forceinline__ static Jac staged_add_psi(const ST& st, const Jac& acc, int dgt, bool neg) {
+    using E = typename Cfg::Endo;
+    using B = typename F::Base;
+    int idx = (dgt < 0 ? -dgt : dgt) - 1;
+    bool flip = (dgt < 0) != neg;
+    FT x = F::mul_base(endo_frob(st.tab[idx].X), B::from_const(E::cx()));
+    FT y = F::mul_base(endo_frob(st.tab[idx].Y), B::from_const(E::cy()));
+    if (flip) y = F::neg(y);
+    if (st.affine) return madd(acc, Affine{x, y, false});
+    return add(acc, Jac{x, y, endo_frob(st.tab[idx].Z)});
+  }
+
   template <class ST>
   __device__ __forceinline__ static Jac staged_loop(const ST& st, const uint32_t* beta) {
     Jac acc = identity();
@@ -368,7 +420,10 @@ template <class Cfg> struct SW {
       }
       int d1 = digit(st.kb1, w);
       if (d1 != 0) acc = staged_add(st, acc, d1, st.neg1, nullptr);
-      if (beta) {
+      if constexpr (Cfg::HAS_GLS2) {
+        int d2 = digit(st.kb2, w);
+        if (d2 != 0) acc = staged_add_psi(st, acc, d2, st.neg2);
+      } else if (beta) {
         int d2 = digit(st.kb2, w);
         if (d2 != 0) acc = staged_add(st, acc, d2, st.neg2, beta);
       }
@@ -525,13 +580,7 @@ template <class Cfg> struct SW {
       using E = typename Cfg::Endo;
       using B = typename F::Base;
       Jac q = mul_const(p, E::tm1(), E::TM1_WORDS);
-      FT fx, fy;
-      if constexpr (F::DEG == 2) { fx = F::conj(p.x); fy = F::conj(p.y); }
-      else {
-        typename B::T w1 = B::from_const(E::w1()), w2 = B::from_const(E::w2());
-        fx = FT{p.x.c0, B::mul(p.x.c1, w1), B::mul(p.x.c2, w2)};
-        fy = FT{p.y.c0, B::mul(p.y.c1, w1), B::mul(p.y.c2, w2)};
-      }
+      FT fx = endo_frob(p.x), fy = endo_frob(p.y);
       Affine t{F::mul_base(fx, B::from_const(E::cx())), F::mul_base(fy, B::from_const(E::cy())), false};
       if (E::TM1_NEG) t.y = F::neg(t.y);                // the ladder ran over |t - 1|
       return jac_eq_affine(q, t);

@@ -153,11 +153,12 @@ template <class G> struct ExpTypes {
   using C = SW<G>;
   using Fr = typename G::Fr;
   static constexpr bool GLS4 = G::HAS_GLS4;            // 4-way psi decomposition (takes precedence over 2-way GLV)
+  static constexpr bool GLS2 = G::HAS_GLS2;            // 2-way psi decomposition (MNT G2)
   static constexpr bool GLV = G::HAS_GLV && !GLS4;
-  static constexpr int KBITS = [] { if constexpr (G::HAS_GLS4) return 64; else if constexpr (G::HAS_GLV) return (int)G::Glv::KBITS; else return (int)G::Fr::P::BITS; }();
-  static constexpr int KW = [] { if constexpr (G::HAS_GLS4) return 2; else if constexpr (G::HAS_GLV) return (int)G::Glv::KW; else return (int)G::Fr::L; }();
+  static constexpr int KBITS = [] { if constexpr (G::HAS_GLS4) return 64; else if constexpr (G::HAS_GLS2) return (int)G::Endo::GLS_KBITS; else if constexpr (G::HAS_GLV) return (int)G::Glv::KBITS; else return (int)G::Fr::P::BITS; }();
+  static constexpr int KW = [] { if constexpr (G::HAS_GLS4) return 2; else if constexpr (G::HAS_GLS2) return (int)G::Endo::GLS_KW; else if constexpr (G::HAS_GLV) return (int)G::Glv::KW; else return (int)G::Fr::L; }();
   static constexpr int NW = (KBITS + 2 + 3) / 4;
-  using State = std::conditional_t<GLS4, typename C::template Staged4<NW>, typename C::template Staged<GLV, KW, NW>>;
+  using State = std::conditional_t<GLS4, typename C::template Staged4<NW>, typename C::template Staged<GLV || GLS2, KW, NW>>;
 };
 
 // staged_src: the thread's serialized input point in shared memory (block_stage_input), or null = read it from global memory
@@ -195,6 +196,13 @@ __device__ __forceinline__ typename G::F::T exp_stage_a(uint32_t tid, const VecB
     C::template gls4_split<Fr::L>(k, kd);
 #pragma unroll
     for (int d = 0; d < 4; d++) C::template bias_scalar<2, ET::NW>(kd[d], st.kb[d]);
+  } else if constexpr (ET::GLS2) {
+    uint32_t k0[ET::KW], k1[ET::KW];
+    C::template gls2_split<Fr::L>(k, k0, k1);
+    st.neg1 = false;
+    st.neg2 = G::Endo::TM1_NEG;                          // psi(P) = [t - 1]P = -[mu]P when the trace is negative (MNT4-753)
+    C::template bias_scalar<ET::KW, ET::NW>(k0, st.kb1);
+    C::template bias_scalar<ET::KW, ET::NW>(k1, st.kb2);
   } else if constexpr (ET::GLV) {
     uint32_t k1[ET::KW], k2[ET::KW];
     C::template glv_split<typename G::Glv, Fr::L>(k, k1, k2, st.neg1, st.neg2);

@@ -132,6 +132,31 @@ def test_bls12_g2_four_way_decomposition_edge_scalars(emul):
         assert out.raw == want, hex(k)
 
 
+@pytest.mark.parametrize("name", ["mnt4_753", "mnt6_753"])
+def test_mnt_g2_two_way_decomposition_edge_scalars(emul, name):
+    """The G2 ladders of the MNT curves split the scalar as k = k0 + k1 mu (mu = |t - 1|, the eigenvalue of the Frobenius
+    endomorphism psi up to sign; Barrett quotient with corrections) and add psi-images of the table entries: scalars on the
+    digit and quotient boundaries, and a base point of the full group order, must still match [k]P."""
+    c = get_curve(name)
+    G = c.g2
+    r = c.Fr.p
+    mu = abs(c.Fq.p - r)                                    # |t - 1| = |q - r|
+    Lr = (c.Fr.bits + 31) // 32
+    pts = [G.mul(G.gen, 0x1234567), G.mul(G.gen, r - 5)]
+    buf = ser.points_to_bytes(G, pts, False)
+    st = (ctypes.c_uint32 * 3)()
+    ks = [1, 2, 7, 8, 9, 15, 16, mu - 1, mu, mu + 1, 2 * mu - 1, 2 * mu, 3 * mu + 5, (r // mu) * mu, (r // mu) * mu - 1, r - 1, r - 2, r // 2,
+          0x8888888888888888 * mu + 0x7777777777777777, (mu - 1) + (mu - 1) * mu if (mu - 1) + (mu - 1) * mu < r else r - 3]
+    for k in ks:
+        k %= r
+        if k == 0:
+            continue
+        want = ser.points_to_bytes(G, [G.mul(P, k) for P in pts], False)
+        out = ctypes.create_string_buffer(len(want))
+        assert emul.emul_batch_exp(c.cid, 1, buf, 0, 2, words(1, Lr), words(k, Lr), ctypes.c_uint64(0), 1, 0, out, 0, st) == 0
+        assert out.raw == want, hex(k)
+
+
 @pytest.mark.parametrize("name,gi", [("bls12_377", 0), ("bls12_377", 1), ("bw6_761", 0), ("bw6_761", 1), ("mnt4_753", 1), ("mnt6_753", 1)])
 def test_endomorphism_subgroup_tests_agree_with_order_check(emul, name, gi):
     """Membership is tested on the device in endomorphism form where the curve has one — BLS12-377: phi(P) = [-x^2]P (G1) /
