@@ -125,6 +125,13 @@ __global__ void __launch_bounds__(128) k_normalize_chunk(const __grid_constant__
   else body_normalize_write<G1>((blockIdx.x - nb2) * blockDim.x + threadIdx.x, b1, jac1, out_compressed);
 }
 
+// The extension-field groups run their batch_exp bodies warp-cooperatively (coop.cuh: one coefficient per lane) on uncompressed
+// input; SSO_COOP_G2=0 in the environment selects the one-thread-per-element bodies (A/B measurements, tools/).
+inline bool coop_g2_enabled() {
+  static const bool on = [] { const char* e = getenv("SSO_COOP_G2"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 template <class G1, class G2>
 inline int run_batch_exp_chunk(Ctx& c, int si, const VecBatch& b1, const VecBatch& b2, uint32_t in_compressed, const uint32_t* d_table,
                                uint32_t out_compressed, uint32_t check, uint32_t* d_status, char* err, size_t errcap) {
@@ -164,9 +171,26 @@ inline int run_batch_exp_chunk(Ctx& c, int si, const VecBatch& b1, const VecBatc
     if (sj != si && (rc = c.fork(sj, si))) return rc;
   }
 #else
-  c.begin(PK_BATCH_EXP_CHUNK, si, n1 + n2);
-  k_batch_exp_chunk<G1, G2><<<nb1 + nb2, EXP_BLOCK, TREE_BYTES, st>>>(b1, b2, nb2, in_compressed, d_table, check, d_jac1, d_jac2, d_status);
-  c.end(si);
+  using G2C = typename CoopOf<G2>::type;
+  bool coop = false;
+  if constexpr (!std::is_void<G2C>::value) {
+    if (!in_compressed && coop_g2_enabled()) {
+      coop = true;
+      constexpr size_t SM1 = 16 + 2 * EXP_BLOCK * sizeof(typename G1::F::T);
+      constexpr size_t SMEM = SM1 > ExpBlock<G2C>::SMEM ? SM1 : ExpBlock<G2C>::SMEM;
+      if (SMEM > 48 * 1024)
+        CUDA_TRY(cudaFuncSetAttribute(k_batch_exp_chunk<G1, G2C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+      nb2 = div_up(n2, ExpBlock<G2C>::PPB);
+      c.begin(PK_BATCH_EXP_CHUNK, si, n1 + n2);
+      k_batch_exp_chunk<G1, G2C><<<nb1 + nb2, EXP_BLOCK, SMEM, st>>>(b1, b2, nb2, 0, d_table, check, d_jac1, d_jac2, d_status);
+      c.end(si);
+    }
+  }
+  if (!coop) {
+    c.begin(PK_BATCH_EXP_CHUNK, si, n1 + n2);
+    k_batch_exp_chunk<G1, G2><<<nb1 + nb2, EXP_BLOCK, TREE_BYTES, st>>>(b1, b2, nb2, in_compressed, d_table, check, d_jac1, d_jac2, d_status);
+    c.end(si);
+  }
 #endif
   uint32_t mb2 = div_up(div_up(n2, NORM_BATCH), 128), mb1 = div_up(div_up(n1, NORM_BATCH), 128);
   c.begin(PK_NORMALIZE_CHUNK, si, n1 + n2);
@@ -216,9 +240,23 @@ inline int run_batch_exp(Ctx& c, int si, const VecBatch& batch, uint32_t in_comp
   constexpr size_t TREE_BYTES = 16 + 2 * EXP_BLOCK * sizeof(typename F::T);
   if (TREE_BYTES > 48 * 1024)
     CUDA_TRY(cudaFuncSetAttribute(k_batch_exp<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TREE_BYTES));
-  c.begin(IS_G1 ? PK_BATCH_EXP_G1 : PK_BATCH_EXP_G2, si, n);
-  k_batch_exp<G><<<div_up(n, EXP_BLOCK), EXP_BLOCK, TREE_BYTES, st>>>(batch, in_compressed, d_table, check, d_jac, d_status);
-  c.end(si);
+  using GC = typename CoopOf<G>::type;
+  bool coop = false;
+  if constexpr (!std::is_void<GC>::value) {
+    if (!in_compressed && coop_g2_enabled()) {
+      coop = true;
+      if (ExpBlock<GC>::SMEM > 48 * 1024)
+        CUDA_TRY(cudaFuncSetAttribute(k_batch_exp<GC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ExpBlock<GC>::SMEM));
+      c.begin(PK_BATCH_EXP_G2, si, n);
+      k_batch_exp<GC><<<div_up(n, ExpBlock<GC>::PPB), EXP_BLOCK, ExpBlock<GC>::SMEM, st>>>(batch, 0, d_table, check, d_jac, d_status);
+      c.end(si);
+    }
+  }
+  if (!coop) {
+    c.begin(IS_G1 ? PK_BATCH_EXP_G1 : PK_BATCH_EXP_G2, si, n);
+    k_batch_exp<G><<<div_up(n, EXP_BLOCK), EXP_BLOCK, TREE_BYTES, st>>>(batch, in_compressed, d_table, check, d_jac, d_status);
+    c.end(si);
+  }
   c.begin(IS_G1 ? PK_NORMALIZE_G1 : PK_NORMALIZE_G2, si, n);
   k_normalize_write<G><<<div_up(div_up(n, NORM_BATCH), 128), 128, 0, st>>>(batch, d_jac, out_compressed);
   c.end(si);

@@ -6,6 +6,7 @@
 // via tools/gen_constants.py.
 #pragma once
 #include "ec.cuh"
+#include "coop.cuh"
 
 namespace sso {
 
@@ -138,13 +139,38 @@ struct Mnt6_753_G2 {
   static constexpr bool A_IS_ZERO = false;
   __device__ __forceinline__ static F::T mul_a(const F::T& x) {
     // x * u^2 = (11 c1, 11 c2, c0), then times 11
-    F::T t{Fq6::mul_small<11>(x.c1), Fq6::mul_small<11>(x.c2), x.c0};
-    return F::mul_small<11>(t);
+    return F::mul_small<11>(F::mul_u2(x));
   }
   __device__ __forceinline__ static bool field_sqrt(const F::T& a, F::T& o) {
     return F::sqrt_ts<TS_q6x3>(a, o, c_q6x3_tm1h, c_q6x3_tsz);
   }
 };
+
+// ---- warp-cooperative variants of the extension-field groups (coop.cuh): the same curve, the same constants, one
+// coefficient of every coordinate per lane.  Used by the batch_exp kernels on uncompressed input; everything else (point
+// decompression, normalisation, MSM, pairing) keeps the one-thread-per-element types above.
+#define SSO_GROUP_COOP(NAME, PLAIN, ...)                                                            \
+  using Plain = PLAIN;                                                                              \
+  using F = __VA_ARGS__;                                                                            \
+  __device__ __forceinline__ static typename F::T coeff_b() { return F::from_const(c_##NAME##_b); } \
+  __device__ __forceinline__ static bool field_sqrt(const typename F::T&, typename F::T&) { return false; }
+struct Bls12_377_G2C : Bls12_377_G2 {
+  SSO_GROUP_COOP(bls12_377_g2, Bls12_377_G2, CFp2<Fq377, 5, true>)
+  __device__ __forceinline__ static F::T mul_a(const F::T&) { return F::zero(); }
+};
+struct Mnt4_753_G2C : Mnt4_753_G2 {
+  SSO_GROUP_COOP(mnt4_753_g2, Mnt4_753_G2, CFp2<Fq4, 13, false>)
+  __device__ __forceinline__ static F::T mul_a(const F::T& x) { return F::mul_small<26>(x); }
+};
+struct Mnt6_753_G2C : Mnt6_753_G2 {
+  SSO_GROUP_COOP(mnt6_753_g2, Mnt6_753_G2, CFp3<Fq6, 11, false>)
+  __device__ __forceinline__ static F::T mul_a(const F::T& x) { return F::mul_small<11>(F::mul_u2(x)); }
+};
+// the cooperative variant of a group, or void
+template <class G> struct CoopOf { using type = void; };
+template <> struct CoopOf<Bls12_377_G2> { using type = Bls12_377_G2C; };
+template <> struct CoopOf<Mnt4_753_G2> { using type = Mnt4_753_G2C; };
+template <> struct CoopOf<Mnt6_753_G2> { using type = Mnt6_753_G2C; };
 
 // ids on the C ABI (include/sso_b200.h)
 enum : uint32_t { CURVE_BLS12_377 = 0, CURVE_BW6_761 = 1, CURVE_MNT4_753 = 2, CURVE_MNT6_753 = 3 };

@@ -361,9 +361,8 @@ template <class Cfg> struct SW {
   // the 753-bit ladder (constants and the numerical checks: tools/gen_constants.py::mnt_endo_block)
   __device__ __forceinline__ static FT endo_frob(const FT& a) {
     using E = typename Cfg::Endo;
-    using B = typename F::Base;
     if constexpr (F::DEG == 2) { return F::conj(a); }
-    else { return FT{a.c0, B::mul(a.c1, B::from_const(E::w1())), B::mul(a.c2, B::from_const(E::w2()))}; }
+    else { return F::frob_w(a, E::w1(), E::w2()); }
   }
   template <int KL>
   __device__ __forceinline__ static void gls2_split(const uint32_t* k, uint32_t* k0, uint32_t* k1) {

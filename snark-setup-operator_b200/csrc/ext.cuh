@@ -21,6 +21,7 @@ template <class B_, class NR> struct Fp2 {
   using B = B_;
   using Base = B_;
   static constexpr int DEG = 2;
+  static constexpr int COOP = 0;
   static constexpr int NBYTES = 2 * B::NBYTES;
   static constexpr int WORDS = 2 * B::L;
   struct T { typename B::T c0, c1; };
@@ -139,6 +140,7 @@ template <class B_, class NR> struct Fp3 {
   using B = B_;
   using Base = B_;
   static constexpr int DEG = 3;
+  static constexpr int COOP = 0;
   static constexpr int NBYTES = 3 * B::NBYTES;
   static constexpr int WORDS = 3 * B::L;
   struct T { typename B::T c0, c1, c2; };
@@ -169,6 +171,12 @@ template <class B_, class NR> struct Fp3 {
   }
   __device__ __noinline__ static T sqr(const T& a) { return mul(a, a); }
   __device__ __forceinline__ static T mul_base(const T& a, const typename B::T& k) { return T{B::mul(a.c0, k), B::mul(a.c1, k), B::mul(a.c2, k)}; }
+  // (c0, c1 w1, c2 w2): the q-power Frobenius with the base-field constants w1, w2 of the tower
+  __device__ __forceinline__ static T frob_w(const T& a, const uint32_t* w1, const uint32_t* w2) {
+    return T{a.c0, B::mul(a.c1, B::from_const(w1)), B::mul(a.c2, B::from_const(w2))};
+  }
+  // x u^2 = (nr c1, nr c2, c0)
+  __device__ __forceinline__ static T mul_u2(const T& a) { return T{NR::mul(a.c1), NR::mul(a.c2), a.c0}; }
   __device__ __noinline__ static T inv(const T& a) {
     typename B::T t0 = B::sub(B::sqr(a.c0), NR::mul(B::mul(a.c1, a.c2)));
     typename B::T t1 = B::sub(NR::mul(B::sqr(a.c2)), B::mul(a.c0, a.c1));

@@ -289,6 +289,7 @@ template <class P_> struct Fp {
   using P = P_;
   static constexpr int L = P::L;
   static constexpr int DEG = 1;
+  static constexpr int COOP = 0;                    // lanes per element (coop.cuh); 0 = one thread per element
   static constexpr int NBYTES = P::NBYTES;          // serialized size
   static constexpr int WORDS = L;                   // uint32 words per element in device arrays
   struct T { uint32_t v[L]; };

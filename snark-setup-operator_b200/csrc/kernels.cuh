@@ -177,7 +177,9 @@ __device__ __forceinline__ typename G::F::T exp_stage_a(uint32_t tid, const VecB
   const VecSeg& sg = b.seg[sidx];
   typename C::Affine p;
   const uint8_t* src = staged_src ? staged_src : sg.in + (size_t)j * (in_compressed ? C::SIZE_C : C::SIZE_U);
-  uint32_t dst = in_compressed ? C::read_compressed(src, p) : C::read_uncompressed(src, p);
+  uint32_t dst;
+  if constexpr (F::COOP != 0) dst = C::read_uncompressed(src, p);     // the cooperative bodies take uncompressed input only (host-selected)
+  else dst = in_compressed ? C::read_compressed(src, p) : C::read_uncompressed(src, p);
   if (dst != C::DESER_OK) { report(status, dst, j, sidx); p.inf = true; }
   if (check != CHECK_NO && dst == C::DESER_OK) {
     if (p.inf) report(status, ST_ZERO_POINT, j, sidx);
@@ -245,13 +247,15 @@ __device__ __forceinline__ void exp_stage_c(uint32_t tid, const VecBatch& b, typ
 // their records byte by byte from global memory touch 32 different lines per instruction).  The buffer is the inversion tree's
 // (used later), plus 16 bytes for the alignment offset.  Returns the thread's record, or null when the block straddles two
 // vectors (at most three blocks per launch: they read global memory directly).
-template <class G>
-__device__ __forceinline__ const uint8_t* block_stage_input(uint32_t block, const VecBatch& b, uint32_t in_compressed, uint8_t* smem) {
+// PPB = points per block (EXP_BLOCK, or fewer when several lanes share a point: coop.cuh), pb = this thread's point inside the block.
+template <class G, int PPB = EXP_BLOCK>
+__device__ __forceinline__ const uint8_t* block_stage_input(uint32_t block, const VecBatch& b, uint32_t in_compressed, uint8_t* smem,
+                                                            uint32_t pb = threadIdx.x) {
   using C = SW<G>;
   const uint32_t sz = in_compressed ? C::SIZE_C : C::SIZE_U;
-  const uint32_t f0 = block * EXP_BLOCK;
+  const uint32_t f0 = block * PPB;
   if (f0 >= b.total) return nullptr;
-  const uint32_t f1 = f0 + EXP_BLOCK - 1 < b.total ? f0 + EXP_BLOCK - 1 : b.total - 1;
+  const uint32_t f1 = f0 + PPB - 1 < b.total ? f0 + PPB - 1 : b.total - 1;
   uint32_t s0, j0, s1, j1;
   locate(b, f0, s0, j0);
   locate(b, f1, s1, j1);
@@ -266,38 +270,111 @@ __device__ __forceinline__ const uint8_t* block_stage_input(uint32_t block, cons
   for (uint32_t k = threadIdx.x; k < full; k += EXP_BLOCK) sv[k] = gv[k];
   for (uint32_t k = (full << 4) + threadIdx.x; k < span; k += EXP_BLOCK) smem[k] = ga[k];      // tail: never past the vector
   __syncthreads();
-  const uint32_t tid = f0 + threadIdx.x;
-  return tid <= f1 ? smem + head + (tid - f0) * sz : nullptr;
+  const uint32_t tid = f0 + pb;
+  return (pb < (uint32_t)PPB && tid <= f1) ? smem + head + (tid - f0) * sz : nullptr;
 }
 
 // whole block: `tree` is shared memory for 2 * EXP_BLOCK field elements (+ 16 bytes, see block_stage_input)
+// Points per block of a batch_exp body: EXP_BLOCK, or EXP_BLOCK / 32 warps x the groups of one warp for the cooperative fields
+template <class G> struct ExpBlock {
+  static constexpr int COOP = G::F::COOP;
+  static constexpr int PPB = COOP == 0 ? EXP_BLOCK : (EXP_BLOCK / 32) * (32 / (COOP == 0 ? 1 : COOP));
+  // shared memory: the inversion tree (2 PPB whole elements) and, before it, the staged input bytes (+ 16 for the alignment offset)
+  static constexpr size_t TREE = G::AFFINE_TABLE ? (size_t)2 * PPB * G::F::WORDS * 4 : 0;
+  static constexpr size_t STAGE = (size_t)PPB * 2 * G::F::NBYTES;
+  static constexpr size_t SMEM = 16 + (TREE > STAGE ? TREE : STAGE);
+};
+
+// Cooperative body (coop.cuh): DEG lanes per point.  The tree holds one array of 2 PPB coefficients per role.
+template <class G>
+__device__ __forceinline__ void block_batch_exp_coop(uint32_t block, const VecBatch& b, const uint32_t* table, uint32_t check,
+                                                     uint32_t* jac_out, uint32_t* status, unsigned char* smem) {
+  using F = typename G::F;
+  using CO = Coop<F::DEG>;
+  constexpr int PPB = ExpBlock<G>::PPB;
+  static_assert(!G::AFFINE_TABLE || (PPB & (PPB - 1)) == 0, "the product tree needs a power of two of leaves");
+  typename ExpTypes<G>::State st;
+  const bool lane_ok = CO::lane_active();
+  const uint32_t pb = lane_ok ? CO::group_in_block() : 0xffffffffu;
+  const uint32_t tid = lane_ok ? block * PPB + pb : 0xffffffffu;       // idle lanes locate nothing and never exchange
+  const uint8_t* staged = block_stage_input<G, PPB>(block, b, 0, smem, pb);
+  typename F::T leaf = exp_stage_a<G>(tid, b, 0, table, check, status, st, staged);
+  __syncthreads();
+  if constexpr (G::AFFINE_TABLE) {
+    typename F::T* tree = reinterpret_cast<typename F::T*>(smem) + (size_t)(lane_ok ? CO::role() : 0) * 2 * PPB;
+    if (lane_ok) tree[PPB + pb] = leaf;
+    for (int n = PPB / 2; n >= 1; n >>= 1) { __syncthreads(); if (lane_ok) tree_up<F>(tree, n, (int)pb); }
+    __syncthreads();
+    if (lane_ok && pb == 0) tree[1] = F::inv(tree[1]);
+    for (int n = 1; n < PPB; n <<= 1) { __syncthreads(); if (lane_ok) tree_down<F>(tree, n, (int)pb); }
+    __syncthreads();
+    if (lane_ok) leaf = tree[PPB + pb];
+  }
+  if (lane_ok) exp_stage_c<G>(tid, b, st, leaf, jac_out);
+}
+
 template <class G>
 __device__ __forceinline__ void block_batch_exp(uint32_t block, const VecBatch& b, uint32_t in_compressed, const uint32_t* table,
                                                 uint32_t check, uint32_t* jac_out, uint32_t* status, typename G::F::T* tree) {
-  typename ExpTypes<G>::State st;
-  uint32_t tid = block * EXP_BLOCK + threadIdx.x;
-  const uint8_t* staged = block_stage_input<G>(block, b, in_compressed, reinterpret_cast<uint8_t*>(tree));
-  typename G::F::T leaf = exp_stage_a<G>(tid, b, in_compressed, table, check, status, st, staged);
-  __syncthreads();                                                    // the staged bytes are dead: the tree may take the buffer
-  if constexpr (G::AFFINE_TABLE) {
-    tree[EXP_BLOCK + threadIdx.x] = leaf;
-    block_batch_inverse<typename G::F>(tree, threadIdx.x);
-    leaf = tree[EXP_BLOCK + threadIdx.x];
+  if constexpr (G::F::COOP != 0) {
+    block_batch_exp_coop<G>(block, b, table, check, jac_out, status, reinterpret_cast<unsigned char*>(tree));
+  } else {
+    typename ExpTypes<G>::State st;
+    uint32_t tid = block * EXP_BLOCK + threadIdx.x;
+    const uint8_t* staged = block_stage_input<G>(block, b, in_compressed, reinterpret_cast<uint8_t*>(tree));
+    typename G::F::T leaf = exp_stage_a<G>(tid, b, in_compressed, table, check, status, st, staged);
+    __syncthreads();                                                  // the staged bytes are dead: the tree may take the buffer
+    if constexpr (G::AFFINE_TABLE) {
+      tree[EXP_BLOCK + threadIdx.x] = leaf;
+      block_batch_inverse<typename G::F>(tree, threadIdx.x);
+      leaf = tree[EXP_BLOCK + threadIdx.x];
+    }
+    exp_stage_c<G>(tid, b, st, leaf, jac_out);
   }
-  exp_stage_c<G>(tid, b, st, leaf, jac_out);
 }
 #else
+// Points per block (see the device version above)
+template <class G> struct ExpBlock {
+  static constexpr int COOP = G::F::COOP;
+  static constexpr int PPB = COOP == 0 ? EXP_BLOCK : (EXP_BLOCK / 32) * (32 / (COOP == 0 ? 1 : COOP));
+};
+// emulation of the cooperative body: the DEG lanes of a group are DEG lockstep host threads, the groups of a block run in turn
+template <class G>
+inline void block_batch_exp_coop_all(uint32_t block, const VecBatch& b, const uint32_t* table, uint32_t check, uint32_t* jac_out,
+                                     uint32_t* status) {
+  using F = typename G::F;
+  constexpr int DEG = F::DEG, PPB = ExpBlock<G>::PPB;
+  std::vector<typename ExpTypes<G>::State> st((size_t)PPB * DEG);
+  std::vector<typename F::T> tree((size_t)DEG * 2 * PPB);
+  uint32_t st_local[DEG][3];
+  for (int r = 0; r < DEG; r++) st_local[r][0] = st_local[r][1] = st_local[r][2] = 0;
+  coop_emu_run(DEG, [&](int r) {
+    typename F::T* tr = tree.data() + (size_t)r * 2 * PPB;
+    for (int p = 0; p < PPB; p++) tr[PPB + p] = exp_stage_a<G>(block * PPB + p, b, 0, table, check, st_local[r], st[(size_t)p * DEG + r]);
+    if constexpr (G::AFFINE_TABLE) {
+      for (int n = PPB / 2; n >= 1; n >>= 1) for (int t = 0; t < n; t++) tree_up<F>(tr, n, t);
+      tr[1] = F::inv(tr[1]);
+      for (int n = 1; n < PPB; n <<= 1) for (int t = 0; t < n; t++) tree_down<F>(tr, n, t);
+    }
+    for (int p = 0; p < PPB; p++) exp_stage_c<G>(block * PPB + p, b, st[(size_t)p * DEG + r], tr[PPB + p], jac_out);
+  });
+  if (status[0] == 0 && st_local[0][0] != 0) { status[0] = st_local[0][0]; status[1] = st_local[0][1]; status[2] = st_local[0][2]; }
+}
 // emulation: one block at a time, stages run for all of its threads in turn
 template <class G>
 inline void block_batch_exp_all(uint32_t block, const VecBatch& b, uint32_t in_compressed, const uint32_t* table, uint32_t check,
                                 uint32_t* jac_out, uint32_t* status) {
   using F = typename G::F;
-  std::vector<typename ExpTypes<G>::State> st(EXP_BLOCK);
-  std::vector<typename F::T> tree(2 * EXP_BLOCK);
-  for (int t = 0; t < EXP_BLOCK; t++)
-    tree[EXP_BLOCK + t] = exp_stage_a<G>(block * EXP_BLOCK + t, b, in_compressed, table, check, status, st[t]);
-  block_batch_inverse_all<F>(tree.data());
-  for (int t = 0; t < EXP_BLOCK; t++) exp_stage_c<G>(block * EXP_BLOCK + t, b, st[t], tree[EXP_BLOCK + t], jac_out);
+  if constexpr (F::COOP != 0) {
+    block_batch_exp_coop_all<G>(block, b, table, check, jac_out, status);
+  } else {
+    std::vector<typename ExpTypes<G>::State> st(EXP_BLOCK);
+    std::vector<typename F::T> tree(2 * EXP_BLOCK);
+    for (int t = 0; t < EXP_BLOCK; t++)
+      tree[EXP_BLOCK + t] = exp_stage_a<G>(block * EXP_BLOCK + t, b, in_compressed, table, check, status, st[t]);
+    block_batch_inverse_all<F>(tree.data());
+    for (int t = 0; t < EXP_BLOCK; t++) exp_stage_c<G>(block * EXP_BLOCK + t, b, st[t], tree[EXP_BLOCK + t], jac_out);
+  }
 }
 #endif
 

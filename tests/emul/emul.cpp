@@ -74,47 +74,67 @@ extern "C" int emul_group_sqrt(uint32_t curve, uint32_t group, const uint8_t* a,
   return rc;
 }
 
+// G = the group configuration of the batch_exp bodies (possibly a cooperative one, coop.cuh), GN = the one-thread-per-element
+// configuration of the same group for the normalisation
+template <class G, class GN>
+static void batch_exp_emul(const uint8_t* in, uint32_t in_compressed, uint32_t n, const uint32_t* tau_canon, const uint32_t* coeff_canon,
+                           uint64_t first_index, uint32_t mode, uint32_t check, uint8_t* out, uint32_t out_compressed, uint32_t* status) {
+  using Fr = typename G::Fr;
+  using F = typename GN::F;
+  using C = SW<GN>;
+  constexpr uint32_t PPB = ExpBlock<G>::PPB;
+  std::vector<uint32_t> table((size_t)TAU_TABLE_ELEMS * Fr::L);
+  std::vector<uint32_t> coeffs((size_t)TAU_COEFF_SLOTS * Fr::L, 0);
+  for (int i = 0; i < TAU_COEFF_SLOTS; i++) coeffs[(size_t)i * Fr::L] = 1;
+  // the coefficient goes to slot 2 so that the slot plumbing is exercised too
+  if (coeff_canon) memcpy(coeffs.data() + 2 * Fr::L, coeff_canon, Fr::L * 4);
+  for (uint32_t t = 0; t < (uint32_t)TAU_TABLE_ELEMS; t++)
+    body_tau_tables<Fr>(t, tau_canon, coeffs.data(), first_index, table.data());
+  // split the vector into two segments to exercise the multi-vector launch path
+  uint32_t n0 = n / 2, n1 = n - n0;
+  size_t isz = in_compressed ? C::SIZE_C : C::SIZE_U, osz = out_compressed ? C::SIZE_C : C::SIZE_U;
+  VecBatch b;
+  memset(&b, 0, sizeof b);
+  if (n0) { b.seg[b.nseg++] = VecSeg{in, out, n0, 2, coeff_canon != nullptr, mode}; }
+  // second segment continues the index range: emulate by a second table start -> instead run it as its own batch
+  b.total = n0;
+  std::vector<uint32_t> jac((size_t)n * 3 * F::WORDS);
+  for (uint32_t blk = 0; blk * PPB < n0; blk++) block_batch_exp_all<G>(blk, b, in_compressed, table.data(), check, jac.data(), status);
+  for (uint32_t t = 0; t * NORM_BATCH < n0; t++) body_normalize_write<GN>(t, b, jac.data(), out_compressed);
+  // remaining elements: a batch of two segments (n1 - 1 elements + 1 element) starting at index first + n0
+  std::vector<uint32_t> table2((size_t)TAU_TABLE_ELEMS * Fr::L);
+  for (uint32_t t = 0; t < (uint32_t)TAU_TABLE_ELEMS; t++)
+    body_tau_tables<Fr>(t, tau_canon, coeffs.data(), first_index + n0, table2.data());
+  uint32_t st2[3] = {0, 0, 0};
+  if (n1 > 0) {
+    VecBatch b2;
+    memset(&b2, 0, sizeof b2);
+    b2.seg[0] = VecSeg{in + n0 * isz, out + n0 * osz, n1, 2, coeff_canon != nullptr, mode};
+    b2.nseg = 1; b2.total = n1;
+    for (uint32_t blk = 0; blk * PPB < n1; blk++) block_batch_exp_all<G>(blk, b2, in_compressed, table2.data(), check, jac.data(), st2);
+    for (uint32_t t = 0; t * NORM_BATCH < n1; t++) body_normalize_write<GN>(t, b2, jac.data(), out_compressed);
+    if (status[0] == 0 && st2[0] != 0) { status[0] = st2[0]; status[1] = st2[1] + n0; }
+  }
+}
+
+// group 0 / 1 = G1 / G2 (one thread per element); group 2 = G2 through the warp-cooperative bodies (uncompressed input only)
 extern "C" int emul_batch_exp(uint32_t curve, uint32_t group, const uint8_t* in, uint32_t in_compressed, uint32_t n,
                               const uint32_t* tau_canon, const uint32_t* coeff_canon, uint64_t first_index, uint32_t mode,
                               uint32_t check, uint8_t* out, uint32_t out_compressed, uint32_t* status) {
   status[0] = status[1] = status[2] = 0;
+  if (group == 2) {
+    if (in_compressed) return -2;
+    return dispatch_group(curve, 1, [&](auto g) {
+      using GN = decltype(g);
+      using GC = typename CoopOf<GN>::type;
+      if constexpr (!std::is_void<GC>::value)
+        batch_exp_emul<GC, GN>(in, 0, n, tau_canon, coeff_canon, first_index, mode, check, out, out_compressed, status);
+      else status[0] = 0xdead;
+    });
+  }
   return dispatch_group(curve, group, [&](auto g) {
     using G = decltype(g);
-    using Fr = typename G::Fr;
-    using F = typename G::F;
-    using C = SW<G>;
-    std::vector<uint32_t> table((size_t)TAU_TABLE_ELEMS * Fr::L);
-    std::vector<uint32_t> coeffs((size_t)TAU_COEFF_SLOTS * Fr::L, 0);
-    for (int i = 0; i < TAU_COEFF_SLOTS; i++) coeffs[(size_t)i * Fr::L] = 1;
-    // the coefficient goes to slot 2 so that the slot plumbing is exercised too
-    if (coeff_canon) memcpy(coeffs.data() + 2 * Fr::L, coeff_canon, Fr::L * 4);
-    for (uint32_t t = 0; t < (uint32_t)TAU_TABLE_ELEMS; t++)
-      body_tau_tables<Fr>(t, tau_canon, coeffs.data(), first_index, table.data());
-    // split the vector into two segments to exercise the multi-vector launch path
-    uint32_t n0 = n / 2, n1 = n - n0;
-    size_t isz = in_compressed ? C::SIZE_C : C::SIZE_U, osz = out_compressed ? C::SIZE_C : C::SIZE_U;
-    VecBatch b;
-    memset(&b, 0, sizeof b);
-    if (n0) { b.seg[b.nseg++] = VecSeg{in, out, n0, 2, coeff_canon != nullptr, mode}; }
-    // second segment continues the index range: emulate by a second table start -> instead run it as its own batch
-    b.total = n0;
-    std::vector<uint32_t> jac((size_t)n * 3 * F::WORDS);
-    for (uint32_t blk = 0; blk * EXP_BLOCK < n0; blk++) block_batch_exp_all<G>(blk, b, in_compressed, table.data(), check, jac.data(), status);
-    for (uint32_t t = 0; t * NORM_BATCH < n0; t++) body_normalize_write<G>(t, b, jac.data(), out_compressed);
-    // remaining elements: a batch of two segments (n1 - 1 elements + 1 element) starting at index first + n0
-    std::vector<uint32_t> table2((size_t)TAU_TABLE_ELEMS * Fr::L);
-    for (uint32_t t = 0; t < (uint32_t)TAU_TABLE_ELEMS; t++)
-      body_tau_tables<Fr>(t, tau_canon, coeffs.data(), first_index + n0, table2.data());
-    uint32_t st2[3] = {0, 0, 0};
-    if (n1 > 0) {
-      VecBatch b2;
-      memset(&b2, 0, sizeof b2);
-      b2.seg[0] = VecSeg{in + n0 * isz, out + n0 * osz, n1, 2, coeff_canon != nullptr, mode};
-      b2.nseg = 1; b2.total = n1;
-      for (uint32_t blk = 0; blk * EXP_BLOCK < n1; blk++) block_batch_exp_all<G>(blk, b2, in_compressed, table2.data(), check, jac.data(), st2);
-      for (uint32_t t = 0; t * NORM_BATCH < n1; t++) body_normalize_write<G>(t, b2, jac.data(), out_compressed);
-      if (status[0] == 0 && st2[0] != 0) { status[0] = st2[0]; status[1] = st2[1] + n0; }
-    }
+    batch_exp_emul<G, G>(in, in_compressed, n, tau_canon, coeff_canon, first_index, mode, check, out, out_compressed, status);
   });
 }
 

@@ -23,7 +23,7 @@ def emul():
                                                     for f in os.listdir(os.path.join(ROOT, "snark-setup-operator_b200", "csrc"))
                                                     if f.endswith((".cuh", ".h"))]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-o", so, os.path.join(EMUL_DIR, "emul.cpp")])
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-pthread", "-o", so, os.path.join(EMUL_DIR, "emul.cpp")])
     return ctypes.CDLL(so)
 
 
@@ -109,7 +109,8 @@ def test_batch_exp_and_reencode(emul, name, gi):
     assert list(st)[:2] == [0, 0]
 
 
-def test_bls12_g2_four_way_decomposition_edge_scalars(emul):
+@pytest.mark.parametrize("body", [1, 2])                    # 1 = one thread per element, 2 = warp-cooperative (coop.cuh)
+def test_bls12_g2_four_way_decomposition_edge_scalars(emul, body):
     """The G2 ladder of BLS12-377 splits the scalar into base-x digits (x = curve parameter) and uses psi, psi^2, psi^3:
     scalars on the digit boundaries, and a small-order base point (Jacobian-table path), must still match [k]P."""
     c = get_curve("bls12_377")
@@ -128,12 +129,13 @@ def test_bls12_g2_four_way_decomposition_edge_scalars(emul):
             continue
         want = ser.points_to_bytes(G, [G.mul(P, k) for P in pts], False)
         out = ctypes.create_string_buffer(len(want))
-        assert emul.emul_batch_exp(c.cid, 1, buf, 0, 2, words(1, Lr), words(k, Lr), ctypes.c_uint64(0), 1, 0, out, 0, st) == 0
+        assert emul.emul_batch_exp(c.cid, body, buf, 0, 2, words(1, Lr), words(k, Lr), ctypes.c_uint64(0), 1, 0, out, 0, st) == 0
         assert out.raw == want, hex(k)
 
 
+@pytest.mark.parametrize("body", [1, 2])
 @pytest.mark.parametrize("name", ["mnt4_753", "mnt6_753"])
-def test_mnt_g2_two_way_decomposition_edge_scalars(emul, name):
+def test_mnt_g2_two_way_decomposition_edge_scalars(emul, name, body):
     """The G2 ladders of the MNT curves split the scalar as k = k0 + k1 mu (mu = |t - 1|, the eigenvalue of the Frobenius
     endomorphism psi up to sign; Barrett quotient with corrections) and add psi-images of the table entries: scalars on the
     digit and quotient boundaries, and a base point of the full group order, must still match [k]P."""
@@ -153,7 +155,7 @@ def test_mnt_g2_two_way_decomposition_edge_scalars(emul, name):
             continue
         want = ser.points_to_bytes(G, [G.mul(P, k) for P in pts], False)
         out = ctypes.create_string_buffer(len(want))
-        assert emul.emul_batch_exp(c.cid, 1, buf, 0, 2, words(1, Lr), words(k, Lr), ctypes.c_uint64(0), 1, 0, out, 0, st) == 0
+        assert emul.emul_batch_exp(c.cid, body, buf, 0, 2, words(1, Lr), words(k, Lr), ctypes.c_uint64(0), 1, 0, out, 0, st) == 0
         assert out.raw == want, hex(k)
 
 
@@ -355,3 +357,39 @@ def test_small_order_base_point(emul):
         out = ctypes.create_string_buffer(len(want))
         assert emul.emul_batch_exp(c.cid, 0, buf, 0, len(pts), words(1, Lr), words(k, Lr), ctypes.c_uint64(0), 1, 0, out, 1, st) == 0
         assert out.raw == want, k
+
+
+@pytest.mark.parametrize("name", ["bls12_377", "mnt4_753", "mnt6_753"])
+def test_cooperative_g2_bodies(emul, name):
+    """coop.cuh: an Fq2 / Fq3 element is held by two / three adjacent lanes (one coefficient each); the lanes of a group are
+    emulated by lockstep host threads and their exchanges by a shared slot array.  Same inputs, same bytes as the
+    one-thread-per-element bodies: tau powers with a coefficient, the shared-scalar mode, an infinity element under
+    CHECK_NONZERO, the on-curve check under CHECK_FULL (accept and reject), more points than one group."""
+    c = get_curve(name)
+    G = c.g2
+    n = 6 if name == "bls12_377" else 4
+    rnd = random.Random(31 * c.cid)
+    Lr = (c.Fr.bits + 31) // 32
+    key = synth.contributor_key(c)
+    pts = [G.mul(G.gen, rnd.randrange(1, G.r)) for _ in range(n - 1)] + [None]
+    buf = ser.points_to_bytes(G, pts, False)
+    first = (1 << 24) + 12345
+    want = ser.points_to_bytes(G, [G.mul(P, key.alpha * pow(key.tau, first + j, c.Fr.p) % c.Fr.p) for j, P in enumerate(pts)], True)
+    out = ctypes.create_string_buffer(len(want))
+    st = (ctypes.c_uint32 * 3)()
+    assert emul.emul_batch_exp(c.cid, 2, buf, 0, n, words(key.tau, Lr), words(key.alpha, Lr), ctypes.c_uint64(first), 0, 1, out, 1, st) == 0
+    assert out.raw == want
+    assert list(st)[:2] == [4, n - 1]
+    # CHECK_FULL accepts curve points; a point off the curve (y + 1) is reported at its index
+    want2 = ser.points_to_bytes(G, [G.mul(P, key.beta) for P in pts[:-1]], False)
+    out2 = ctypes.create_string_buffer(len(want2))
+    assert emul.emul_batch_exp(c.cid, 2, buf, 0, n - 1, words(1, Lr), words(key.beta, Lr), ctypes.c_uint64(0), 1, 2, out2, 0, st) == 0
+    assert out2.raw == want2 and list(st)[:2] == [0, 0]
+    F = G.F
+    bad = list(pts[:-1])
+    bad[1] = (bad[1][0], F.add(bad[1][1], F.one))
+    assert emul.emul_batch_exp(c.cid, 2, ser.points_to_bytes(G, bad, False), 0, n - 1, words(1, Lr), words(key.beta, Lr),
+                               ctypes.c_uint64(0), 1, 2, out2, 0, st) == 0
+    assert list(st)[:2] == [3, 1]                            # ST_NOT_ON_CURVE at element 1
+    # compressed input is not taken by the cooperative bodies (the host selects the other kernel)
+    assert emul.emul_batch_exp(c.cid, 2, want, 1, n, words(1, Lr), words(key.beta, Lr), ctypes.c_uint64(0), 1, 0, out2, 0, st) == -2
