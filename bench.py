@@ -67,11 +67,20 @@ def ncu_dram_bytes_per_launch(curve: str):
     return (tot or None), os.path.relpath(best[1], ROOT)
 
 
+COOP_G2_DEFAULT = {"bls12_377": False, "bw6_761": False, "mnt4_753": True, "mnt6_753": True}      # csrc/curves.cuh::COOP_DEFAULT
+
+
+def coop_g2(curve: str) -> bool:
+    """Does the G2 half of a chunk run through the warp-cooperative bodies (csrc/coop.cuh)?  SSO_COOP_G2 = 0 / 1 forces it."""
+    e = os.environ.get("SSO_COOP_G2", "")
+    return COOP_G2_DEFAULT[curve] if not e else e[0] != "0"
+
+
 def declared_work_per_point(curve: str, group: int):
     """Closed-form count of base-field multiplications and squarings (m, s) of the batch_exp kernel per point:
       read the point into Montgomery form            2 deg
       window table 1P..8P                            4 dbl + 3 madd
-      affine table (all groups but MNT6 G2)          6 F-mul (Z products) + 13 F-mul + 7 (1 S + 3 M) (normalisation)
+      affine table (all but the one-thread MNT6 G2)  6 F-mul (Z products) + 13 F-mul + 7 (1 S + 3 M) (normalisation)
                                                      + 3 F-mul (share of the per-block inversion tree)
       window loop, signed 4-bit digits               4 (NW - 1) dbl + additions on 15/16 of the windows:
          plain ladder (MNT4/6)   NW = ceil((bits+2)/4)   one addition per window
@@ -80,7 +89,9 @@ def declared_work_per_point(curve: str, group: int):
          4-way psi decomposition (BLS12-377 G2)  NW = 17  four additions per window + (4 + 2 + 2) Fq-muls for psi, psi^2, psi^3
       additions are mixed (madd) with the affine table, full Jacobian additions otherwise.
     Base-field cost of an extension operation: Fq2 mul = 3 M, Fq2 sqr = 2 M (complex squaring); Fq3 mul = sqr = 6 M;
-    only prime-field squarings use the dedicated squaring (fewer multiply-accumulates, macs_per_fq_sqr)."""
+    only prime-field squarings use the dedicated squaring (fewer multiply-accumulates, macs_per_fq_sqr).
+    The warp-cooperative Fq2 body executes FOUR base multiplications per Fq2 product (two per lane); the declared work keeps
+    Karatsuba's three — the roofline fraction is quoted on the algorithmic count, not on what the layout executes."""
     _, bits = CURVE_BITS[curve]
     deg = G2_DEG[curve] if group == 1 else 1
     M, S = {1: ((1, 0), (0, 1)), 2: ((3, 0), (2, 0)), 3: ((6, 0), (6, 0))}[deg]
@@ -94,7 +105,8 @@ def declared_work_per_point(curve: str, group: int):
     madd = comb((7, M), (4, S))
     add = comb((11, M), (5, S))
     base = (1, 0)
-    affine = not (curve == "mnt6_753" and group == 1)
+    # MNT6-753 G2: Jacobian table in the one-thread-per-element body, affine table in the warp-cooperative body (the default)
+    affine = not (curve == "mnt6_753" and group == 1) or coop_g2(curve)
     terms = [(2 * deg, base), (4, dbl), (3, madd)]
     if affine:
         terms += [(6 + 13 + 21 + 3, M), (7, S)]
@@ -831,6 +843,8 @@ def main():
         "points_per_step": npts,
         "verify": verify,
     }
+    line["config"]["g2_body"] = "warp-cooperative (coop.cuh)" if coop_g2(args.curve) else "one thread per element"
+
     if not args.no_cpu_baseline:
         cb, _ = cpu_reference_run(args.curve, args.power, args.chunk_log, 1, 0, 12.0)
         line["cpu_baseline"] = cb

@@ -113,12 +113,6 @@ template <int DEG> struct Coop {
 };
 #endif
 
-// (nr + 1) x for the small non-residues of ext.cuh::SmallNR
-template <class B, int K, bool NEG> __device__ __forceinline__ typename B::T nr_plus_one(const typename B::T& x) {
-  if constexpr (NEG) return B::neg(B::template mul_small<K - 1>(x));
-  else return B::template mul_small<K + 1>(x);
-}
-
 // select without divergence
 template <int N> __device__ __forceinline__ void sel_words(uint32_t* out, bool c, const uint32_t* a, const uint32_t* b) {
 #pragma unroll
@@ -153,27 +147,31 @@ template <class B_, int K, bool NEG> struct CFp2 {
   __device__ __forceinline__ static T neg(const T& a) { return B::neg(a); }
   template <int M> __device__ __forceinline__ static T mul_small(const T& a) { return B::template mul_small<M>(a); }
 
-  // (a0 + a1 u)(b0 + b1 u): lane r forms a_r b_r and a_r b_(1-r); c0 = a0 b0 + nr a1 b1, c1 = a0 b1 + a1 b0
+  // (a0 + a1 u)(b0 + b1 u), c0 = a0 b0 + nr a1 b1, c1 = a0 b1 + a1 b0: lane r forms a_r (k_r b_r) with k_0 = 1, k_1 = nr — the
+  // non-residue rides on an UNREDUCED operand (fp.cuh "lazy operands"), so the multiplication itself reduces nr a1 b1 — and
+  // a_r b_(1-r); the lanes swap one product and finish with one addition
   __device__ __noinline__ static T mul_val(T a, T b) {
     const bool hi = CO::role() != 0;
     T ob = other(b);
-    T ps = B::mul(a, b);
-    T pc = B::mul(a, ob);
-    T recv = other(pick(hi, ps, pc));                 // lane 0 receives a1 b1, lane 1 receives a0 b1
-    T nrv = NR::mul(recv);
-    return B::add(pick(hi, pc, ps), pick(hi, recv, nrv));
+    T x = NEG ? pick(hi, B::neg_lazy(b), b) : b;
+    T kb = B::mad_small_lazy(B::zero(), hi ? (uint32_t)K : 1u, x);
+    T ps = B::mul(a, kb);                             // lane 0: a0 b0, lane 1: nr a1 b1
+    T pc = B::mul(a, ob);                             // a_r b_(1-r)
+    T recv = other(pick(hi, ps, pc));                 // lane 0 receives nr a1 b1, lane 1 receives a0 b1
+    return B::add(pick(hi, pc, ps), recv);
   }
-  // complex squaring: c0 = (a0 + a1)(a0 + nr a1) - (nr + 1) a0 a1, c1 = 2 a0 a1 — one base multiplication per lane
+  // complex squaring, ONE base multiplication per lane: lane 0 forms P = (a0 + a1)(a0 + nr a1), lane 1 forms w = (2 a1) a0;
+  // c0 = P - (nr + 1) a0 a1 = P - h w with h = (nr + 1) / 2 (nr is odd), c1 = w.  All four factors are unreduced operands.
   __device__ __noinline__ static T sqr_val(T a) {
+    static_assert((K & 1) == 1, "odd non-residue");
+    constexpr int H = (NEG ? K - 1 : K + 1) / 2;      // |h|; the sign of -h is + for a negative non-residue
     const bool hi = CO::role() != 0;
     T o = other(a);
-    T s = B::add(a, o);
-    T t = B::add(a, NR::mul(o));
-    T p = B::mul(pick(hi, a, s), pick(hi, o, t));      // lane 0: (a0 + a1)(a0 + nr a1); lane 1: a1 a0
-    T v = other(p);                                    // lane 0 receives a0 a1
-    T c0 = B::sub(p, nr_plus_one<B, K, NEG>(v));
-    T c1 = B::dbl(p);
-    return pick(hi, c1, c0);
+    T X = B::add_lazy(a, pick(hi, a, o));              // lane 0: a0 + a1, lane 1: 2 a1
+    T Y = B::mad_small_lazy(pick(hi, o, a), hi ? 0u : (uint32_t)K, NEG ? B::neg_lazy(o) : o);   // lane 0: a0 + nr a1, lane 1: a0
+    T P = B::mul(X, Y);
+    T w = other(P);                                    // lane 0 receives 2 a0 a1
+    return B::reduce_small(B::mad_small_lazy(P, hi ? 0u : (uint32_t)H, NEG ? w : B::neg_lazy(w)));
   }
   __device__ __forceinline__ static T mul(const T& a, const T& b) { return mul_val(a, b); }
   __device__ __forceinline__ static T sqr(const T& a) { return sqr_val(a); }
@@ -233,19 +231,36 @@ template <class B_, int K, bool NEG> struct CFp3 {
   // Karatsuba with v_r = a_r b_r, s_r = (a_r + a_(r+1))(b_r + b_(r+1)), u_r = s_r - v_r (indices mod 3):
   //   c0 = v0 + nr (u1 - v2)      c1 = (u0 - v1) + nr v2      c2 = (u2 - v0) + v1
   __device__ __noinline__ static T mul_val(T a, T b) {
+    static_assert(!NEG, "positive non-residue");
     const uint32_t r = CO::role();
     T v = B::mul(a, b);
-    T s = B::mul(B::add(a, from(a, 1)), B::add(b, from(b, 1)));
+    T s = B::mul(B::add_lazy(a, from(a, 1)), B::add_lazy(b, from(b, 1)));     // unreduced factors (< 2 p each): fp.cuh "lazy operands"
     T u = B::sub(s, v);
     T r1 = from(pick(r == 1, u, v), 1);                // lane 0: u1, lane 1: v2, lane 2: v0
     T r2 = from(pick(r == 0, u, v), 2);                // lane 0: v2, lane 1: u0, lane 2: v1
     T d = B::sub(pick(r == 0, r1, pick(r == 1, r2, u)), pick(r == 0, r2, pick(r == 1, v, r1)));
-    T nrx = NR::mul(pick(r == 0, d, r1));
-    return B::add(pick(r == 0, v, d), pick(r == 2, r2, nrx));
+    // c0 = v + nr d, c1 = d + nr r1, c2 = d + r2: one multiply-add by a small constant and one reduction for all three lanes
+    return B::reduce_small(B::mad_small_lazy(pick(r == 0, v, d), r == 2 ? 1u : (uint32_t)K, pick(r == 0, d, pick(r == 1, r1, r2))));
   }
   __device__ __forceinline__ static T mul(const T& a, const T& b) { return mul_val(a, b); }
   __device__ __forceinline__ static T sqr(const T& a) { return mul_val(a, a); }
   __device__ __forceinline__ static T mul_base(const T& a, const typename B::T& k) { return B::mul(a, k); }
+  // 1 / a = (t0, t1, t2) / n with t0 = a0^2 - nr a1 a2, t1 = nr a2^2 - a0 a1, t2 = a1^2 - a0 a2, n = a0 t0 + nr (a2 t1 + a1 t2);
+  // lane r forms t_r and its term of n, the norm and its inverse are formed by all three lanes (same data, same path).
+  // Once per thread block (the root of the inversion tree): not tuned.
+  __device__ __noinline__ static T inv(const T& a) {
+    const uint32_t r = CO::role();
+    T an = from(a, 1), ap = from(a, 2);                // a_(r+1), a_(r+2)
+    T sq = B::sqr(pick(r == 0, a, pick(r == 1, an, ap)));                           // a0^2 | a2^2 | a1^2
+    T pr = B::mul(pick(r == 1, ap, an), pick(r == 0, ap, a));                       // a1 a2 | a0 a1 | a0 a2
+    T nrs = NR::mul(pick(r == 0, pr, sq));
+    T t = B::sub(pick(r == 1, nrs, sq), pick(r == 0, nrs, pr));
+    T m = B::mul(pick(r == 0, a, pick(r == 1, an, ap)), t);                         // a0 t0 | a2 t1 | a1 t2
+    T mn = from(m, 1), mp = from(m, 2);
+    T cand = B::add(m, NR::mul(B::add(mn, mp)));      // the norm, on lane 0
+    T n = from(cand, r == 0 ? 0u : 3u - r);
+    return B::mul(t, B::inv(n));
+  }
   // (c0, c1 w1, c2 w2): the q-power Frobenius with the base-field constants w1, w2 of the tower
   __device__ __forceinline__ static T frob_w(const T& a, const uint32_t* w1, const uint32_t* w2) {
     const uint32_t r = CO::role();

@@ -162,7 +162,13 @@ struct Mnt4_753_G2C : Mnt4_753_G2 {
   SSO_GROUP_COOP(mnt4_753_g2, Mnt4_753_G2, CFp2<Fq4, 13, false>)
   __device__ __forceinline__ static F::T mul_a(const F::T& x) { return F::mul_small<26>(x); }
 };
+#ifndef SSO_MNT6_COOP_AFFINE
+#define SSO_MNT6_COOP_AFFINE 1
+#endif
 struct Mnt6_753_G2C : Mnt6_753_G2 {
+  // three lanes per point: the inversion tree of a block is 64 leaves of one coefficient per lane (37 KB instead of the 72 KB
+  // that made the affine table a loss for the one-thread-per-element body), so mixed additions pay here
+  static constexpr bool AFFINE_TABLE = SSO_MNT6_COOP_AFFINE != 0;
   SSO_GROUP_COOP(mnt6_753_g2, Mnt6_753_G2, CFp3<Fq6, 11, false>)
   __device__ __forceinline__ static F::T mul_a(const F::T& x) { return F::mul_small<11>(F::mul_u2(x)); }
 };

@@ -11,9 +11,25 @@ namespace sso {
 
 // Non-residue multiplication by a small integer: x -> (NEG ? -K x : K x)
 template <class B, int K, bool NEG> struct SmallNR {
+  static constexpr int ABS = K;
+  static constexpr bool IS_NEG = NEG;
   __device__ __forceinline__ static typename B::T mul(const typename B::T& x) {
     typename B::T t = B::template mul_small<K>(x);
     return NEG ? B::neg(t) : t;
+  }
+  // c + nr x as an UNREDUCED integer below (K + 1) p: an operand for a multiplication (fp.cuh "lazy operands")
+  __device__ __forceinline__ static typename B::T mad_lazy(const typename B::T& c, const typename B::T& x) {
+    return B::mad_small_lazy(c, (uint32_t)K, NEG ? B::neg_lazy(x) : x);
+  }
+  // c - (nr + 1) x, canonical
+  __device__ __forceinline__ static typename B::T sub_nr_plus_one(const typename B::T& c, const typename B::T& x) {
+    constexpr int M = NEG ? K - 1 : K + 1;                 // |nr + 1|
+    if constexpr (M <= 4) {
+      typename B::T m = B::template mul_small<M>(x);
+      return NEG ? B::add(c, m) : B::sub(c, m);
+    } else {
+      return B::reduce_small(B::mad_small_lazy(c, (uint32_t)M, NEG ? x : B::neg_lazy(x)));
+    }
   }
 };
 
@@ -58,11 +74,18 @@ template <class B_, class NR> struct Fp2 {
     return r;
   }
   __device__ __noinline__ static T sqr_val(T a) {
-    // (a0 + a1)(a0 + nr a1) = a0^2 + nr a1^2 + (nr + 1) a0 a1
+    // (a0 + a1)(a0 + nr a1) = a0^2 + nr a1^2 + (nr + 1) a0 a1; the two factors stay unreduced (< 2 p and < (|nr| + 1) p:
+    // their product is below p R for every tower here), so forming them costs two carry chains instead of seven modular ops
     typename B::T v = bmul(a.c0, a.c1);
+#ifndef SSO_NO_LAZY_OPERANDS
+    typename B::T pr = bmul(B::add_lazy(a.c0, a.c1), NR::mad_lazy(a.c0, a.c1));
+    T r;
+    r.c0 = NR::sub_nr_plus_one(pr, v);
+#else
     typename B::T pr = bmul(B::add(a.c0, a.c1), B::add(a.c0, NR::mul(a.c1)));
     T r;
     r.c0 = B::sub(B::sub(pr, v), NR::mul(v));
+#endif
     r.c1 = B::dbl(v);
     return r;
   }

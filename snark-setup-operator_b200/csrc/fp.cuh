@@ -331,6 +331,59 @@ template <class P_> struct Fp {
     for (int i = 0; i < L; i++) t.v[i] = z ? 0u : t.v[i];
     return t;
   }
+  // ---- unreduced ("lazy") operands --------------------------------------------------------------------------------
+  // mont_mul does not need reduced inputs: for a < A p, b < B p the CIOS accumulator stays below (A + 1) p and the result is
+  // < a b / R + p, i.e. < 2 p whenever A B p < R — its final conditional subtraction then returns the canonical residue.
+  // The base fields of the curves leave 7 (377 / 761 bits) or 15 (753 bits) spare bits in R = 2^(32 L), so sums and small
+  // multiples of reduced elements (A B <= 32) can feed a multiplication WITHOUT the compare-subtract-select of add() /
+  // mul_small(): one carry chain instead of up to six.  Only for products of the extension-field formulas (ext.cuh, coop.cuh);
+  // every value that leaves them is canonical again.
+  static constexpr int SPARE_BITS = 32 * L - P::BITS;
+  // a + b as integers (< 2 p)
+  __device__ __forceinline__ static T add_lazy(const T& a, const T& b) { T r; limbs_add<L>(r.v, a.v, b.v); return r; }
+  // p - a as an integer (a < p; p for a = 0: another representative of 0)
+  __device__ __forceinline__ static T neg_lazy(const T& a) { T r; limbs_sub<L>(r.v, P::p(), a.v); return r; }
+  // c + k x as integers; the caller guarantees (k + 1) p < R
+  __device__ __forceinline__ static T mad_small_lazy(const T& c, uint32_t k, const T& x) {
+    uint32_t ev[L], od[L];
+    mul_n<L>(ev, x.v, k);                            // k x[j] for even j: disjoint 64-bit pairs at limbs j, j + 1
+    mul_n<L>(od, x.v + 1, k);                        // k x[j] for odd j: pairs at limbs j, j + 1 (od[] starts at limb 1)
+    T r;
+    r.v[0] = add_cc(c.v[0], ev[0]);
+#pragma unroll
+    for (int i = 1; i < L - 1; i++) r.v[i] = addc_cc(c.v[i], ev[i]);
+    r.v[L - 1] = addc(c.v[L - 1], ev[L - 1]);
+    r.v[1] = add_cc(r.v[1], od[0]);
+#pragma unroll
+    for (int i = 2; i < L - 1; i++) r.v[i] = addc_cc(r.v[i], od[i - 1]);
+    r.v[L - 1] = addc(r.v[L - 1], od[L - 2]);         // od[L - 1] = high word of k x[L - 1] = 0 by the no-overflow guarantee
+    return r;
+  }
+  // canonical residue of y < 16 p: quotient estimate from the top limbs (never too large, at most one too small because the
+  // top limb of p has >= 17 bits), one multiple of p subtracted, one conditional subtraction
+  __device__ __forceinline__ static T reduce_small(const T& y) {
+    static_assert(SPARE_BITS >= 7 && SPARE_BITS <= 15, "top limb of p must hold at least 17 bits, and 16 p < R");
+    uint32_t q = y.v[L - 1] / (P::p()[L - 1] + 1u);
+    uint32_t ev[L], od[L], mod[L];
+    load_modulus<P>(mod);
+    mul_n<L>(ev, mod, q);
+    mul_n<L>(od, mod + 1, q);
+    T d;
+    d.v[0] = sub_cc(y.v[0], ev[0]);
+#pragma unroll
+    for (int i = 1; i < L - 1; i++) d.v[i] = subc_cc(y.v[i], ev[i]);
+    d.v[L - 1] = subc(y.v[L - 1], ev[L - 1]);
+    d.v[1] = sub_cc(d.v[1], od[0]);
+#pragma unroll
+    for (int i = 2; i < L - 1; i++) d.v[i] = subc_cc(d.v[i], od[i - 1]);
+    d.v[L - 1] = subc(d.v[L - 1], od[L - 2]);
+    T t, r;
+    uint32_t borrow = limbs_sub<L>(t.v, d.v, mod);
+#pragma unroll
+    for (int i = 0; i < L; i++) r.v[i] = borrow ? d.v[i] : t.v[i];
+    return r;
+  }
+
   // 24-limb multiplications are ~2.5k instructions each: keep one out-of-line copy so that point
   // formulas do not overflow the instruction cache; 8/12-limb ones are inlined.
   // by-value parameters: the device ABI passes them in registers (by-reference would round-trip through local memory)

@@ -279,8 +279,10 @@ __device__ __forceinline__ const uint8_t* block_stage_input(uint32_t block, cons
 template <class G> struct ExpBlock {
   static constexpr int COOP = G::F::COOP;
   static constexpr int PPB = COOP == 0 ? EXP_BLOCK : (EXP_BLOCK / 32) * (32 / (COOP == 0 ? 1 : COOP));
-  // shared memory: the inversion tree (2 PPB whole elements) and, before it, the staged input bytes (+ 16 for the alignment offset)
-  static constexpr size_t TREE = G::AFFINE_TABLE ? (size_t)2 * PPB * G::F::WORDS * 4 : 0;
+  // leaves of the inversion tree: the next power of two (40 points per block with three lanes per point -> 64, padded with ones)
+  static constexpr int TL = PPB <= 32 ? 32 : PPB <= 64 ? 64 : 128;
+  // shared memory: the inversion tree (2 TL whole elements) and, before it, the staged input bytes (+ 16 for the alignment offset)
+  static constexpr size_t TREE = G::AFFINE_TABLE ? (size_t)2 * TL * G::F::WORDS * 4 : 0;
   static constexpr size_t STAGE = (size_t)PPB * 2 * G::F::NBYTES;
   static constexpr size_t SMEM = 16 + (TREE > STAGE ? TREE : STAGE);
 };
@@ -291,8 +293,7 @@ __device__ __forceinline__ void block_batch_exp_coop(uint32_t block, const VecBa
                                                      uint32_t* jac_out, uint32_t* status, unsigned char* smem) {
   using F = typename G::F;
   using CO = Coop<F::DEG>;
-  constexpr int PPB = ExpBlock<G>::PPB;
-  static_assert(!G::AFFINE_TABLE || (PPB & (PPB - 1)) == 0, "the product tree needs a power of two of leaves");
+  constexpr int PPB = ExpBlock<G>::PPB, TL = ExpBlock<G>::TL;
   typename ExpTypes<G>::State st;
   const bool lane_ok = CO::lane_active();
   const uint32_t pb = lane_ok ? CO::group_in_block() : 0xffffffffu;
@@ -301,14 +302,18 @@ __device__ __forceinline__ void block_batch_exp_coop(uint32_t block, const VecBa
   typename F::T leaf = exp_stage_a<G>(tid, b, 0, table, check, status, st, staged);
   __syncthreads();
   if constexpr (G::AFFINE_TABLE) {
-    typename F::T* tree = reinterpret_cast<typename F::T*>(smem) + (size_t)(lane_ok ? CO::role() : 0) * 2 * PPB;
-    if (lane_ok) tree[PPB + pb] = leaf;
-    for (int n = PPB / 2; n >= 1; n >>= 1) { __syncthreads(); if (lane_ok) tree_up<F>(tree, n, (int)pb); }
+    typename F::T* tree = reinterpret_cast<typename F::T*>(smem) + (size_t)(lane_ok ? CO::role() : 0) * 2 * TL;
+    if (lane_ok) {
+      tree[TL + pb] = leaf;
+      if (PPB < TL && pb + PPB < (uint32_t)TL) tree[TL + PPB + pb] = F::one();      // padding leaves (TL - PPB <= PPB)
+    }
+    static_assert(TL - PPB <= PPB, "one padding leaf per group at most");
+    for (int n = TL / 2; n >= 1; n >>= 1) { __syncthreads(); if (lane_ok) tree_up<F>(tree, n, (int)pb); }
     __syncthreads();
     if (lane_ok && pb == 0) tree[1] = F::inv(tree[1]);
-    for (int n = 1; n < PPB; n <<= 1) { __syncthreads(); if (lane_ok) tree_down<F>(tree, n, (int)pb); }
+    for (int n = 1; n < TL; n <<= 1) { __syncthreads(); if (lane_ok) tree_down<F>(tree, n, (int)pb); }
     __syncthreads();
-    if (lane_ok) leaf = tree[PPB + pb];
+    if (lane_ok) leaf = tree[TL + pb];
   }
   if (lane_ok) exp_stage_c<G>(tid, b, st, leaf, jac_out);
 }
@@ -337,26 +342,28 @@ __device__ __forceinline__ void block_batch_exp(uint32_t block, const VecBatch& 
 template <class G> struct ExpBlock {
   static constexpr int COOP = G::F::COOP;
   static constexpr int PPB = COOP == 0 ? EXP_BLOCK : (EXP_BLOCK / 32) * (32 / (COOP == 0 ? 1 : COOP));
+  static constexpr int TL = PPB <= 32 ? 32 : PPB <= 64 ? 64 : 128;
 };
 // emulation of the cooperative body: the DEG lanes of a group are DEG lockstep host threads, the groups of a block run in turn
 template <class G>
 inline void block_batch_exp_coop_all(uint32_t block, const VecBatch& b, const uint32_t* table, uint32_t check, uint32_t* jac_out,
                                      uint32_t* status) {
   using F = typename G::F;
-  constexpr int DEG = F::DEG, PPB = ExpBlock<G>::PPB;
+  constexpr int DEG = F::DEG, PPB = ExpBlock<G>::PPB, TL = ExpBlock<G>::TL;
   std::vector<typename ExpTypes<G>::State> st((size_t)PPB * DEG);
-  std::vector<typename F::T> tree((size_t)DEG * 2 * PPB);
+  std::vector<typename F::T> tree((size_t)DEG * 2 * TL);
   uint32_t st_local[DEG][3];
   for (int r = 0; r < DEG; r++) st_local[r][0] = st_local[r][1] = st_local[r][2] = 0;
   coop_emu_run(DEG, [&](int r) {
-    typename F::T* tr = tree.data() + (size_t)r * 2 * PPB;
-    for (int p = 0; p < PPB; p++) tr[PPB + p] = exp_stage_a<G>(block * PPB + p, b, 0, table, check, st_local[r], st[(size_t)p * DEG + r]);
+    typename F::T* tr = tree.data() + (size_t)r * 2 * TL;
+    for (int p = 0; p < PPB; p++) tr[TL + p] = exp_stage_a<G>(block * PPB + p, b, 0, table, check, st_local[r], st[(size_t)p * DEG + r]);
+    for (int p = PPB; p < TL; p++) tr[TL + p] = F::one();
     if constexpr (G::AFFINE_TABLE) {
-      for (int n = PPB / 2; n >= 1; n >>= 1) for (int t = 0; t < n; t++) tree_up<F>(tr, n, t);
+      for (int n = TL / 2; n >= 1; n >>= 1) for (int t = 0; t < n; t++) tree_up<F>(tr, n, t);
       tr[1] = F::inv(tr[1]);
-      for (int n = 1; n < PPB; n <<= 1) for (int t = 0; t < n; t++) tree_down<F>(tr, n, t);
+      for (int n = 1; n < TL; n <<= 1) for (int t = 0; t < n; t++) tree_down<F>(tr, n, t);
     }
-    for (int p = 0; p < PPB; p++) exp_stage_c<G>(block * PPB + p, b, st[(size_t)p * DEG + r], tr[PPB + p], jac_out);
+    for (int p = 0; p < PPB; p++) exp_stage_c<G>(block * PPB + p, b, st[(size_t)p * DEG + r], tr[TL + p], jac_out);
   });
   if (status[0] == 0 && st_local[0][0] != 0) { status[0] = st_local[0][0]; status[1] = st_local[0][1]; status[2] = st_local[0][2]; }
 }

@@ -44,8 +44,33 @@ template <class F> static int field_op(int op, const uint8_t* a, const uint8_t* 
   return rc;
 }
 
+// the same operations on a cooperative extension field (coop.cuh): lane r parses, computes and writes coefficient r
+template <class F> static int field_op_coop(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+  using B = typename F::B;
+  int rcs[3] = {0, 0, 0};
+  coop_emu_run(F::DEG, [&](int role) {
+    typename F::T x, y, r;
+    uint32_t fl;
+    if (!F::from_bytes(a, false, fl, x) || !F::from_bytes(b, false, fl, y)) { rcs[role] = -1; return; }
+    switch (op) {
+      case 0: r = F::mul(x, y); break;
+      case 1: r = F::add(x, y); break;
+      case 2: r = F::sub(x, y); break;
+      case 3: case 6: r = F::sqr(x); break;
+      case 4: r = F::neg(x); break;
+      case 5: r = F::inv(x); break;
+      default: rcs[role] = -2; return;
+    }
+    B::to_bytes(out + (size_t)role * B::NBYTES, r, 0);
+  });
+  return rcs[0];
+}
+
 extern "C" int emul_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
   switch (field) {
+    case 8: return field_op_coop<Bls12_377_G2C::F>(op, a, b, out);
+    case 9: return field_op_coop<Mnt4_753_G2C::F>(op, a, b, out);
+    case 10: return field_op_coop<Mnt6_753_G2C::F>(op, a, b, out);
     case 0: return field_op<Fr253>(op, a, b, out);
     case 1: return field_op<Fq377>(op, a, b, out);
     case 2: return field_op<Fq761>(op, a, b, out);
