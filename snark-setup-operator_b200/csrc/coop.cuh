@@ -129,6 +129,12 @@ template <class B_, int K, bool NEG> struct CFp2 {
   using CO = Coop<2>;
   static constexpr int DEG = 2;
   static constexpr int COOP = 2;
+  // mul_val / sqr_val only ever feed their arguments to base multiplications (through unreduced sums themselves), so the point
+  // formulas may pass unreduced arguments: with coefficients below A p and B p the largest product is 13 A B p^2 (mul) and
+  // 28 A^2 p^2 (sqr) — inside p R for the bounds ec.cuh produces on the 753-bit tower (A <= 29, A B <= 58; R / p = 37054).
+  // A negative non-residue would need p - x of an unreduced x: canonical arguments only.
+  static constexpr bool LAZY_OK = !NEG && B_::SPARE_BITS >= 15;
+  static constexpr bool SQR_CHEAPER = true;            // one multiplication round against two
   static constexpr int L = B::L;
   static constexpr int NBYTES = 2 * B::NBYTES;
   static constexpr int WORDS = 2 * B::L;              // words of a whole element in device arrays
@@ -146,6 +152,9 @@ template <class B_, int K, bool NEG> struct CFp2 {
   __device__ __forceinline__ static T dbl(const T& a) { return B::dbl(a); }
   __device__ __forceinline__ static T neg(const T& a) { return B::neg(a); }
   template <int M> __device__ __forceinline__ static T mul_small(const T& a) { return B::template mul_small<M>(a); }
+  __device__ __forceinline__ static T add_lazy(const T& a, const T& b) { return B::add_lazy(a, b); }
+  __device__ __forceinline__ static T sub_lazy(const T& a, const T& b) { return B::sub_lazy(a, b); }
+  __device__ __forceinline__ static T mad_small_lazy(const T& c, uint32_t k, const T& x) { return B::mad_small_lazy(c, k, x); }
 
   // (a0 + a1 u)(b0 + b1 u), c0 = a0 b0 + nr a1 b1, c1 = a0 b1 + a1 b0: lane r forms a_r (k_r b_r) with k_0 = 1, k_1 = nr — the
   // non-residue rides on an UNREDUCED operand (fp.cuh "lazy operands"), so the multiplication itself reduces nr a1 b1 — and
@@ -210,6 +219,9 @@ template <class B_, int K, bool NEG> struct CFp3 {
   using CO = Coop<3>;
   static constexpr int DEG = 3;
   static constexpr int COOP = 3;
+  // as for CFp2: arguments below A p and B p give products up to 4 A B p^2 (ec.cuh keeps A, B <= 8 here)
+  static constexpr bool LAZY_OK = B_::SPARE_BITS >= 15;
+  static constexpr bool SQR_CHEAPER = false;           // squaring = multiplication
   static constexpr int L = B::L;
   static constexpr int NBYTES = 3 * B::NBYTES;
   static constexpr int WORDS = 3 * B::L;
@@ -227,6 +239,9 @@ template <class B_, int K, bool NEG> struct CFp3 {
   __device__ __forceinline__ static T dbl(const T& a) { return B::dbl(a); }
   __device__ __forceinline__ static T neg(const T& a) { return B::neg(a); }
   template <int M> __device__ __forceinline__ static T mul_small(const T& a) { return B::template mul_small<M>(a); }
+  __device__ __forceinline__ static T add_lazy(const T& a, const T& b) { return B::add_lazy(a, b); }
+  __device__ __forceinline__ static T sub_lazy(const T& a, const T& b) { return B::sub_lazy(a, b); }
+  __device__ __forceinline__ static T mad_small_lazy(const T& c, uint32_t k, const T& x) { return B::mad_small_lazy(c, k, x); }
 
   // Karatsuba with v_r = a_r b_r, s_r = (a_r + a_(r+1))(b_r + b_(r+1)), u_r = s_r - v_r (indices mod 3):
   //   c0 = v0 + nr (u1 - v2)      c1 = (u0 - v1) + nr v2      c2 = (u2 - v0) + v1

@@ -127,9 +127,16 @@ __global__ void __launch_bounds__(128) k_normalize_chunk(const __grid_constant__
 
 // The extension-field groups run their batch_exp bodies warp-cooperatively (coop.cuh: one coefficient per lane) on uncompressed
 // input; SSO_COOP_G2=0 in the environment selects the one-thread-per-element bodies (A/B measurements, tools/).
-inline bool coop_g2_enabled() {
-  static const bool on = [] { const char* e = getenv("SSO_COOP_G2"); return !(e && e[0] == '0'); }();
-  return on;
+// Default per curve (measured on B200, profiles/r2_coop_ab.txt): on for the 753-bit towers, off for BLS12-377 (12-limb
+// coefficients: four base multiplications per Fq2 product instead of Karatsuba's three cost more than the registers gain).
+//   -1 = not set, 0 / 1 = forced
+inline int coop_g2_override() {
+  static const int v = [] { const char* e = getenv("SSO_COOP_G2"); return !e || !e[0] ? -1 : (e[0] == '0' ? 0 : 1); }();
+  return v;
+}
+template <class GC> inline bool coop_g2_enabled() {
+  int o = coop_g2_override();
+  return o < 0 ? GC::COOP_DEFAULT : o != 0;
 }
 
 template <class G1, class G2>
@@ -174,7 +181,7 @@ inline int run_batch_exp_chunk(Ctx& c, int si, const VecBatch& b1, const VecBatc
   using G2C = typename CoopOf<G2>::type;
   bool coop = false;
   if constexpr (!std::is_void<G2C>::value) {
-    if (!in_compressed && coop_g2_enabled()) {
+    if (!in_compressed && coop_g2_enabled<G2C>()) {
       coop = true;
       constexpr size_t SM1 = 16 + 2 * EXP_BLOCK * sizeof(typename G1::F::T);
       constexpr size_t SMEM = SM1 > ExpBlock<G2C>::SMEM ? SM1 : ExpBlock<G2C>::SMEM;
@@ -243,7 +250,7 @@ inline int run_batch_exp(Ctx& c, int si, const VecBatch& batch, uint32_t in_comp
   using GC = typename CoopOf<G>::type;
   bool coop = false;
   if constexpr (!std::is_void<GC>::value) {
-    if (!in_compressed && coop_g2_enabled()) {
+    if (!in_compressed && coop_g2_enabled<GC>()) {
       coop = true;
       if (ExpBlock<GC>::SMEM > 48 * 1024)
         CUDA_TRY(cudaFuncSetAttribute(k_batch_exp<GC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ExpBlock<GC>::SMEM));

@@ -100,6 +100,7 @@ struct Mnt4_753_G1 {
   SSO_GROUP_COMMON(mnt4_753_g1, Fq4, Fq6)
   static constexpr bool A_IS_ZERO = false;
   __device__ __forceinline__ static F::T mul_a(const F::T& x) { return F::dbl(x); }
+  __device__ __forceinline__ static F::T mad_a_lazy(const F::T& c, const F::T& x) { return F::mad_small_lazy(c, 2u, x); }   // c + a x, unreduced
   __device__ __forceinline__ static bool field_sqrt(const F::T& a, F::T& o) { return F::sqrt(a, o); }
 };
 struct Mnt4_753_G2 {
@@ -125,6 +126,7 @@ struct Mnt6_753_G1 {
   SSO_GROUP_COMMON(mnt6_753_g1, Fq6, Fq4)
   static constexpr bool A_IS_ZERO = false;
   __device__ __forceinline__ static F::T mul_a(const F::T& x) { return F::mul_small<11>(x); }
+  __device__ __forceinline__ static F::T mad_a_lazy(const F::T& c, const F::T& x) { return F::mad_small_lazy(c, 11u, x); }
   __device__ __forceinline__ static bool field_sqrt(const F::T& a, F::T& o) { return F::sqrt(a, o); }
 };
 struct Mnt6_753_G2 {
@@ -155,12 +157,15 @@ struct Mnt6_753_G2 {
   __device__ __forceinline__ static typename F::T coeff_b() { return F::from_const(c_##NAME##_b); } \
   __device__ __forceinline__ static bool field_sqrt(const typename F::T&, typename F::T&) { return false; }
 struct Bls12_377_G2C : Bls12_377_G2 {
+  static constexpr bool COOP_DEFAULT = false;          // measured: 28.9 ms per chunk against 27.5 ms (profiles/r2_coop_ab.txt)
   SSO_GROUP_COOP(bls12_377_g2, Bls12_377_G2, CFp2<Fq377, 5, true>)
   __device__ __forceinline__ static F::T mul_a(const F::T&) { return F::zero(); }
 };
 struct Mnt4_753_G2C : Mnt4_753_G2 {
+  static constexpr bool COOP_DEFAULT = true;           // 462 ms per chunk against 515 ms
   SSO_GROUP_COOP(mnt4_753_g2, Mnt4_753_G2, CFp2<Fq4, 13, false>)
   __device__ __forceinline__ static F::T mul_a(const F::T& x) { return F::mul_small<26>(x); }
+  __device__ __forceinline__ static F::T mad_a_lazy(const F::T& c, const F::T& x) { return F::mad_small_lazy(c, 26u, x); }
 };
 #ifndef SSO_MNT6_COOP_AFFINE
 #define SSO_MNT6_COOP_AFFINE 1
@@ -169,8 +174,11 @@ struct Mnt6_753_G2C : Mnt6_753_G2 {
   // three lanes per point: the inversion tree of a block is 64 leaves of one coefficient per lane (37 KB instead of the 72 KB
   // that made the affine table a loss for the one-thread-per-element body), so mixed additions pay here
   static constexpr bool AFFINE_TABLE = SSO_MNT6_COOP_AFFINE != 0;
+  static constexpr bool COOP_DEFAULT = true;           // 759 ms per chunk against 910 ms
   SSO_GROUP_COOP(mnt6_753_g2, Mnt6_753_G2, CFp3<Fq6, 11, false>)
   __device__ __forceinline__ static F::T mul_a(const F::T& x) { return F::mul_small<11>(F::mul_u2(x)); }
+  // the Fq3 products tolerate arguments below 8 p only: a x stays canonical
+  __device__ __forceinline__ static F::T mad_a_lazy(const F::T& c, const F::T& x) { return F::add_lazy(c, mul_a(x)); }
 };
 // the cooperative variant of a group, or void
 template <class G> struct CoopOf { using type = void; };

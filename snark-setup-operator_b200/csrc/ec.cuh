@@ -16,6 +16,14 @@
 #ifndef SSO_POINT_BY_VALUE
 #define SSO_POINT_BY_VALUE 0
 #endif
+// 1: doubling and mixed addition hand UNREDUCED sums (2 Y, 3 X^2, 4 H^2, D - X3 + p ...) to the multiplications instead of
+// reducing every intermediate (fp.cuh "lazy operands"), on the fields that allow it (F::LAZY_OK): 4-6 modular operations per
+// formula instead of 14-18.  Where a squaring only served to avoid a multiplication by a sum ((X + B)^2 - A - C = 2 X B,
+// (Y + Z)^2 - YY - ZZ = 2 Y Z) and the field's squaring is not cheaper than its multiplication (F::SQR_CHEAPER false: the
+// 24-limb prime fields, Fq3), the product is formed directly.
+#ifndef SSO_LAZY_EC
+#define SSO_LAZY_EC 1
+#endif
 
 namespace sso {
 
@@ -59,7 +67,54 @@ template <class Cfg> struct SW {
   __device__ __noinline__ static Jac add_ref(const Jac& p, const Jac& q) { return add_body(p, q); }
   __device__ __forceinline__ static Jac add(const Jac& p, const Jac& q) { if constexpr (BY_VALUE) return add_val(p, q); else return add_ref(p, q); }
 
+  // operation counts with the unreduced operands (M = multiplication, S = squaring of F):
+  //   a = 0:  trading   3 M + 4 S, 4 modular operations     keeping the squarings   2 M + 5 S, 8
+  //   a != 0: trading   3 M + 6 S, 4                        keeping the squarings   1 M + 8 S, 11
+  __device__ __forceinline__ static Jac dbl_lazy_body(const Jac& p) {
+    Jac r;
+    constexpr bool TRADE = !F::SQR_CHEAPER;
+    if constexpr (Cfg::A_IS_ZERO) {
+      FT A = F::sqr(p.X);
+      FT B = F::sqr(p.Y);
+      FT D, C8;                                           // 4 X Y^2, 8 Y^4
+      if constexpr (TRADE) {
+        FT X2 = F::add_lazy(p.X, p.X);
+        D = F::mul(F::add_lazy(X2, X2), B);
+        C8 = F::dbl(F::sqr(F::add_lazy(B, B)));
+      } else {
+        FT C = F::sqr(B);
+        D = F::dbl(F::sub(F::sub(F::sqr(F::add_lazy(p.X, B)), A), C));
+        C8 = F::dbl(F::dbl(F::dbl(C)));
+      }
+      FT E = F::add_lazy(F::add_lazy(A, A), A);           // 3 X^2 < 3 p
+      r.Z = F::mul(F::add_lazy(p.Y, p.Y), p.Z);
+      r.X = F::sub(F::sqr(E), F::dbl(D));
+      r.Y = F::sub(F::mul(E, F::sub_lazy(D, r.X)), C8);
+    } else {
+      FT XX = F::sqr(p.X);
+      FT YY = F::sqr(p.Y);
+      FT ZZ = F::sqr(p.Z);
+      FT S, Y8;                                           // 4 X Y^2, 8 Y^4
+      if constexpr (TRADE) {
+        FT X2 = F::add_lazy(p.X, p.X);
+        S = F::mul(F::add_lazy(X2, X2), YY);
+        r.Z = F::mul(F::add_lazy(p.Y, p.Y), p.Z);
+        Y8 = F::dbl(F::sqr(F::add_lazy(YY, YY)));
+      } else {
+        FT YYYY = F::sqr(YY);
+        S = F::dbl(F::sub(F::sub(F::sqr(F::add_lazy(p.X, YY)), XX), YYYY));
+        r.Z = F::sub(F::sub(F::sqr(F::add_lazy(p.Y, p.Z)), YY), ZZ);
+        Y8 = F::dbl(F::dbl(F::dbl(YYYY)));
+      }
+      FT M = Cfg::mad_a_lazy(F::add_lazy(F::add_lazy(XX, XX), XX), F::sqr(ZZ));      // 3 X^2 + a Z^4, unreduced
+      r.X = F::sub(F::sqr(M), F::dbl(S));
+      r.Y = F::sub(F::mul(M, F::sub_lazy(S, r.X)), Y8);
+    }
+    return r;
+  }
+
   __device__ __forceinline__ static Jac dbl_body(const Jac& p) {
+    if constexpr (SSO_LAZY_EC && F::LAZY_OK) return dbl_lazy_body(p);
     Jac r;
     if (Cfg::A_IS_ZERO) {
       FT A = F::sqr(p.X);
@@ -101,6 +156,22 @@ template <class Cfg> struct SW {
     if (F::is_zero(H)) {
       if (F::is_zero(rr)) return dbl(p);
       return identity();
+    }
+    if constexpr (SSO_LAZY_EC && F::LAZY_OK) {
+      // unreduced 2 r, 4 H^2, V - X3 + p, 2 Y (and 2 Z where the squaring is traded): 6 modular operations instead of 14;
+      // 8 M + 3 S when trading, 7 M + 4 S otherwise
+      FT r2 = F::add_lazy(rr, rr);
+      FT HH = F::sqr(H);
+      FT HH2 = F::add_lazy(HH, HH);
+      FT I = F::add_lazy(HH2, HH2);
+      FT J = F::mul(H, I);
+      FT V = F::mul(p.X, I);
+      Jac r;
+      r.X = F::sub(F::sub(F::sqr(r2), J), F::dbl(V));
+      r.Y = F::sub(F::mul(r2, F::sub_lazy(V, r.X)), F::mul(F::add_lazy(p.Y, p.Y), J));
+      if constexpr (!F::SQR_CHEAPER) r.Z = F::mul(F::add_lazy(p.Z, p.Z), H);
+      else r.Z = F::sub(F::sub(F::sqr(F::add_lazy(p.Z, H)), Z1Z1), HH);
+      return r;
     }
     rr = F::dbl(rr);
     FT HH = F::sqr(H);

@@ -38,6 +38,7 @@ template <class B_, class NR> struct Fp2 {
   using Base = B_;
   static constexpr int DEG = 2;
   static constexpr int COOP = 0;
+  static constexpr bool LAZY_OK = false;              // Karatsuba forms sums of coefficients with modular additions: canonical inputs only
   static constexpr int NBYTES = 2 * B::NBYTES;
   static constexpr int WORDS = 2 * B::L;
   struct T { typename B::T c0, c1; };
@@ -164,6 +165,7 @@ template <class B_, class NR> struct Fp3 {
   using Base = B_;
   static constexpr int DEG = 3;
   static constexpr int COOP = 0;
+  static constexpr bool LAZY_OK = false;
   static constexpr int NBYTES = 3 * B::NBYTES;
   static constexpr int WORDS = 3 * B::L;
   struct T { typename B::T c0, c1, c2; };

@@ -26,6 +26,16 @@
 #define SSO_INLINE_MUL_MAX_L 8
 #endif
 
+// The point formulas use the dedicated squaring up to this many limbs (see Fp::sqr)
+#ifndef SSO_SQR_EC_MAX_L
+#define SSO_SQR_EC_MAX_L 12
+#endif
+// 1: the point formulas trade squarings for multiplications on every prime field (A/B knob; default: only where the field has
+// no dedicated squaring)
+#ifndef SSO_LAZY_TRADE_ALL
+#define SSO_LAZY_TRADE_ALL 0
+#endif
+
 namespace sso {
 
 // ---------------------------------------------------------------------------------------------
@@ -339,10 +349,21 @@ template <class P_> struct Fp {
   // mul_small(): one carry chain instead of up to six.  Only for products of the extension-field formulas (ext.cuh, coop.cuh);
   // every value that leaves them is canonical again.
   static constexpr int SPARE_BITS = 32 * L - P::BITS;
+  // May the point formulas (ec.cuh, SSO_LAZY_EC) hand unreduced sums to mul / sqr of this field?  R / p >= 128 is enough for them.
+  static constexpr bool LAZY_OK = SPARE_BITS >= 7;
+  // in a point formula, is a squaring worth keeping where a multiplication would save modular additions?  (dedicated squaring)
+  static constexpr bool SQR_CHEAPER = L <= SSO_SQR_EC_MAX_L && !SSO_LAZY_TRADE_ALL;
   // a + b as integers (< 2 p)
   __device__ __forceinline__ static T add_lazy(const T& a, const T& b) { T r; limbs_add<L>(r.v, a.v, b.v); return r; }
   // p - a as an integer (a < p; p for a = 0: another representative of 0)
   __device__ __forceinline__ static T neg_lazy(const T& a) { T r; limbs_sub<L>(r.v, P::p(), a.v); return r; }
+  // a - b + p as an integer (a < A p, b <= p: the result is below (A + 1) p and positive)
+  __device__ __forceinline__ static T sub_lazy(const T& a, const T& b) {
+    T n, r;
+    limbs_sub<L>(n.v, P::p(), b.v);
+    limbs_add<L>(r.v, a.v, n.v);
+    return r;
+  }
   // c + k x as integers; the caller guarantees (k + 1) p < R
   __device__ __forceinline__ static T mad_small_lazy(const T& c, uint32_t k, const T& x) {
     uint32_t ev[L], od[L];
