@@ -114,6 +114,7 @@ struct Mnt4_753_G2 {
   SSO_GROUP_COMMON(mnt4_753_g2, Fq4x2, Fq6)
   static constexpr bool A_IS_ZERO = false;
   __device__ __forceinline__ static F::T mul_a(const F::T& x) { return F::mul_small<26>(x); }
+  __device__ __forceinline__ static F::T mad_a_lazy(const F::T& c, const F::T& x) { return F::mad_small_lazy(c, 26u, x); }
   __device__ __forceinline__ static bool field_sqrt(const F::T& a, F::T& o) { return F::sqrt(a, o); }
 };
 struct Mnt6_753_G1 {
@@ -143,6 +144,7 @@ struct Mnt6_753_G2 {
     // x * u^2 = (11 c1, 11 c2, c0), then times 11
     return F::mul_small<11>(F::mul_u2(x));
   }
+  __device__ __forceinline__ static F::T mad_a_lazy(const F::T& c, const F::T& x) { return F::add_lazy(c, mul_a(x)); }   // a x stays canonical
   __device__ __forceinline__ static bool field_sqrt(const F::T& a, F::T& o) {
     return F::sqrt_ts<TS_q6x3>(a, o, c_q6x3_tm1h, c_q6x3_tsz);
   }

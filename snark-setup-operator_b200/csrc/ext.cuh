@@ -21,6 +21,18 @@ template <class B, int K, bool NEG> struct SmallNR {
   __device__ __forceinline__ static typename B::T mad_lazy(const typename B::T& c, const typename B::T& x) {
     return B::mad_small_lazy(c, (uint32_t)K, NEG ? B::neg_lazy(x) : x);
   }
+  // the same for an x below 4 p (point formulas with unreduced sums, ec.cuh SSO_LAZY_EC): a negative non-residue subtracts x
+  // from 4 p; the result stays below c + 4 K p
+  __device__ __forceinline__ static typename B::T mad_lazy_wide(const typename B::T& c, const typename B::T& x) {
+    if constexpr (!NEG) return B::mad_small_lazy(c, (uint32_t)K, x);
+    else {
+      typename B::T p4, n;
+#pragma unroll
+      for (int i = 0; i < B::L; i++) p4.v[i] = (B::P::p()[i] << 2) | (i ? B::P::p()[i - 1] >> 30 : 0u);
+      limbs_sub<B::L>(n.v, p4.v, x.v);
+      return B::mad_small_lazy(c, (uint32_t)K, n);
+    }
+  }
   // c - (nr + 1) x, canonical
   __device__ __forceinline__ static typename B::T sub_nr_plus_one(const typename B::T& c, const typename B::T& x) {
     constexpr int M = NEG ? K - 1 : K + 1;                 // |nr + 1|
@@ -38,7 +50,11 @@ template <class B_, class NR> struct Fp2 {
   using Base = B_;
   static constexpr int DEG = 2;
   static constexpr int COOP = 0;
-  static constexpr bool LAZY_OK = false;              // Karatsuba forms sums of coefficients with modular additions: canonical inputs only
+  // The products below only hand their arguments (and unreduced sums of them) to base multiplications, so the point formulas may
+  // pass coefficients below A p, B p: mul needs 4 A B p < R; sqr (A <= 3) needs 6 (3 + 4 |nr|) p = 138 p < R for u^2 = -5
+  // (R / p = 152.3 on the 377-bit field) and 6 * 42 p for u^2 = 13 (R / p = 37054).
+  static constexpr bool LAZY_OK = B_::SPARE_BITS >= 7;
+  static constexpr bool SQR_CHEAPER = true;           // two base multiplications against three
   static constexpr int NBYTES = 2 * B::NBYTES;
   static constexpr int WORDS = 2 * B::L;
   struct T { typename B::T c0, c1; };
@@ -54,6 +70,11 @@ template <class B_, class NR> struct Fp2 {
   template <int K> __device__ __forceinline__ static T mul_small(const T& a) {
     return T{B::template mul_small<K>(a.c0), B::template mul_small<K>(a.c1)};
   }
+  __device__ __forceinline__ static T add_lazy(const T& a, const T& b) { return T{B::add_lazy(a.c0, b.c0), B::add_lazy(a.c1, b.c1)}; }
+  __device__ __forceinline__ static T sub_lazy(const T& a, const T& b) { return T{B::sub_lazy(a.c0, b.c0), B::sub_lazy(a.c1, b.c1)}; }
+  __device__ __forceinline__ static T mad_small_lazy(const T& c, uint32_t k, const T& x) {
+    return T{B::mad_small_lazy(c.c0, k, x.c0), B::mad_small_lazy(c.c1, k, x.c1)};
+  }
   // out of line, parameters and result by value (registers under the device ABI; see fp.cuh)
 #ifndef SSO_FQ2_INLINE_BASE_MUL
 #define SSO_FQ2_INLINE_BASE_MUL 0
@@ -68,7 +89,11 @@ template <class B_, class NR> struct Fp2 {
   __device__ __noinline__ static T mul_val(T a, T b) {
     typename B::T v0 = bmul(a.c0, b.c0);
     typename B::T v1 = bmul(a.c1, b.c1);
+#ifndef SSO_NO_LAZY_OPERANDS
+    typename B::T s = bmul(B::add_lazy(a.c0, a.c1), B::add_lazy(b.c0, b.c1));
+#else
     typename B::T s = bmul(B::add(a.c0, a.c1), B::add(b.c0, b.c1));
+#endif
     T r;
     r.c0 = B::add(v0, NR::mul(v1));
     r.c1 = B::sub(B::sub(s, v0), v1);
@@ -79,7 +104,7 @@ template <class B_, class NR> struct Fp2 {
     // their product is below p R for every tower here), so forming them costs two carry chains instead of seven modular ops
     typename B::T v = bmul(a.c0, a.c1);
 #ifndef SSO_NO_LAZY_OPERANDS
-    typename B::T pr = bmul(B::add_lazy(a.c0, a.c1), NR::mad_lazy(a.c0, a.c1));
+    typename B::T pr = bmul(B::add_lazy(a.c0, a.c1), NR::mad_lazy_wide(a.c0, a.c1));
     T r;
     r.c0 = NR::sub_nr_plus_one(pr, v);
 #else
@@ -165,7 +190,8 @@ template <class B_, class NR> struct Fp3 {
   using Base = B_;
   static constexpr int DEG = 3;
   static constexpr int COOP = 0;
-  static constexpr bool LAZY_OK = false;
+  static constexpr bool LAZY_OK = B_::SPARE_BITS >= 15;  // coefficients below A p, B p: products up to 4 A B p^2 (ec.cuh keeps A, B <= 8)
+  static constexpr bool SQR_CHEAPER = false;          // squaring = multiplication
   static constexpr int NBYTES = 3 * B::NBYTES;
   static constexpr int WORDS = 3 * B::L;
   struct T { typename B::T c0, c1, c2; };
@@ -181,13 +207,21 @@ template <class B_, class NR> struct Fp3 {
   template <int K> __device__ __forceinline__ static T mul_small(const T& a) {
     return T{B::template mul_small<K>(a.c0), B::template mul_small<K>(a.c1), B::template mul_small<K>(a.c2)};
   }
+  __device__ __forceinline__ static T add_lazy(const T& a, const T& b) { return T{B::add_lazy(a.c0, b.c0), B::add_lazy(a.c1, b.c1), B::add_lazy(a.c2, b.c2)}; }
+  __device__ __forceinline__ static T sub_lazy(const T& a, const T& b) { return T{B::sub_lazy(a.c0, b.c0), B::sub_lazy(a.c1, b.c1), B::sub_lazy(a.c2, b.c2)}; }
   __device__ __noinline__ static T mul(const T& a, const T& b) {
     typename B::T v0 = B::mul(a.c0, b.c0);
     typename B::T v1 = B::mul(a.c1, b.c1);
     typename B::T v2 = B::mul(a.c2, b.c2);
+#ifndef SSO_NO_LAZY_OPERANDS
+    typename B::T t12 = B::mul(B::add_lazy(a.c1, a.c2), B::add_lazy(b.c1, b.c2));
+    typename B::T t01 = B::mul(B::add_lazy(a.c0, a.c1), B::add_lazy(b.c0, b.c1));
+    typename B::T t02 = B::mul(B::add_lazy(a.c0, a.c2), B::add_lazy(b.c0, b.c2));
+#else
     typename B::T t12 = B::mul(B::add(a.c1, a.c2), B::add(b.c1, b.c2));
     typename B::T t01 = B::mul(B::add(a.c0, a.c1), B::add(b.c0, b.c1));
     typename B::T t02 = B::mul(B::add(a.c0, a.c2), B::add(b.c0, b.c2));
+#endif
     T r;
     r.c0 = B::add(v0, NR::mul(B::sub(B::sub(t12, v1), v2)));
     r.c1 = B::add(B::sub(B::sub(t01, v0), v1), NR::mul(v2));
