@@ -88,6 +88,9 @@ def declared_work_per_point(curve: str, group: int):
          2-way psi (MNT4/6 G2)   NW = 95                 two additions per window + the psi-image of the table entry
          4-way psi decomposition (BLS12-377 G2)  NW = 17  four additions per window + (4 + 2 + 2) Fq-muls for psi, psi^2, psi^3
       additions are mixed (madd) with the affine table, full Jacobian additions otherwise.
+    Point formulas with unreduced operands (csrc/ec.cuh SSO_LAZY_EC): where the field's squaring is no cheaper than its
+    multiplication (24-limb prime fields, Fq3) the doubling is 3 M + 4 S (a = 0) / 3 M + 6 S (a != 0) and the mixed addition
+    8 M + 3 S — the same totals as the 2 M + 5 S / 1 M + 8 S / 7 M + 4 S counted below, and there M and S cost the same.
     Base-field cost of an extension operation: Fq2 mul = 3 M, Fq2 sqr = 2 M (complex squaring); Fq3 mul = sqr = 6 M;
     only prime-field squarings use the dedicated squaring (fewer multiply-accumulates, macs_per_fq_sqr).
     The warp-cooperative Fq2 body executes FOUR base multiplications per Fq2 product (two per lane); the declared work keeps

@@ -131,8 +131,8 @@ __global__ void __launch_bounds__(128) k_normalize_chunk(const __grid_constant__
 // coefficients: four base multiplications per Fq2 product instead of Karatsuba's three cost more than the registers gain).
 //   -1 = not set, 0 / 1 = forced
 inline int coop_g2_override() {
-  static const int v = [] { const char* e = getenv("SSO_COOP_G2"); return !e || !e[0] ? -1 : (e[0] == '0' ? 0 : 1); }();
-  return v;
+  const char* e = getenv("SSO_COOP_G2");                // read per call: the parity tests run both bodies in one process
+  return !e || !e[0] ? -1 : (e[0] == '0' ? 0 : 1);
 }
 template <class GC> inline bool coop_g2_enabled() {
   int o = coop_g2_override();

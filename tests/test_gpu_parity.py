@@ -45,6 +45,64 @@ def test_field_mul_bit_exact(fid):
     assert out.raw == want
 
 
+@pytest.mark.parametrize("name", ["bls12_377", "mnt4_753", "mnt6_753"])
+def test_cooperative_and_single_thread_g2_bodies_agree(name, monkeypatch):
+    """csrc/coop.cuh: the G2 batch_exp bodies with two / three lanes per Fq2 / Fq3 element against the one-thread-per-element
+    bodies (SSO_COOP_G2 = 1 / 0 forces either; the default is per curve) and against the oracle: a ragged count that leaves the
+    last group of lanes, the last warp and the last block partly empty, an infinity element, CHECK_FULL on curve points, and a
+    chunk contribution through both."""
+    c = get_curve(name)
+    G = c.g2
+    rnd = random.Random(17 * c.cid)
+    key = synth.contributor_key(c)
+    n = 131                                                  # 64 (Fq2) / 40 (Fq3) points per block: three or four blocks, ragged tail
+    base = [G.mul(G.gen, rnd.randrange(1, G.r)) for _ in range(4)]
+    pts = [base[i % 4] for i in range(n)]
+    pts[77] = None
+    first = (1 << 24) + 7
+    ks = [key.alpha * pow(key.tau, first + j, c.Fr.p) % c.Fr.p for j in range(n)]
+    # the oracle on the points that differ in (point, scalar); every output is checked against the other body bit for bit
+    d_in = dev_bytes(ser.points_to_bytes(G, pts, False))
+    outs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("SSO_COOP_G2", mode)
+        d_out = torch.zeros(n * ser.point_size(G, True), dtype=torch.uint8, device="cuda")
+        sso.batch_exp(name, 1, d_in, n, first, key.tau, key.alpha, d_out)
+        outs[mode] = host_bytes(d_out)
+        with pytest.raises(sso.SsoError) as e:
+            sso.batch_exp(name, 1, d_in, n, first, key.tau, key.alpha, d_out, check=sso.CHECK_NONZERO)
+        assert e.value.code == -3 and "infinity" in e.value.message and "77" in e.value.message
+    assert outs["0"] == outs["1"]
+    sz = ser.point_size(G, True)
+    for j in (0, 1, 63, 64, 76, 77, 78, 119, 120, 130):
+        assert outs["1"][j * sz:(j + 1) * sz] == ser.point_to_bytes(G, G.mul(pts[j], ks[j]) if pts[j] is not None else None, True), j
+    # CHECK_FULL (on-curve test of uncompressed input) accepts, and rejects a point off the curve, in both bodies
+    good = [p for p in pts if p is not None][:70]
+    bad = list(good)
+    bad[41] = (bad[41][0], G.F.add(bad[41][1], G.F.one))
+    for mode in ("0", "1"):
+        monkeypatch.setenv("SSO_COOP_G2", mode)
+        d_out = torch.zeros(70 * sz, dtype=torch.uint8, device="cuda")
+        sso.batch_exp(name, 1, dev_bytes(ser.points_to_bytes(G, good, False)), 70, 0, key.tau, None, d_out, check=sso.CHECK_FULL)
+        with pytest.raises(sso.SsoError) as e:
+            sso.batch_exp(name, 1, dev_bytes(ser.points_to_bytes(G, bad, False)), 70, 0, key.tau, None, d_out, check=sso.CHECK_FULL)
+        assert "41" in e.value.message
+    # a whole chunk contribution (fused G1 + G2 launch) through both bodies
+    from oracle.params import Phase1Params
+    o = Phase1Params.new_chunk(name, 1, 8, 4, 8)
+    p = sso.Phase1Parameters.new_chunk(name, 1, 8, 4, 8)
+    ch = synth.synthetic_challenge(o)
+    resp = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("SSO_COOP_G2", mode)
+        r = bytearray(p.contribution_size)
+        sso.contribute_buf(p, ch, r, key.tau, key.alpha, key.beta, pubkey=bytes(o.public_key_size))
+        resp[mode] = bytes(r)
+    assert resp["0"] == resp["1"]
+    from oracle import phase1
+    assert resp["1"] == phase1.contribute_with_key(o, ch, key, bytes(o.public_key_size))
+
+
 @pytest.mark.parametrize("name", CURVE_NAMES)
 @pytest.mark.parametrize("gi", [0, 1])
 def test_batch_exp_matches_oracle(name, gi):
