@@ -85,15 +85,18 @@ __global__ void __launch_bounds__(128, (G::GROUP == 0 ? SSO_EXP_MIN_BLOCKS_G1 : 
   block_batch_exp<G>(blockIdx.x, batch, in_compressed, table, check, jac_out, status, reinterpret_cast<typename G::F::T*>(tree_raw));
 }
 
+// Every kernel states its resident blocks per SM explicitly: with __launch_bounds__(128) alone ptxas picks the register budget of
+// a kernel's whole call tree by an occupancy heuristic and chose 32 registers for the MNT4-753 G2 bucket / fold / window kernels —
+// the 24-limb multiplication spilled 7.5 KB per call and k_msm_buckets ran 4.5x slower (profiles/r2_verify_kernels_mnt4_753.txt).
 template <class G>
-__global__ void __launch_bounds__(128) k_normalize_write(const __grid_constant__ VecBatch batch, const uint32_t* jac,
+__global__ void __launch_bounds__(128, 1) k_normalize_write(const __grid_constant__ VecBatch batch, const uint32_t* jac,
                                                           uint32_t out_compressed) {
   uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   body_normalize_write<G>(tid, batch, jac, out_compressed);
 }
 
 template <class G>
-__global__ void __launch_bounds__(128) k_reencode(uint32_t n, const uint8_t* in, uint32_t in_compressed, uint8_t* out,
+__global__ void __launch_bounds__(128, 1) k_reencode(uint32_t n, const uint8_t* in, uint32_t in_compressed, uint8_t* out,
                                                    uint32_t out_compressed, uint32_t check, uint32_t subgroup, uint32_t* aff_out,
                                                    uint32_t* status) {
   uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -119,7 +122,7 @@ __global__ void __launch_bounds__(128, SSO_CHUNK_MIN_BLOCKS) k_batch_exp_chunk(c
   }
 }
 template <class G1, class G2>
-__global__ void __launch_bounds__(128) k_normalize_chunk(const __grid_constant__ VecBatch b1, const __grid_constant__ VecBatch b2,
+__global__ void __launch_bounds__(128, 1) k_normalize_chunk(const __grid_constant__ VecBatch b1, const __grid_constant__ VecBatch b2,
                                                           uint32_t nb2, const uint32_t* jac1, const uint32_t* jac2, uint32_t out_compressed) {
   if (blockIdx.x < nb2) body_normalize_write<G2>(blockIdx.x * blockDim.x + threadIdx.x, b2, jac2, out_compressed);
   else body_normalize_write<G1>((blockIdx.x - nb2) * blockDim.x + threadIdx.x, b1, jac1, out_compressed);
@@ -304,25 +307,25 @@ __global__ void k_msm_keys(uint32_t n, uint32_t nwin, uint32_t c, const uint32_t
   body_msm_keys<RLC_WORDS>(blockIdx.x * blockDim.x + threadIdx.x, n, nwin, c, scalars, keys, vals);
 }
 template <class G>
-__global__ void __launch_bounds__(128) k_msm_buckets(uint32_t n, uint32_t nwin, uint32_t c, const uint32_t* keys, const uint32_t* vals,
+__global__ void __launch_bounds__(128, 1) k_msm_buckets(uint32_t n, uint32_t nwin, uint32_t c, const uint32_t* keys, const uint32_t* vals,
                                                       const uint32_t* aff_a, const uint32_t* aff_b, uint32_t* buckets) {
   body_msm_buckets<G>(blockIdx.x * blockDim.x + threadIdx.x, n, nwin, c, keys, vals, aff_a, aff_b, buckets);
 }
 template <class G>
-__global__ void __launch_bounds__(128) k_msm_fold(uint32_t nwin, uint32_t c, const uint32_t* buckets, uint32_t* seg_out) {
+__global__ void __launch_bounds__(128, 1) k_msm_fold(uint32_t nwin, uint32_t c, const uint32_t* buckets, uint32_t* seg_out) {
   body_msm_fold<G>(blockIdx.x * blockDim.x + threadIdx.x, nwin, c, buckets, seg_out);
 }
 template <class G>
-__global__ void __launch_bounds__(128) k_msm_window(uint32_t nwin, uint32_t c, const uint32_t* seg_in, uint32_t* win_out) {
+__global__ void __launch_bounds__(128, 1) k_msm_window(uint32_t nwin, uint32_t c, const uint32_t* seg_in, uint32_t* win_out) {
   body_msm_window<G>(blockIdx.x * blockDim.x + threadIdx.x, nwin, c, seg_in, win_out);
 }
 template <class G>
-__global__ void __launch_bounds__(128) k_msm_final(uint32_t nwin, uint32_t c, const uint32_t* win_in, uint8_t* out) {
+__global__ void __launch_bounds__(128, 1) k_msm_final(uint32_t nwin, uint32_t c, const uint32_t* win_in, uint8_t* out) {
   body_msm_final<G>(blockIdx.x * blockDim.x + threadIdx.x, nwin, c, win_in, out);
 }
 
 template <class G1, class G2, class PP>
-__global__ void __launch_bounds__(64) k_same_ratio(const uint8_t* checks, uint32_t* verdicts) {
+__global__ void __launch_bounds__(64, 1) k_same_ratio(const uint8_t* checks, uint32_t* verdicts) {
   using PR = Pairing<G1, G2, PP>;
   using Fq = typename G1::F;
   __shared__ typename PR::Ws ws[2];
