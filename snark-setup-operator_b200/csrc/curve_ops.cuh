@@ -53,6 +53,9 @@ struct CurveOps {
   int (*fill_generator)(Ctx& c, int si, uint32_t group, uint64_t n, uint8_t* d_out, uint32_t out_compressed, char* err, size_t errcap);
   uint32_t fr_bytes;
   uint32_t aff_words[2];     // words per affine point (x|y) in device arrays, per group
+  // device time of decoding + checking + the power-ratio MSM of one G2 element relative to one G1 element (measured launch
+  // lists, profiles/r2_verify_kernels_*): chunk verification balances its two streams with it
+  float verify_g2_weight;
 };
 
 template <class Fr>
@@ -560,7 +563,7 @@ template <class G1, class G2, class PP> struct CurveImpl {
     return SSO_E_ARG;
   }
   static const CurveOps* ops() {
-    static const CurveOps o = {&tau_tables, &batch_exp, &batch_exp_chunk, &reencode, &msm_pairs, &same_ratio, (uint32_t)Pairing<G1, G2, PP>::CHECK_BYTES, &keygen_g1, &keygen_scalars, &hash_to_g2, (uint32_t)G1::Fr::L, &points_sum, &fill_generator, (uint32_t)G1::Fr::NBYTES, {2u * G1::F::WORDS, 2u * G2::F::WORDS}};
+    static const CurveOps o = {&tau_tables, &batch_exp, &batch_exp_chunk, &reencode, &msm_pairs, &same_ratio, (uint32_t)Pairing<G1, G2, PP>::CHECK_BYTES, &keygen_g1, &keygen_scalars, &hash_to_g2, (uint32_t)G1::Fr::L, &points_sum, &fill_generator, (uint32_t)G1::Fr::NBYTES, {2u * G1::F::WORDS, 2u * G2::F::WORDS}, G2::VERIFY_WEIGHT};
     return &o;
   }
 };

@@ -50,6 +50,7 @@ struct Bls12_377_G1 {
   __device__ __forceinline__ static bool field_sqrt(const F::T& a, F::T& o) { return F::sqrt(a, o); }
 };
 struct Bls12_377_G2 {
+  static constexpr float VERIFY_WEIGHT = 1.6f;            // curve_ops.cuh::CurveOps::verify_g2_weight
   static constexpr bool AFFINE_TABLE = true;
   static constexpr bool HAS_GLV = true;
   using Glv = GLV_bls12_377_g2;
@@ -78,6 +79,7 @@ struct Bw6_761_G1 {
   __device__ __forceinline__ static bool field_sqrt(const F::T& a, F::T& o) { return F::sqrt(a, o); }
 };
 struct Bw6_761_G2 {
+  static constexpr float VERIFY_WEIGHT = 1.5f;            // curve_ops.cuh::CurveOps::verify_g2_weight
   static constexpr bool AFFINE_TABLE = true;
   static constexpr bool HAS_GLV = true;
   using Glv = GLV_bw6_761_g2;
@@ -104,6 +106,7 @@ struct Mnt4_753_G1 {
   __device__ __forceinline__ static bool field_sqrt(const F::T& a, F::T& o) { return F::sqrt(a, o); }
 };
 struct Mnt4_753_G2 {
+  static constexpr float VERIFY_WEIGHT = 10.f;            // curve_ops.cuh::CurveOps::verify_g2_weight
   static constexpr bool AFFINE_TABLE = true;
   static constexpr bool HAS_GLV = false;
   static constexpr int ENDO_SUBGROUP_TEST = 4;          // psi(P) = [t - 1]P  (ec.cuh::in_subgroup)
@@ -131,6 +134,7 @@ struct Mnt6_753_G1 {
   __device__ __forceinline__ static bool field_sqrt(const F::T& a, F::T& o) { return F::sqrt(a, o); }
 };
 struct Mnt6_753_G2 {
+  static constexpr float VERIFY_WEIGHT = 20.f;            // curve_ops.cuh::CurveOps::verify_g2_weight
   static constexpr bool AFFINE_TABLE = false;   // measured: the 72 KB Fq3 inversion tree costs more than mixed additions save
   static constexpr bool HAS_GLV = false;
   static constexpr int ENDO_SUBGROUP_TEST = 4;          // psi(P) = [t - 1]P  (ec.cuh::in_subgroup)

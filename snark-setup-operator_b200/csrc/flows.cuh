@@ -285,9 +285,25 @@ inline int verify_chunk_host(Ctx& c, const CurveOps* ops, const P1Layout& L, uin
     CUDA_TRY(cudaStreamSynchronize(c.s[0]));
     uint32_t* d_aff[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     if ((rc = c.fork(0, 1))) return rc;
+    // the vectors go to the two streams by estimated device time, longest first onto the less loaded stream (on BLS12-377
+    // that is tau_g2 + beta_g1 | tau_g1 + alpha_g1 instead of G2 | all of G1: the few-thread tails of one MSM then overlap
+    // the other stream's work)
+    int stream_of[5] = {0, 0, 0, 0, 0};
+    {
+      double cost[5], load[2] = {0.0, 0.0};
+      int order[5] = {0, 1, 2, 3, 4};
+      for (int v = 0; v < 5; v++) cost[v] = (double)counts[v] * (groups[v] == GROUP_G2 ? (double)ops->verify_g2_weight : 1.0);
+      std::sort(order, order + 5, [&](int a, int b) { return cost[a] > cost[b]; });
+      for (int k = 0; k < 5; k++) {
+        int v = order[k], s = load[1] < load[0] ? 1 : 0;
+        if (c.aliased) s = 0;
+        stream_of[v] = s;
+        load[s] += cost[v];
+      }
+    }
     for (int v = 0; v < 5; v++) {
       if (counts[v] == 0) continue;
-      int si = groups[v] == GROUP_G2 ? 1 : 0;
+      int si = stream_of[v];
       if (ratio_check && v < 4 && counts[v] >= 2)
         if ((rc = c.alloc((void**)&d_aff[v], counts[v] * ops->aff_words[groups[v]] * 4, si))) return rc;
       if ((rc = ops->reencode(c, si, groups[v], d_resp + L.off_c[v], 1, counts[v], d_new + L.off_u[v], 0, elem_check, subgroup,
@@ -298,7 +314,7 @@ inline int verify_chunk_host(Ctx& c, const CurveOps* ops, const P1Layout& L, uin
     uint8_t* d_pairs[4] = {nullptr, nullptr, nullptr, nullptr};
     for (int v = 0; v < 4; v++) {
       if (!d_aff[v]) continue;
-      int si = groups[v] == GROUP_G2 ? 1 : 0;
+      int si = stream_of[v];
       size_t usz = groups[v] == GROUP_G1 ? g1u : g2u;
       const uint64_t tweak[4] = {TWEAK_P1_VERIFY | (uint64_t)v, chunk_index, 0, 0};
       if ((rc = c.alloc((void**)&d_pairs[v], 2 * usz, si))) return rc;
