@@ -150,7 +150,11 @@ struct Mnt6_753_G2 {
   }
   __device__ __forceinline__ static F::T mad_a_lazy(const F::T& c, const F::T& x) { return F::add_lazy(c, mul_a(x)); }   // a x stays canonical
   __device__ __forceinline__ static bool field_sqrt(const F::T& a, F::T& o) {
+#ifdef SSO_FQ3_SQRT_PLAIN
     return F::sqrt_ts<TS_q6x3>(a, o, c_q6x3_tm1h, c_q6x3_tsz);
+#else
+    return F::sqrt_ts_norm<TS_q6x3>(a, o, c_q6x3_tsz, ENDO_mnt6_753::w1(), ENDO_mnt6_753::w2());
+#endif
   }
 };
 

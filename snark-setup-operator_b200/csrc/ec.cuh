@@ -578,12 +578,70 @@ template <class Cfg> struct SW {
     return acc;
   }
 
-  // plain MSB-first double-and-add for a constant-memory exponent (subgroup checks, cofactors)
+  // [e]P for a constant-memory exponent (membership tests, cofactor clearing): MSB-first double-and-add for sparse exponents
+  // (the BLS12 / BW6 curve parameter: a handful of additions), a width-4 NAF for the dense ones — digits odd in [-7, 7], one
+  // full addition per five doublings on average instead of one mixed addition per two (377-bit ladder over Fq2: 3.3 k
+  // instead of 5.5 k base multiplications in additions), Jacobian table P, 3P, 5P, 7P.  The recoding runs per thread on the raw
+  // words: a few hundred integer operations against ~10^4 field multiplications.
+  static constexpr int NAF_MAX_WORDS = 48;
+#ifndef SSO_NO_NAF
+#define SSO_NO_NAF 0
+#endif
   __device__ __noinline__ static Jac mul_const(const Affine& base, const uint32_t* e, int nwords) {
+    int weight = 0, bitlen = 0;
+    for (int i = 0; i < nwords; i++) {
+      weight += __popc(e[i]);
+      if (e[i]) bitlen = 32 * i + 32 - __clz(e[i]);
+    }
+    // a full addition costs ~1.46 mixed additions: the NAF pays when weight > 0.29 bits (+ its table)
+    if (SSO_NO_NAF || nwords > NAF_MAX_WORDS || weight * 100 <= 30 * bitlen + 500 || base.inf) {
+      Jac acc = identity();
+      for (int i = nwords * 32 - 1; i >= 0; i--) {
+        acc = dbl(acc);
+        if ((e[i >> 5] >> (i & 31)) & 1) acc = madd(acc, base);
+      }
+      return acc;
+    }
+    uint32_t k[NAF_MAX_WORDS + 1];
+    for (int i = 0; i <= NAF_MAX_WORDS; i++) k[i] = i < nwords ? e[i] : 0u;
+    signed char dig[32 * NAF_MAX_WORDS + 2];
+    int nd = 0, top = nwords;                           // words [0, top] may be non-zero
+    for (;;) {
+      while (top > 0 && k[top] == 0) top--;
+      if (top == 0 && k[0] == 0) break;
+      int d = 0;
+      if (k[0] & 1u) {
+        d = (int)(k[0] & 15u);
+        if (d >= 8) d -= 16;
+        // k -= d
+        if (d > 0) {
+          uint32_t b = (uint32_t)d;
+          for (int i = 0; i <= top && b; i++) { uint32_t o = k[i]; k[i] = o - b; b = o < b ? 1u : 0u; }
+        } else {
+          uint32_t cy = (uint32_t)(-d);
+          for (int i = 0; i <= top + 1 && i <= NAF_MAX_WORDS && cy; i++) { uint32_t o = k[i]; k[i] = o + cy; cy = k[i] < o ? 1u : 0u; }
+          if (top < NAF_MAX_WORDS && k[top + 1]) top++;
+        }
+      }
+      dig[nd++] = (signed char)d;
+      for (int i = 0; i < top; i++) k[i] = (k[i] >> 1) | (k[i + 1] << 31);
+      k[top] >>= 1;
+    }
+    Jac tab[4];
+    tab[0] = Jac{base.x, base.y, F::one()};
+    Jac two = dbl(tab[0]);
+    tab[1] = madd(two, base);
+    tab[2] = add(tab[1], two);
+    tab[3] = add(tab[2], two);
     Jac acc = identity();
-    for (int i = nwords * 32 - 1; i >= 0; i--) {
+    for (int i = nd - 1; i >= 0; i--) {
       acc = dbl(acc);
-      if ((e[i >> 5] >> (i & 31)) & 1) acc = madd(acc, base);
+      int d = dig[i];
+      if (d != 0) {
+        Jac q = tab[(d < 0 ? -d : d) >> 1];
+        if (d < 0) q.Y = F::neg(q.Y);
+        acc = add(acc, q);
+      }
     }
     return acc;
   }

@@ -76,6 +76,8 @@ static inline uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return e
 static inline uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return emu_add(mul_hi(a, b), c, g_cf, true); }
 static inline uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return emu_add(mul_hi(a, b), c, g_cf, false); }
 static inline uint32_t shl1_from(uint32_t lo, uint32_t hi) { return (hi << 1) | (lo >> 31); }
+static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
+static inline int __clz(uint32_t x) { return x ? __builtin_clz(x) : 32; }
 #endif
 
 // ---------------------------------------------------------------------------------------------
