@@ -98,6 +98,13 @@ __global__ void __launch_bounds__(128, 1) k_normalize_write(const __grid_constan
   body_normalize_write<G>(tid, batch, jac, out_compressed);
 }
 
+template <class GC>
+__global__ void __launch_bounds__(128, 1) k_subgroup_coop(uint32_t n, const uint32_t* aff, const uint8_t* pts, uint32_t* status) {
+  using CO = Coop<GC::F::DEG>;
+  if (!CO::lane_active()) return;
+  body_subgroup_coop<GC>(blockIdx.x * ExpBlock<GC>::PPB + CO::group_in_block(), n, aff, pts, status);
+}
+
 template <class G>
 __global__ void __launch_bounds__(128, 1) k_reencode(uint32_t n, const uint8_t* in, uint32_t in_compressed, uint8_t* out,
                                                    uint32_t out_compressed, uint32_t check, uint32_t subgroup, uint32_t* aff_out,
@@ -484,8 +491,19 @@ inline int run_reencode(Ctx& c, int si, const uint8_t* d_in, uint32_t in_compres
   if (n == 0) return SSO_OK;
   if (n > 0xffffffffull) { set_err(err, errcap, "vector too long"); return SSO_E_ARG; }
   constexpr bool IS_G1 = G::GROUP == 0;
+  // the membership test of the 753-bit extension-field groups runs through the cooperative fields (2 / 3 lanes per point) in a
+  // second kernel over the decoded points; SSO_COOP_G2 = 0 keeps it inside the decoding kernel
+  using GC = typename CoopOf<G>::type;
+  bool coop = false;
+  if constexpr (!std::is_void<GC>::value) {
+    if constexpr (GC::ENDO_SUBGROUP_TEST == 4)
+      coop = subgroup && (d_aff || (d_out && !out_compressed)) && coop_g2_enabled<GC>();
+  }
   c.begin(IS_G1 ? PK_REENCODE_G1 : PK_REENCODE_G2, si, n);
-  k_reencode<G><<<div_up(n, 128), 128, 0, c.s[si]>>>((uint32_t)n, d_in, in_compressed, d_out, out_compressed, check, subgroup, d_aff, d_status);
+  k_reencode<G><<<div_up(n, 128), 128, 0, c.s[si]>>>((uint32_t)n, d_in, in_compressed, d_out, out_compressed, check, coop ? 2u : subgroup, d_aff, d_status);
+  if constexpr (!std::is_void<GC>::value) {
+    if (coop) k_subgroup_coop<GC><<<div_up(n, ExpBlock<GC>::PPB), 128, 0, c.s[si]>>>((uint32_t)n, d_aff, d_aff ? nullptr : d_out, d_status);
+  }
   c.end(si);
   CUDA_TRY(cudaGetLastError());
   return SSO_OK;

@@ -460,8 +460,9 @@ __device__ __forceinline__ void body_reencode(uint32_t tid, uint32_t n, const ui
     // CheckForCorrectness and SubgroupCheckMode are independent knobs of the reference (src/bin/contribute.rs:971-984):
     // `check` decides non-zero / on-curve, `subgroup` decides the membership test.  A decompressed point is on the curve by
     // construction; an uncompressed one is checked whenever the membership test (which assumes a curve point) follows.
+    // subgroup == 2: the membership test runs in the cooperative kernel that follows (body_subgroup_coop)
     if (!in_compressed && (check == CHECK_FULL || subgroup) && !C::on_curve(p)) report(status, ST_NOT_ON_CURVE, tid);
-    else if (subgroup && !C::in_subgroup(p)) report(status, ST_NOT_IN_SUBGROUP, tid);
+    else if (subgroup == 1 && !C::in_subgroup(p)) report(status, ST_NOT_IN_SUBGROUP, tid);
   }
   if (out) {
     if (out_compressed) C::write_compressed(out + (size_t)tid * C::SIZE_C, p);
@@ -472,6 +473,30 @@ __device__ __forceinline__ void body_reencode(uint32_t tid, uint32_t n, const ui
     F::store(o, 1, p.inf ? F::zero() : p.x);
     F::store(o + F::WORDS, 1, p.inf ? F::zero() : p.y);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3b: the membership test of decoded points through the warp-cooperative fields (coop.cuh): DEG lanes per point, the same
+// SW::in_subgroup template.  Points come from the array the decoding kernel left: affine Montgomery words ([point][x|y], all-zero
+// = infinity) when `aff` is given, else the uncompressed serialisation.  Points the decoding kernel rejected were reported
+// there (first report wins); infinity is skipped.
+// ---------------------------------------------------------------------------------------------
+template <class GC>
+__device__ __forceinline__ void body_subgroup_coop(uint32_t point, uint32_t n, const uint32_t* aff, const uint8_t* pts, uint32_t* status) {
+  using C = SW<GC>;
+  using F = typename GC::F;
+  if (point >= n) return;
+  typename C::Affine p;
+  if (aff) {
+    const uint32_t* a = aff + (size_t)point * 2 * F::WORDS;
+    p.x = F::load(a, 1);
+    p.y = F::load(a + F::WORDS, 1);
+    p.inf = F::is_zero(p.x) && F::is_zero(p.y);
+  } else {
+    if (C::read_uncompressed(pts + (size_t)point * C::SIZE_U, p) != C::DESER_OK) return;
+  }
+  if (p.inf) return;
+  if (!C::in_subgroup(p)) report(status, ST_NOT_IN_SUBGROUP, point);
 }
 
 }  // namespace sso

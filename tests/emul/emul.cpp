@@ -189,14 +189,49 @@ extern "C" int emul_batch_exp2(uint32_t curve, uint32_t group, const uint8_t* in
   });
 }
 
+// The G2 membership test of the 753-bit towers has two implementations — inside body_reencode (one thread per element) and in the
+// cooperative kernel that follows it (body_subgroup_coop, lanes emulated by lockstep threads).  Both are run; rc = -7 if their
+// reports differ.
 extern "C" int emul_reencode(uint32_t curve, uint32_t group, const uint8_t* in, uint32_t in_compressed, uint32_t n,
                              uint8_t* out, uint32_t out_compressed, uint32_t check, uint32_t subgroup, uint32_t* status) {
   status[0] = status[1] = status[2] = 0;
-  return dispatch_group(curve, group, [&](auto g) {
+  int mismatch = 0;
+  int rc = dispatch_group(curve, group, [&](auto g) {
     using G = decltype(g);
+    using F = typename G::F;
     for (uint32_t t = 0; t < n; t++)
       body_reencode<G>(t, n, in, in_compressed, out, out_compressed, check, subgroup, nullptr, status);
+    using GC = typename CoopOf<G>::type;
+    if constexpr (!std::is_void<GC>::value) {
+      if constexpr (GC::ENDO_SUBGROUP_TEST == 4) {
+        if (subgroup) {
+          uint32_t st2[3] = {0, 0, 0};
+          std::vector<uint32_t> aff((size_t)n * 2 * F::WORDS);
+          for (uint32_t t = 0; t < n; t++)
+            body_reencode<G>(t, n, in, in_compressed, nullptr, 0, check, 2, aff.data(), st2);
+          uint32_t stl[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+          coop_emu_run(GC::F::DEG, [&](int r) {
+            for (uint32_t t = 0; t < n; t++) body_subgroup_coop<GC>(t, n, aff.data(), nullptr, stl[r]);
+          });
+          if (st2[0] == 0 && stl[0][0] != 0) { st2[0] = stl[0][0]; st2[1] = stl[0][1]; }
+          // the same through the uncompressed serialisation, when there is one
+          uint32_t st3[3] = {st2[0], st2[1], 0};
+          if (out && !out_compressed) {
+            uint32_t stm[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+            coop_emu_run(GC::F::DEG, [&](int r) {
+              for (uint32_t t = 0; t < n; t++) body_subgroup_coop<GC>(t, n, nullptr, out, stm[r]);
+            });
+            uint32_t st4[3] = {0, 0, 0};
+            for (uint32_t t = 0; t < n; t++) body_reencode<G>(t, n, in, in_compressed, nullptr, 0, check, 2, nullptr, st4);
+            if (st4[0] == 0 && stm[0][0] != 0) { st4[0] = stm[0][0]; st4[1] = stm[0][1]; }
+            st3[0] = st4[0]; st3[1] = st4[1];
+          }
+          if (st2[0] != status[0] || st2[1] != status[1] || st3[0] != status[0] || st3[1] != status[1]) mismatch = 1;
+        }
+      }
+    }
   });
+  return mismatch ? -7 : rc;
 }
 
 // power_pairs on n serialized points with ChaCha20(seed) scalars; the CUB sort is replaced by std::sort.
