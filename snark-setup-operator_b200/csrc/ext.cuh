@@ -51,8 +51,9 @@ template <class B_, class NR> struct Fp2 {
   static constexpr int DEG = 2;
   static constexpr int COOP = 0;
   // The products below only hand their arguments (and unreduced sums of them) to base multiplications, so the point formulas may
-  // pass coefficients below A p, B p: mul needs 4 A B p < R; sqr (A <= 3) needs 6 (3 + 4 |nr|) p = 138 p < R for u^2 = -5
-  // (R / p = 152.3 on the 377-bit field) and 6 * 42 p for u^2 = 13 (R / p = 37054).
+  // pass coefficients below A p, B p.  mul needs 4 A B p < R.  sqr forms (a0 + a1)(a0 + nr a1): for u^2 = -5 (BLS12-377,
+  // R / p = 152.3) the subtrahend is taken from 4 p, so A <= 3 (the largest ec.cuh produces there: 3 X^2) gives
+  // 6 p * (3 + 5 * 4) p = 138 p^2; for u^2 = 13 (MNT4-753, R / p = 37054) A <= 29 (3 X^2 + 26 Z^4) gives 58 p * 406 p = 23548 p^2.
   static constexpr bool LAZY_OK = B_::SPARE_BITS >= 7;
   static constexpr bool SQR_CHEAPER = true;           // two base multiplications against three
   static constexpr int NBYTES = 2 * B::NBYTES;
