@@ -83,6 +83,32 @@ extern "C" int emul_field_op(int field, int op, const uint8_t* a, const uint8_t*
   return -3;
 }
 
+// Raw-limb probes of the unreduced-operand machinery (fp.cuh "lazy operands"): operands are little-endian words that need not be
+// below p.  op 0: out = mont_mul(a, b) (= a b R^-1 mod p, canonical when a b < p R); op 1: out = reduce_small(a) (a < 16 p);
+// op 2: out = mad_small_lazy(a, k, b) = a + k b as integers; op 3: out = mont_sqr(a) (dedicated squaring).
+template <class F> static int lazy_probe(int op, const uint32_t* a, const uint32_t* b, uint32_t k, uint32_t* out) {
+  typename F::T x, y, r;
+  for (int i = 0; i < F::L; i++) { x.v[i] = a[i]; y.v[i] = b[i]; }
+  switch (op) {
+    case 0: r = F::mul(x, y); break;
+    case 1: r = F::reduce_small(x); break;
+    case 2: r = F::mad_small_lazy(x, k, y); break;
+    case 3: r = F::sqr_dedicated(x); break;
+    default: return -2;
+  }
+  for (int i = 0; i < F::L; i++) out[i] = r.v[i];
+  return 0;
+}
+extern "C" int emul_lazy_probe(int field, int op, const uint32_t* a, const uint32_t* b, uint32_t k, uint32_t* out) {
+  switch (field) {
+    case 1: return lazy_probe<Fq377>(op, a, b, k, out);
+    case 2: return lazy_probe<Fq761>(op, a, b, k, out);
+    case 3: return lazy_probe<Fq4>(op, a, b, k, out);
+    case 4: return lazy_probe<Fq6>(op, a, b, k, out);
+  }
+  return -3;
+}
+
 // out = some sqrt of a (rc 1) or rc 0 if non-square; field ids as above but via the group configs
 template <class G> static int group_sqrt(const uint8_t* a, uint8_t* out) {
   using F = typename G::F;

@@ -402,3 +402,55 @@ def test_cooperative_g2_bodies(emul, name):
     assert list(st)[:2] == [3, 1]                            # ST_NOT_ON_CURVE at element 1
     # compressed input is not taken by the cooperative bodies (the host selects the other kernel)
     assert emul.emul_batch_exp(c.cid, 2, want, 1, n, words(1, Lr), words(key.beta, Lr), ctypes.c_uint64(0), 1, 0, out2, 0, st) == -2
+
+
+@pytest.mark.parametrize("fid", [1, 2, 3, 4])
+def test_unreduced_operands_at_their_bounds(emul, fid):
+    """fp.cuh "lazy operands": mont_mul returns the canonical a b R^-1 mod p for operands below A p and B p whenever A B p <= R,
+    the dedicated squaring for A^2 p <= R, reduce_small for any y < 16 p, mad_small_lazy is the integer c + k x.  Probed at the
+    LARGEST magnitudes the extension-field products and the point formulas produce: operands of the form
+    (A - 1) p + (p - 1), all-ones limb patterns below the bound, and random ones."""
+    F = _field(fid)
+    p = F.p
+    L = (F.bits + 31) // 32
+    R = 1 << (32 * L)
+    Rinv = pow(R, -1, p)
+    rnd = random.Random(100 + fid)
+    ratio = R // p                                            # 152 (377 bits), 225 (761), 37054 (753)
+
+    def arr(v):
+        assert 0 <= v < R
+        return (ctypes.c_uint32 * L)(*[(v >> (32 * i)) & 0xFFFFFFFF for i in range(L)])
+
+    def val(a):
+        return sum(int(a[i]) << (32 * i) for i in range(L))
+
+    out = (ctypes.c_uint32 * L)()
+    # (A, B) pairs used by the code, largest products first: Fq2 squaring on BLS12-377 (6 p, 23 p), cooperative / plain MNT4
+    # squaring (58 p, 406 p), MNT6 G1 doubling (14 p, 14 p), point formulas (3 p, 3 p), (4 p, 2 p), ...
+    pairs = {152: [(6, 23), (4, 6), (3, 3), (2, 12)], 225: [(3, 3), (4, 4), (4, 2), (15, 15)],
+             37054: [(58, 406), (29, 754 // 29), (14, 14), (125, 2), (192, 192)]}[ratio]
+    for A, B in pairs:
+        assert A * B <= ratio
+        cases = [(A * p - 1, B * p - 1), ((A - 1) * p + rnd.randrange(p), (B - 1) * p + rnd.randrange(p)), (A * p - 1, 1), (0, B * p - 1)]
+        cases += [(min(A * p - 1, (1 << (A * p).bit_length() - 1) - 1), min(B * p - 1, (1 << (B * p).bit_length() - 1) - 1))]
+        for a, b in cases:
+            assert emul.emul_lazy_probe(fid, 0, arr(a), arr(b), 0, out) == 0
+            assert val(out) == a * b * Rinv % p, (fid, A, B)
+    # dedicated squaring (12-limb fields use it in the point formulas): arguments up to 3 p (3 X^2) and 4 p
+    if L <= 12:
+        for A in (2, 3, 4):
+            for a in (A * p - 1, (A - 1) * p + rnd.randrange(p)):
+                assert emul.emul_lazy_probe(fid, 3, arr(a), arr(0), 0, out) == 0
+                assert val(out) == a * a * Rinv % p
+    # reduce_small over [0, 16 p)
+    for y in [0, p - 1, p, p + 1, 2 * p - 1, 8 * p - 1, 15 * p + (p - 1), 16 * p - 1] + [rnd.randrange(16 * p) for _ in range(20)]:
+        assert emul.emul_lazy_probe(fid, 1, arr(y), arr(0), 0, out) == 0
+        assert val(out) == y % p, hex(y)
+    # mad_small_lazy: c + k x as integers
+    for k in (0, 1, 5, 13, 14, 26):
+        for c, x in ((p - 1, p - 1), (rnd.randrange(3 * p), rnd.randrange(p)), (0, p - 1)):
+            if c + k * x >= R:
+                continue
+            assert emul.emul_lazy_probe(fid, 2, arr(c), arr(x), k, out) == 0
+            assert val(out) == c + k * x
